@@ -1,0 +1,137 @@
+/* kbner_b200 -- C ABI of the B200-native KB-NER token-classification hot path.
+ *
+ * The reference (Alibaba-NLP/KB-NER, a flair-0.4.3 fork) is 100 % Python and has
+ * no FFI of its own; its "plugin API" is the Python class contract
+ *   flair.embeddings.TransformerWordEmbeddings   (flair/embeddings.py:2906-3416)
+ *   flair.models.SequenceTagger / FastSequenceTagger
+ *                                               (flair/models/sequence_tagger_model.py:99,1823)
+ * This header is the C boundary the replacement classes (kb-ner_b200/*.py) bind with
+ * ctypes -- one entry point per device-op of the path.
+ * Each declaration cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are stream-ordered,
+ *     allocate nothing, and return 0 on success or a negative KBNER_E* code;
+ *   - bf16 tensors are raw uint16_t storage (__nv_bfloat16 bit patterns);
+ *   - matrices are row-major; Linear weights are [out_features, in_features]
+ *     exactly as torch.nn.Linear stores them;
+ *   - transitions are trans[to][from] (sequence_tagger_model.py:402-410).
+ */
+#ifndef KBNER_B200_H_
+#define KBNER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBNER_OK            0
+#define KBNER_EINVAL       -1   /* bad argument (shape / alignment / range)         */
+#define KBNER_ECUDA        -2   /* a CUDA runtime / driver call failed              */
+#define KBNER_EUNSUPPORTED -3   /* shape outside what the kernels are built for     */
+#define KBNER_ENODEVICE    -4   /* no sm_100 device                                  */
+
+/* ---- library ----------------------------------------------------------------------- */
+/* ABI version of this header (bumped on any signature change). */
+int kbner_abi_version(void);
+/* Human-readable text of the last error on this thread (never NULL). */
+const char *kbner_last_error(void);
+/* 0 if device `dev` is an sm_100 part the kernels can run on. */
+int kbner_device_check(int dev);
+/* Number of kernels launched by this library since load (the bench's gpu_launches). */
+uint64_t kbner_launch_count(void);
+
+/* ---- CRF ---------------------------------------------------------------------------- */
+/* remove-X compaction: pos[b][i] = original index of the i-th kept token, klen[b] = #kept,
+ * pos[b][i>=klen] = -1.  Replaces the per-sentence masked_select loop,
+ * sequence_tagger_model.py:2474-2488 and :1198-1200. */
+int kbner_crf_compact(const uint8_t *keep /*[B,T]*/, int B, int T,
+                      int32_t *pos /*[B,T]*/, int32_t *klen /*[B]*/, void *stream);
+
+/* Viterbi decode + per-step confidence + S-X padding.
+ * Replaces SequenceTagger._viterbi_decode (:1248-1304) as driven by _obtain_labels
+ * (:1193-1210).  pos may be NULL (kept tokens are 0..klen-1).  tags_out/conf_out are
+ * [B,T]: kept positions get the decoded tag / confidence, other positions < slen[b]
+ * get x_idx / 1.0, positions >= slen[b] get -1 / 0.  Bit-exact tag indices. L <= 32. */
+int kbner_crf_viterbi(const float *emis /*[B,T,L]*/, const int32_t *pos /*[B,T] or NULL*/,
+                      const int32_t *klen /*[B]*/, const int32_t *slen /*[B]*/,
+                      const float *trans /*[L,L]*/, int B, int T, int L,
+                      int start_idx, int stop_idx, int x_idx,
+                      int32_t *tags_out /*[B,T]*/, float *conf_out /*[B,T]*/, void *stream);
+
+/* log-partition + gold-path score of every sentence.
+ * Replaces _forward_alg (:1329-1394) and FastSequenceTagger._score_sentence (:2544-2591).
+ * alpha (optional, [B,T,L], compacted time index) is what crf_nll_bwd consumes. */
+int kbner_crf_nll_fwd(const float *emis /*[B,T,L]*/, const int32_t *tags /*[B,T]*/,
+                      const int32_t *pos /*[B,T] or NULL*/, const int32_t *klen /*[B]*/,
+                      const float *trans /*[L,L]*/, int B, int T, int L,
+                      int start_idx, int stop_idx,
+                      float *logz /*[B]*/, float *gold /*[B]*/, float *alpha /*[B,T,L] or NULL*/,
+                      void *stream);
+
+/* Gradient of sum_b w[b]*(logZ_b - gold_b): what autograd derives from the two functions
+ * above (loss = mean, :2499-2506, means w[b] = 1/B).  d_emis is fully written (zeros at
+ * un-kept positions); d_trans is ACCUMULATED into (caller zeroes it). */
+int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const int32_t *pos,
+                      const int32_t *klen, const float *trans, const float *alpha,
+                      const float *logz, const float *w /*[B]*/, int B, int T, int L,
+                      int start_idx, int stop_idx,
+                      float *d_emis /*[B,T,L]*/, float *d_trans /*[L,L]*/, void *stream);
+
+/* ---- encoder: HBM-bound kernels ------------------------------------------------------ */
+/* word_emb[ids] + pos_emb[position] + type_emb[0] -> LayerNorm -> bf16.
+ * position = cumsum(ids != pad_id) * (ids != pad_id) + pad_id, computed in-kernel
+ * (HF XLMRobertaEmbeddings as called from flair/embeddings.py:3269).
+ * One row of `ids` is one window of S sub-tokens. */
+int kbner_embed_ln_fwd(const int32_t *ids /*[R,S]*/, const float *word_emb /*[V,H] fp32 master*/,
+                       const float *pos_emb /*[P,H] fp32*/, const float *type_emb /*[H] fp32*/,
+                       const float *gamma, const float *beta, float eps, int pad_id,
+                       int R, int S, int H, int V, int P,
+                       uint16_t *out /*[R*S,H] bf16*/, void *stream);
+
+/* y = LayerNorm(x) * gamma + beta, x fp32 (the GEMM epilogue already added bias + residual),
+ * y bf16; optionally saves mean / rstd (fp32 [M]) for the backward pass.  SURVEY E4/E6. */
+int kbner_layernorm_fwd(const float *x /*[M,H]*/, const float *gamma, const float *beta, float eps,
+                        int M, int H, uint16_t *y /*[M,H] bf16*/,
+                        float *mean /*[M] or NULL*/, float *rstd /*[M] or NULL*/, void *stream);
+
+/* First-sub-token pooling + word dropout + tag projection in one pass:
+ * logits[b,t,:] = keep_t * hidden[row(b), first_idx[b,t], :] . W^T + bias
+ * first_idx[b,t] = sub-token index inside the window row (or -1 => zero vector, i.e. bias only).
+ * Replaces the pooling loop flair/embeddings.py:3288-3345, assign_batch_features :108-124,
+ * WordDropout flair/nn.py:176-183 and self.linear sequence_tagger_model.py:1027.
+ * drop_keep (optional, [T] u8) is the (T,1,1) word-dropout mask shared across the batch. */
+int kbner_gather_tagproj_fwd(const uint16_t *hidden /*[R*S,H] bf16*/, const int32_t *row_of /*[B]*/,
+                             const int32_t *first_idx /*[B,T]*/, const uint8_t *drop_keep /*[T] or NULL*/,
+                             const float *W /*[L,H] fp32*/, const float *bias /*[L]*/,
+                             int B, int T, int S, int H, int L,
+                             float *logits /*[B,T,L]*/, void *stream);
+
+/* ---- encoder: tensor-core kernels (tcgen05 + TMEM + TMA) ------------------------------ */
+#define KBNER_EPI_BIAS            0  /* C(bf16)  = A.B^T + bias                         (QKV)          */
+#define KBNER_EPI_BIAS_GELU       1  /* C(bf16)  = gelu_erf(A.B^T + bias)               (FFN up)       */
+#define KBNER_EPI_BIAS_RESID_F32  2  /* C(fp32)  = A.B^T + bias + residual(bf16)        (attn-out, FFN down; LN follows) */
+#define KBNER_EPI_NONE_F32        3  /* C(fp32)  = A.B^T                                (tests / wgrad) */
+
+/* C[M,N] = epilogue(A[M,K] . B[N,K]^T): both operands K-major bf16 ("TN" GEMM, the layout of
+ * torch.nn.Linear).  M, N, K arbitrary multiples of 8 (TMA handles ragged tile edges);
+ * lda/ldb/ldc in elements.  SURVEY E2/E4/E5/E6. */
+int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias /*[N] or NULL*/,
+                       const uint16_t *residual /*[M,N] bf16 or NULL*/, void *C,
+                       int M, int N, int K, int lda, int ldb, int ldc, int epilogue, void *stream);
+
+/* softmax(Q.K^T / sqrt(d) + key-padding mask) . V for every (window, head); flash-style, never
+ * materialises the [S,S] scores.  qkv is the fused projection output [R*S, 3*H] bf16 (Q | K | V,
+ * each H = heads*64 wide); key_len[r] = number of valid sub-tokens of window r (keys beyond it
+ * are masked exactly as HF's additive -inf mask does).  out [R*S, H] bf16.  d = 64.  SURVEY E3. */
+int kbner_attention_fwd(const uint16_t *qkv /*[R*S,3H]*/, const int32_t *key_len /*[R]*/,
+                        int R, int S, int heads, uint16_t *out /*[R*S,H]*/,
+                        float *lse /*[R,heads,S] or NULL*/, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBNER_B200_H_ */

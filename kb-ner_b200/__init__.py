@@ -1,0 +1,9 @@
+"""kbner_b200 -- B200-native KB-NER token-classification hot path (XLM-R encoder + CRF).
+
+Hand-written sm_100a CUDA kernels behind a C ABI (include/kbner_b200.h), bound with ctypes,
+exposed through mirrors of the reference's flair classes.  See DESIGN.md.
+"""
+from . import _lib  # noqa: F401
+from . import ops  # noqa: F401
+
+__all__ = ["_lib", "ops"]

@@ -1,0 +1,62 @@
+"""ctypes binding of the C ABI declared in include/kbner_b200.h.
+
+There is NO fallback: if libkbner_b200.so is missing or a call fails, this raises.  The CPU
+oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkbner_b200.so")
+
+_c_void_p, _c_int, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes ; every entry point of include/kbner_b200.h
+SIGNATURES = {
+    "kbner_abi_version": ([], _c_int),
+    "kbner_last_error": ([], ctypes.c_char_p),
+    "kbner_device_check": ([_c_int], _c_int),
+    "kbner_launch_count": ([], ctypes.c_uint64),
+    "kbner_crf_compact": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "kbner_crf_viterbi": ([_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p] * 3, _c_int),
+    "kbner_crf_nll_fwd": ([_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p] * 4, _c_int),
+    "kbner_crf_nll_bwd": ([_c_void_p] * 8 + [_c_int] * 5 + [_c_void_p] * 3, _c_int),
+    "kbner_embed_ln_fwd": ([_c_void_p] * 6 + [_c_float, _c_int] + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
+    "kbner_layernorm_fwd": ([_c_void_p] * 3 + [_c_float, _c_int, _c_int] + [_c_void_p] * 4, _c_int),
+    "kbner_gather_tagproj_fwd": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
+    "kbner_gemm_bf16_tn": ([_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p], _c_int),
+    "kbner_attention_fwd": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p] * 3, _c_int),
+}
+
+_lib = None
+
+
+class KbnerError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KbnerError(
+            "kbner_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().kbner_last_error()
+        raise KbnerError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(load().kbner_launch_count())

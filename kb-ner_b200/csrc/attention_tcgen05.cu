@@ -1,0 +1,252 @@
+// Fused multi-head self-attention forward for one encoder layer (head dim 64):
+//   O = softmax(Q.K^T / 8 + key-padding mask) . V       per (window, head),
+// flash-style: the [S,S] score matrix the reference's transformers-3.0.0 path materialises in
+// fp32 (call site /root/reference/flair/embeddings.py:3269) never leaves the SM.
+//
+// One CTA = one (window r, head h, block of 128 query rows).  S <= 512 so the whole K and V of
+// the head (<= 4 blocks of 128 keys) are TMA-loaded once into shared memory.
+//   warp 4        TMA + MMA issuer (one lane): S_j = Q.K_j^T  -> TMEM (2 buffers of 128 cols),
+//                 O_j = P_j.V_j -> TMEM (2 buffers of 64 cols); tcgen05.mma kind::f16,
+//                 V is consumed MN-major straight from its row-major [key][d] tile
+//   warps 0..3    softmax: thread = query row = TMEM lane; tcgen05.ld the score row, online
+//                 max / exp2 / sum in fp32 registers, P_j -> bf16 -> shared memory in the
+//                 SWIZZLE_128B K-major layout the MMA reads; running O kept in registers
+//                 (O = O*alpha + P_j.V_j), so no TMEM read-modify-write correction pass.
+// Pipeline: S_{j+1} is issued before softmax(j) finishes, P/O buffers are double-buffered.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace kbner {
+
+constexpr int kAttnD = 64;
+constexpr int kBQ = 128, kBKV = 128, kMaxKB = 4;
+constexpr int kAttnThreads = 160;
+constexpr uint32_t kTileBytes = 128 * 64 * 2;   // one [128 rows][64 bf16] SWIZZLE_128B tile
+
+struct AttnSmem {
+    uint8_t q[kTileBytes];
+    uint8_t k[kMaxKB][kTileBytes];
+    uint8_t v[kMaxKB][kTileBytes];
+    uint8_t p[2][2][kTileBytes];       // [buffer][64-key half][128 rows x 64 keys]
+    uint64_t bar_q;
+    uint64_t bar_kv[kMaxKB];
+    uint64_t bar_s[2];                 // S_j ready in TMEM buffer j&1
+    uint64_t bar_p[2];                 // P_j written to smem buffer j&1 (128 arrivals)
+    uint64_t bar_o[2];                 // O_j ready in TMEM buffer j&1
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ key_len, int S, int H,
+                     int heads, uint16_t *__restrict__ out, float *__restrict__ lse_out) {
+    extern __shared__ uint8_t smem_raw[];
+    AttnSmem &s = *reinterpret_cast<AttnSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
+    const int klen = min(key_len[r], S);
+    const int nkb = (klen + kBKV - 1) / kBKV;        // key blocks that hold at least one valid key
+    const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmQKV);
+        ptx::mbar_init(&s.bar_q, 1);
+        for (int i = 0; i < kMaxKB; ++i) ptx::mbar_init(&s.bar_kv[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&s.bar_s[i], 1);
+            ptx::mbar_init(&s.bar_p[i], 128);
+            ptx::mbar_init(&s.bar_o[i], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) ptx::tmem_alloc<512>(&s.tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const uint32_t tmem_s = tmem_base;            // 2 x 128 columns
+    const uint32_t tmem_o = tmem_base + 256;      // 2 x 64 columns
+
+    if (warp == 4) {
+        if (lane == 0 && nkb > 0) {
+            // ---- loads: Q tile, then K_j / V_j per key block (separate barriers: compute starts early)
+            ptx::mbar_expect_tx(&s.bar_q, kTileBytes);
+            ptx::tma_load_2d(s.q, &tmQKV, &s.bar_q, h * kAttnD, row0 + qb * kBQ);
+            for (int j = 0; j < nkb; ++j) {
+                ptx::mbar_expect_tx(&s.bar_kv[j], 2 * kTileBytes);
+                ptx::tma_load_2d(s.k[j], &tmQKV, &s.bar_kv[j], H + h * kAttnD, row0 + j * kBKV);
+                ptx::tma_load_2d(s.v[j], &tmQKV, &s.bar_kv[j], 2 * H + h * kAttnD, row0 + j * kBKV);
+            }
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);   // S = Q.K^T : both K-major
+            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);    // O = P.V   : V is MN-major
+            const uint32_t q_addr = ptx::smem_u32(s.q);
+            auto issue_s = [&](int j) {
+                ptx::mbar_wait(&s.bar_kv[j], 0);
+                ptx::tc_fence_after();
+                const uint32_t k_addr = ptx::smem_u32(s.k[j]);
+#pragma unroll
+                for (int kk = 0; kk < kAttnD / 16; ++kk) {
+                    const uint64_t da = ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024);
+                    const uint64_t db = ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024);
+                    ptx::mma_f16_ss(tmem_s + (j & 1) * 128, da, db, idesc_s, kk != 0);
+                }
+                ptx::mma_commit(&s.bar_s[j & 1]);
+            };
+            ptx::mbar_wait(&s.bar_q, 0);
+            issue_s(0);
+            if (nkb > 1) issue_s(1);
+            for (int j = 0; j < nkb; ++j) {
+                // P_j in smem (written by the softmax warps; they passed fence.proxy.async first)
+                ptx::mbar_wait(&s.bar_p[j & 1], (j >> 1) & 1);
+                ptx::tc_fence_after();
+                const uint32_t v_addr = ptx::smem_u32(s.v[j]);
+#pragma unroll
+                for (int kk = 0; kk < kBKV / 16; ++kk) {
+                    const uint32_t p_addr = ptx::smem_u32(s.p[j & 1][kk >> 2]) + (kk & 3) * 32;
+                    const uint64_t da = ptx::make_sw128_desc(p_addr, 16, 1024);
+                    // V tile [key][d]: 16 keys per MMA = two 8-row swizzle atoms, 1024 B apart (SBO)
+                    const uint64_t db = ptx::make_sw128_desc(v_addr + kk * 16 * 128, 16, 1024);
+                    ptx::mma_f16_ss(tmem_o + (j & 1) * 64, da, db, idesc_o, kk != 0);
+                }
+                ptx::mma_commit(&s.bar_o[j & 1]);
+                if (j + 2 < nkb) issue_s(j + 2);   // S buffer j&1 was drained before P_j was published
+            }
+        }
+    } else {
+        // ===================== softmax warps: thread = query row =====================
+        const int row = warp * 32 + lane;                 // TMEM lane == row in the query block
+        const int qrow = qb * kBQ + row;                  // sub-token index inside the window
+        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+        const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+        float m_run = -CUDART_INF_F, l_run = 0.0f, alpha_prev = 1.0f;
+        float o_acc[kAttnD];
+#pragma unroll
+        for (int i = 0; i < kAttnD; ++i) o_acc[i] = 0.0f;
+
+        auto accumulate_o = [&](int j, float alpha) {
+            ptx::mbar_wait(&s.bar_o[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t ro[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + (j & 1) * 64 + c * 32, ro);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(ro[i]));
+            }
+            ptx::tc_fence_before();
+        };
+
+        for (int j = 0; j < nkb; ++j) {
+            ptx::mbar_wait(&s.bar_s[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            float sc[kBKV];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t rs[32];
+                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 128 + c * 32, rs);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sc[c * 32 + i] = __uint_as_float(rs[i]);
+            }
+            ptx::tc_fence_before();
+            // scale, key-padding mask, row max
+            const int kbase = j * kBKV;
+            float m_blk = -CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < kBKV; ++i) {
+                const float x = (kbase + i < klen) ? sc[i] * scale_log2 : -CUDART_INF_F;
+                sc[i] = x;
+                m_blk = fmaxf(m_blk, x);
+            }
+            const float m_new = fmaxf(m_run, m_blk);     // finite: every processed block has >= 1 valid key
+            const float alpha = exp2f(m_run - m_new);    // first block: exp2(-inf) = 0
+            float l_blk = 0.0f;
+            // P_j (bf16) into the SWIZZLE_128B K-major tile pair; row-sum over the ROUNDED values so that
+            // normalisation matches what the tensor core actually multiplies
+            uint8_t *pbase = s.p[j & 1][0];
+#pragma unroll
+            for (int ci = 0; ci < 16; ++ci) {
+                float pv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pv[e] = exp2f(sc[ci * 8 + e] - m_new);
+                uint4 pk;
+                pk.x = pack_bf16x2(pv[0], pv[1]);
+                pk.y = pack_bf16x2(pv[2], pv[3]);
+                pk.z = pack_bf16x2(pv[4], pv[5]);
+                pk.w = pack_bf16x2(pv[6], pv[7]);
+                float a0, a1;
+                unpack_bf16x2(pk.x, a0, a1); l_blk += a0 + a1;
+                unpack_bf16x2(pk.y, a0, a1); l_blk += a0 + a1;
+                unpack_bf16x2(pk.z, a0, a1); l_blk += a0 + a1;
+                unpack_bf16x2(pk.w, a0, a1); l_blk += a0 + a1;
+                const int half = ci >> 3, cc = ci & 7;
+                uint8_t *dst = pbase + half * kTileBytes + row * 128 + ((cc ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4 *>(dst) = pk;
+            }
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+            ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
+            ptx::mbar_arrive(&s.bar_p[j & 1]);
+            // deferred accumulation of the previous block's P.V (overlaps this block's MMA)
+            if (j > 0) accumulate_o(j - 1, alpha_prev);
+            alpha_prev = alpha;
+        }
+        if (nkb > 0) accumulate_o(nkb - 1, alpha_prev);
+        // epilogue: normalise, bf16, 128 contiguous bytes per row
+        if (qrow < S) {
+            const float inv = (l_run > 0.0f) ? 1.0f / l_run : 0.0f;
+            uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD;
+#pragma unroll
+            for (int i = 0; i < kAttnD; i += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+                o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+                o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+                o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                *reinterpret_cast<uint4 *>(orow + i) = o;
+            }
+            if (lse_out)   // natural-log LSE of the scaled scores (for the backward pass)
+                lse_out[((size_t)r * heads + h) * S + qrow] =
+                    (l_run > 0.0f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -CUDART_INF_F;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace kbner
+
+using namespace kbner;
+
+extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                   uint16_t *out, float *lse, void *stream) {
+    KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
+    KBNER_CHECK_ARG(R > 0 && S > 0 && heads > 0, "attention_fwd: empty problem");
+    KBNER_CHECK_ARG(S <= kMaxKB * kBKV, "attention_fwd: S=%d exceeds the %d-sub-token window of XLM-R", S,
+                    kMaxKB * kBKV);
+    const int H = heads * kAttnD;
+    CUtensorMap tm;
+    int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)R * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, 64);
+    if (rc) return rc;
+    const size_t smem = sizeof(AttnSmem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return KBNER_ECUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((S + kBQ - 1) / kBQ, heads, R);
+    attention_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tm, key_len, S, H, heads, out, lse);
+    KBNER_CHECK_LAUNCH("attention_fwd");
+    return KBNER_OK;
+}

@@ -1,0 +1,72 @@
+// Shared helpers for the kbner_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/kbner_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "kbner_b200 kernels are written for sm_100a only"
+#endif
+
+namespace kbner {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define KBNER_CHECK_ARG(cond, ...)                       \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            ::kbner::set_error(__VA_ARGS__);             \
+            return KBNER_EINVAL;                         \
+        }                                                \
+    } while (0)
+
+#define KBNER_CHECK_LAUNCH(name)                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) {                                                          \
+            ::kbner::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+            return KBNER_ECUDA;                                                            \
+        }                                                                                  \
+        ::kbner::count_launch();                                                           \
+    } while (0)
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
+__device__ __forceinline__ void unpack_bf16x2(uint32_t p, float &a, float &b) {
+    a = __uint_as_float(p << 16);
+    b = __uint_as_float(p & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// 16-byte streaming loads/stores (data touched once: do not pollute L1)
+__device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_na_v4(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace kbner

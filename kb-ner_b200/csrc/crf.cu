@@ -1,0 +1,515 @@
+// Linear-chain CRF on sm_100a: remove-X compaction, Viterbi (+confidence), log-partition /
+// gold score, and their gradient.  Replaces the per-token Python loops of
+// /root/reference/flair/models/sequence_tagger_model.py (_viterbi_decode :1248-1304,
+// _forward_alg :1329-1394, _score_sentence :2544-2591, _calculate_loss :2448-2506,
+// _obtain_labels :1193-1210).
+//
+// Mapping: one group of G lanes per sentence (G = 16 when L <= 16, two sentences per warp;
+// else G = 32), lane j owns tag j.  The recurrence state lives in registers, the transition
+// row of the lane in registers, the all-to-all exchange of the previous state is G width-G
+// shuffles.  These kernels are bound by the dependent chain / issue rate, their HBM traffic
+// is the emissions read once ("CRF kernels").
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace kbner {
+
+constexpr float kNeg = -1e12f;  // the reference's sentinel (sequence_tagger_model.py:402-410,1252)
+
+// ------------------------------------------------------------------------------------------
+// compaction: one warp per sentence, ballot + popc prefix sum
+// ------------------------------------------------------------------------------------------
+__global__ void crf_compact_kernel(const uint8_t *__restrict__ keep, int B, int T,
+                                   int32_t *__restrict__ pos, int32_t *__restrict__ klen) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const uint8_t *kr = keep + (size_t)warp * T;
+    int32_t *pr = pos + (size_t)warp * T;
+    int n = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        const bool k = (t < T) && kr[t] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (k) pr[n + __popc(m & ((1u << lane) - 1u))] = t;
+        n += __popc(m);
+    }
+    for (int t = n + lane; t < T; t += 32) pr[t] = -1;
+    if (lane == 0) klen[warp] = n;
+}
+
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, G));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_max_int(int v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o, G));
+    return v;
+}
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Viterbi.  Bit-exact with the reference: fp32, c = v[k] + A[j][k] (one add), first maximal k,
+// then + e[j] (second add); terminal v + A[STOP], entries STOP/START forced to -1e12, first max.
+// Back-pointers: one byte per (step, tag) in shared memory; back-trace by lane 0 of the group.
+// Confidence = 1 / sum_k exp(v_t[k] - max_k v_t[k]) is computed G steps at a time from a
+// G x G staging tile (lane r finishes step r), so it costs ~L/G exps per step instead of a
+// cross-lane reduction per step.
+// ------------------------------------------------------------------------------------------
+constexpr int kVitUnroll = 8;
+
+template <int G>
+__global__ void __launch_bounds__(128)
+crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ pos,
+                   const int32_t *__restrict__ klen, const int32_t *__restrict__ slen,
+                   const float *__restrict__ trans, int B, int T, int L, int start, int stop,
+                   int x_idx, int32_t *__restrict__ tags_out, float *__restrict__ conf_out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int SPW = 32 / G;
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / G, j = lane % G;
+    const int slot = warp * SPW + sub;
+    const int b = blockIdx.x * W * SPW + slot;
+    uint8_t *bp = smem + (size_t)slot * T * G;
+    float *vt = reinterpret_cast<float *>(smem + (size_t)W * SPW * T * G) + slot * G * G;
+
+    const bool valid = b < B;
+    const int n = valid ? klen[b] : 0;
+    const int ns = valid ? slen[b] : 0;
+    const int nmax = warp_max_int(n);
+    const size_t rowbase = (size_t)(valid ? b : 0) * T;
+
+    // default fill (S-X padding of _obtain_labels :1202-1208, -1 beyond the sentence)
+    if (valid) {
+        for (int t = j; t < T; t += G) {
+            tags_out[rowbase + t] = (t < ns) ? x_idx : -1;
+            conf_out[rowbase + t] = (t < ns) ? 1.0f : 0.0f;
+        }
+    }
+    // transition row of this lane; padding lanes / columns are -inf so they never win
+    float A[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) A[k] = (j < L && k < L) ? trans[j * L + k] : -CUDART_INF_F;
+
+    float v = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
+    __syncwarp();
+
+    float e_cur[kVitUnroll], e_nxt[kVitUnroll];
+    auto load_block = [&](int i0, float (&dst)[kVitUnroll]) {
+#pragma unroll
+        for (int u = 0; u < kVitUnroll; ++u) {
+            const int i = i0 + u;
+            float ev = 0.0f;
+            if (i < n && j < L) {
+                const int t = pos ? __ldg(pos + rowbase + i) : i;
+                ev = __ldg(emis + (rowbase + t) * L + j);
+            }
+            dst[u] = ev;
+        }
+    };
+    load_block(0, e_cur);
+    for (int i0 = 0; i0 < nmax; i0 += kVitUnroll) {
+        load_block(i0 + kVitUnroll, e_nxt);
+#pragma unroll
+        for (int u = 0; u < kVitUnroll; ++u) {
+            const int i = i0 + u;
+            if (i < nmax) {   // warp-uniform
+                const bool act = i < n;
+                float best = -CUDART_INF_F;
+                int bk = 0;
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const float c = __shfl_sync(0xffffffffu, v, k, G) + A[k];
+                    if (c > best) { best = c; bk = k; }
+                }
+                if (act) {
+                    bp[(size_t)i * G + j] = (uint8_t)bk;
+                    v = best + e_cur[u];
+                }
+                vt[(i & (G - 1)) * G + j] = v;
+                if ((i & (G - 1)) == G - 1 || i == nmax - 1) {
+                    __syncwarp();
+                    const int s = (i & ~(G - 1)) + j;   // lane j finishes step s
+                    if (s <= i && s < n) {
+                        const float *r = vt + (s & (G - 1)) * G;
+                        float m = r[0];
+                        for (int k = 1; k < L; ++k) m = fmaxf(m, r[k]);
+                        float sum = 0.0f;
+                        for (int k = 0; k < L; ++k) sum += expf(r[k] - m);
+                        const int t = pos ? __ldg(pos + rowbase + s) : s;
+                        conf_out[rowbase + t] = 1.0f / sum;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVitUnroll; ++u) e_cur[u] = e_nxt[u];
+    }
+    // terminal (:1279-1287): first max of v + A[STOP], with STOP / START forced to -1e12
+    float term = -CUDART_INF_F;
+    if (j < L) {
+        term = v + trans[stop * L + j];
+        if (j == stop || j == start) term = kNeg;
+    }
+    int idx = j;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, term, o, G);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o, G);
+        if (ov > term || (ov == term && oi < idx)) { term = ov; idx = oi; }
+    }
+    __syncwarp();
+    if (j == 0 && n > 0) {
+        int cur = idx;
+        for (int i = n - 1; i >= 0; --i) {
+            const int t = pos ? __ldg(pos + rowbase + i) : i;
+            tags_out[rowbase + t] = cur;
+            cur = bp[(size_t)i * G + cur];
+        }
+        // cur is START here for every well-formed transition matrix (reference assert :1303)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// log Z and gold score.  The reference evaluates alpha'[j] = max_k x + log sum_k exp(x - max),
+// x = (e[j] + A[j][k]) + alpha[k]  (L^2 exps per step).  Here the same quantity is evaluated as
+//   alpha'[j] = e[j] + rmax_j + M + log sum_k E[j][k] * exp(alpha[k] - M),
+// E[j][k] = exp(A[j][k] - rmax_j), M = max_k alpha[k]: one exp per lane per step and an FMA per
+// pair; differs from the reference by fp32 rounding only (tests: 1e-5 relative).
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
+                   const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
+                   const float *__restrict__ trans, int B, int T, int L, int start, int stop,
+                   float *__restrict__ logz, float *__restrict__ gold, float *__restrict__ alpha_out) {
+    constexpr int SPW = 32 / G;
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / G, j = lane % G;
+    const int b = (blockIdx.x * W + warp) * SPW + sub;
+    const bool valid = b < B;
+    const int n = valid ? klen[b] : 0;
+    const int nmax = warp_max_int(n);
+    const size_t rowbase = (size_t)(valid ? b : 0) * T;
+
+    float rmax = -CUDART_INF_F;
+    if (j < L)
+        for (int k = 0; k < L; ++k) rmax = fmaxf(rmax, trans[j * L + k]);
+    float E[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) E[k] = (j < L && k < L) ? expf(trans[j * L + k] - rmax) : 0.0f;
+    if (j >= L) rmax = 0.0f;
+
+    float a = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
+    constexpr int U = 4;
+    float e_cur[U], e_nxt[U];
+    auto load_block = [&](int i0, float (&dst)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u;
+            float ev = 0.0f;
+            if (i < n && j < L) {
+                const int t = pos ? __ldg(pos + rowbase + i) : i;
+                ev = __ldg(emis + (rowbase + t) * L + j);
+            }
+            dst[u] = ev;
+        }
+    };
+    load_block(0, e_cur);
+    for (int i0 = 0; i0 < nmax; i0 += U) {
+        load_block(i0 + U, e_nxt);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u;
+            if (i < nmax) {
+                const float M = group_max<G>(a);
+                const float p = expf(a - M);
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < G; ++k) s = fmaf(E[k], __shfl_sync(0xffffffffu, p, k, G), s);
+                const float an = (e_cur[u] + rmax) + (M + logf(s));
+                if (i < n) {
+                    a = an;
+                    if (alpha_out && j < L) alpha_out[(rowbase + i) * L + j] = a;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) e_cur[u] = e_nxt[u];
+    }
+    // terminal: log_sum_exp_batch(alpha_len + A[STOP])  (:1381-1392)
+    const float x = (j < L) ? a + trans[stop * L + j] : -CUDART_INF_F;
+    const float M2 = group_max<G>(x);
+    const float s2 = group_sum<G>(expf(x - M2));
+    // gold score (:2544-2591): lanes stride over the kept tokens
+    float g = 0.0f;
+    for (int i = j; i < n; i += G) {
+        const int t = pos ? pos[rowbase + i] : i;
+        const int y = tags[rowbase + t];
+        int prev = start;
+        if (i > 0) {
+            const int tp = pos ? pos[rowbase + i - 1] : i - 1;
+            prev = tags[rowbase + tp];
+        }
+        g += emis[(rowbase + t) * L + y] + trans[y * L + prev];
+    }
+    g = group_sum<G>(g);
+    if (valid && j == 0) {
+        int last = start;
+        if (n > 0) {
+            const int tl = pos ? pos[rowbase + n - 1] : n - 1;
+            last = tags[rowbase + tl];
+        }
+        logz[b] = M2 + logf(s2);
+        gold[b] = g + trans[stop * L + last];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// gradient of sum_b w[b] (logZ_b - gold_b).  Reverse (beta) recursion in the same scaled form;
+// unary marginals -> d_emis, pairwise marginals accumulated per lane as
+//   acc[j][k] += c * q_j * a_k   (dT[j][k] = E[j][k] * acc[j][k]),
+// persistent over sentences, reduced through shared memory, one global atomic set per block.
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
+                   const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
+                   const float *__restrict__ trans, const float *__restrict__ alpha,
+                   const float *__restrict__ logz, const float *__restrict__ w, int B, int T, int L,
+                   int start, int stop, float *__restrict__ d_emis, float *__restrict__ d_trans) {
+    __shared__ float s_dt[32 * 32];
+    constexpr int SPW = 32 / G;
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / G, j = lane % G;
+    for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_dt[i] = 0.0f;
+    __syncthreads();
+
+    float rmax = -CUDART_INF_F;
+    if (j < L)
+        for (int k = 0; k < L; ++k) rmax = fmaxf(rmax, trans[j * L + k]);
+    // Ecol[jj] = E[jj][j]: column j of the row-normalised exp(A)
+    float Ecol[G];
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) {
+        float v = 0.0f;
+        if (j < L && jj < L) {
+            float rm = -CUDART_INF_F;
+            for (int k = 0; k < L; ++k) rm = fmaxf(rm, trans[jj * L + k]);
+            v = expf(trans[jj * L + j] - rm);
+        }
+        Ecol[jj] = v;
+    }
+    if (j >= L) rmax = 0.0f;
+    float acc[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) acc[k] = 0.0f;
+
+    const int groups_total = gridDim.x * W * SPW;
+    const int g0 = (blockIdx.x * W + warp) * SPW + sub;
+    const int iters = (B + groups_total - 1) / groups_total;
+    for (int it = 0; it < iters; ++it) {
+        const int b = g0 + it * groups_total;
+        const bool valid = b < B;
+        const int n = valid ? klen[b] : 0;
+        const int nmax = warp_max_int(n);
+        const size_t rowbase = (size_t)(valid ? b : 0) * T;
+        const float lz = valid ? logz[b] : 0.0f;
+        const float wb = valid ? w[b] : 0.0f;
+        if (nmax == 0) continue;   // warp-uniform
+
+        float beta = (j < L) ? trans[stop * L + j] : -CUDART_INF_F;   // beta_n[k] = A[STOP][k]
+        // terminal pairwise term: dT[STOP][k] += w * exp(alpha_n[k] + A[STOP][k] - logZ)
+        if (n > 0 && j < L) {
+            const float an = alpha[(rowbase + n - 1) * L + j];
+            atomicAdd(&s_dt[stop * L + j], wb * expf(an + beta - lz));
+        }
+        for (int i = nmax - 1; i >= 0; --i) {
+            const bool act = i < n;
+            float e = 0.0f, anext = -CUDART_INF_F, aprev = -CUDART_INF_F;
+            int t = 0, y = -1, yprev = start;
+            if (act) {
+                t = pos ? pos[rowbase + i] : i;
+                y = tags[rowbase + t];
+                if (i > 0) {
+                    const int tp = pos ? pos[rowbase + i - 1] : i - 1;
+                    yprev = tags[rowbase + tp];
+                }
+                if (j < L) {
+                    e = emis[(rowbase + t) * L + j];
+                    anext = alpha[(rowbase + i) * L + j];
+                    aprev = (i > 0) ? alpha[(rowbase + i - 1) * L + j] : ((j == start) ? 0.0f : kNeg);
+                }
+            }
+            // unary marginal
+            if (act && j < L) {
+                const float pj = expf(anext + beta - lz);
+                d_emis[(rowbase + t) * L + j] = wb * (pj - ((j == y) ? 1.0f : 0.0f));
+            }
+            const float u = (j < L && act) ? (e + beta + rmax) : -CUDART_INF_F;
+            const float Mb = group_max<G>(u);
+            const float Ma = group_max<G>(aprev);
+            const float q = (act && j < L) ? expf(u - Mb) : 0.0f;
+            const float av = (act && j < L) ? expf(aprev - Ma) : 0.0f;
+            const float c = act ? wb * expf(fminf(Ma + Mb - lz, 80.0f)) : 0.0f;
+            const float cq = c * q;
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                acc[k] = fmaf(cq, __shfl_sync(0xffffffffu, av, k, G), acc[k]);
+                s = fmaf(Ecol[k], __shfl_sync(0xffffffffu, q, k, G), s);
+            }
+            if (act) beta = Mb + logf(s);
+            // gold transition count
+            if (act && j == 0) atomicAdd(&s_dt[y * L + yprev], -wb);
+        }
+        if (n > 0 && j == 0) {
+            const int tl = pos ? pos[rowbase + n - 1] : n - 1;
+            atomicAdd(&s_dt[stop * L + tags[rowbase + tl]], -wb);
+        }
+    }
+    // dT[j][k] += E[j][k] * acc[k]
+    if (j < L) {
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+            if (k < L && acc[k] != 0.0f) atomicAdd(&s_dt[j * L + k], expf(trans[j * L + k] - rmax) * acc[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * L; i += blockDim.x)
+        if (s_dt[i] != 0.0f) atomicAdd(&d_trans[i], s_dt[i]);
+}
+
+}  // namespace kbner
+
+using namespace kbner;
+
+extern "C" int kbner_crf_compact(const uint8_t *keep, int B, int T, int32_t *pos, int32_t *klen,
+                                 void *stream) {
+    KBNER_CHECK_ARG(keep && pos && klen && B >= 0 && T > 0, "crf_compact: bad arguments");
+    if (B == 0) return KBNER_OK;
+    const int threads = 128;
+    const int blocks = (B * 32 + threads - 1) / threads;
+    crf_compact_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(keep, B, T, pos, klen);
+    KBNER_CHECK_LAUNCH("crf_compact");
+    return KBNER_OK;
+}
+
+template <int G>
+static int launch_viterbi(const float *emis, const int32_t *pos, const int32_t *klen,
+                          const int32_t *slen, const float *trans, int B, int T, int L, int start,
+                          int stop, int x_idx, int32_t *tags_out, float *conf_out, cudaStream_t st) {
+    constexpr int SPW = 32 / G;
+    int W = 4;
+    size_t smem = 0;
+    for (; W >= 1; W >>= 1) {
+        smem = (size_t)W * SPW * ((size_t)T * G + (size_t)G * G * sizeof(float));
+        if (smem <= 200 * 1024) break;
+    }
+    if (W < 1) {
+        set_error("crf_viterbi: T=%d too long for the shared-memory back-pointer table", T);
+        return KBNER_EUNSUPPORTED;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(crf_viterbi_kernel<G>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        if (e != cudaSuccess) {
+            set_error("crf_viterbi: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return KBNER_ECUDA;
+        }
+        configured = 200 * 1024;
+    }
+    const int per_block = W * SPW;
+    const int blocks = (B + per_block - 1) / per_block;
+    crf_viterbi_kernel<G><<<blocks, W * 32, smem, st>>>(emis, pos, klen, slen, trans, B, T, L, start,
+                                                         stop, x_idx, tags_out, conf_out);
+    KBNER_CHECK_LAUNCH("crf_viterbi");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_crf_viterbi(const float *emis, const int32_t *pos, const int32_t *klen,
+                                 const int32_t *slen, const float *trans, int B, int T, int L,
+                                 int start_idx, int stop_idx, int x_idx, int32_t *tags_out,
+                                 float *conf_out, void *stream) {
+    KBNER_CHECK_ARG(emis && klen && slen && trans && tags_out && conf_out, "crf_viterbi: null pointer");
+    KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_viterbi: need L in [2,32], got L=%d T=%d", L, T);
+    KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,
+                    "crf_viterbi: start/stop index out of range");
+    if (B == 0) return KBNER_OK;
+    if (L <= 16)
+        return launch_viterbi<16>(emis, pos, klen, slen, trans, B, T, L, start_idx, stop_idx, x_idx,
+                                  tags_out, conf_out, (cudaStream_t)stream);
+    return launch_viterbi<32>(emis, pos, klen, slen, trans, B, T, L, start_idx, stop_idx, x_idx,
+                              tags_out, conf_out, (cudaStream_t)stream);
+}
+
+extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const int32_t *pos,
+                                 const int32_t *klen, const float *trans, int B, int T, int L,
+                                 int start_idx, int stop_idx, float *logz, float *gold, float *alpha,
+                                 void *stream) {
+    KBNER_CHECK_ARG(emis && tags && klen && trans && logz && gold, "crf_nll_fwd: null pointer");
+    KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_fwd: need L in [2,32], got %d", L);
+    KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,
+                    "crf_nll_fwd: start/stop index out of range");
+    if (B == 0) return KBNER_OK;
+    const int W = 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (L <= 16) {
+        const int per_block = W * 2;
+        crf_nll_fwd_kernel<16><<<(B + per_block - 1) / per_block, W * 32, 0, st>>>(
+            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha);
+    } else {
+        crf_nll_fwd_kernel<32><<<(B + W - 1) / W, W * 32, 0, st>>>(
+            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha);
+    }
+    KBNER_CHECK_LAUNCH("crf_nll_fwd");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const int32_t *pos,
+                                 const int32_t *klen, const float *trans, const float *alpha,
+                                 const float *logz, const float *w, int B, int T, int L,
+                                 int start_idx, int stop_idx, float *d_emis, float *d_trans,
+                                 void *stream) {
+    KBNER_CHECK_ARG(emis && tags && klen && trans && alpha && logz && w && d_emis && d_trans,
+                    "crf_nll_bwd: null pointer");
+    KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_bwd: need L in [2,32], got %d", L);
+    if (B == 0) return KBNER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_emis, 0, sizeof(float) * (size_t)B * T * L, st);
+    if (e != cudaSuccess) {
+        set_error("crf_nll_bwd: memset: %s", cudaGetErrorString(e));
+        return KBNER_ECUDA;
+    }
+    const int W = 4;
+    const int spw = (L <= 16) ? 2 : 1;
+    int blocks = (B + W * spw - 1) / (W * spw);
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;   // persistent over sentences beyond that
+    if (L <= 16)
+        crf_nll_bwd_kernel<16><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, logz, w,
+                                                          B, T, L, start_idx, stop_idx, d_emis, d_trans);
+    else
+        crf_nll_bwd_kernel<32><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, logz, w,
+                                                          B, T, L, start_idx, stop_idx, d_emis, d_trans);
+    KBNER_CHECK_LAUNCH("crf_nll_bwd");
+    return KBNER_OK;
+}

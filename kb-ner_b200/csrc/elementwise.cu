@@ -1,0 +1,266 @@
+// HBM-bound kernels of the encoder / tagger head: embedding gather + LayerNorm, LayerNorm,
+// first-sub-token gather + word dropout + tag projection.  One warp per row, 16-byte loads,
+// fp32 statistics (two-pass, from registers), bf16 activations out.
+#include "common.cuh"
+
+namespace kbner {
+
+constexpr int kLnWarps = 4;
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over fp32 rows (the GEMM epilogue already produced x = A.B^T + bias + residual in
+// fp32), bf16 out.  HF BertSelfOutput / BertOutput LayerNorm as called from
+// /root/reference/flair/embeddings.py:3269.  VPL = float4 per lane.
+// ------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                     float eps, int M, uint16_t *__restrict__ y, float *__restrict__ mean_out,
+                     float *__restrict__ rstd_out) {
+    constexpr int H = VPL * 128;
+    const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * H);
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const uint4 u = ld_nc_v4(xr + i * 32 + lane);
+        v[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * (1.0f / H);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+    uint16_t *yr = y + (size_t)row * H;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta) + i * 32 + lane);
+        uint2 o;
+        o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+        o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        *reinterpret_cast<uint2 *>(yr + (i * 32 + lane) * 4) = o;
+    }
+    if (mean_out && lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding gather + LayerNorm.  HF (XLM-)RobertaEmbeddings: word[ids] + type[0] + pos[p],
+// p = cumsum(ids != pad) * (ids != pad) + pad  (padding_idx = 1), LayerNorm(eps), SURVEY E1.
+// Block = 4 warps = 16 consecutive sub-tokens of one window; the non-pad prefix count up to the
+// chunk is a block-wide count, inside the chunk a ballot.
+// ------------------------------------------------------------------------------------------
+constexpr int kEmbTok = 16;
+
+template <int VPL>
+__global__ void __launch_bounds__(128)
+embed_ln_fwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ word_emb,
+                    const float *__restrict__ pos_emb, const float *__restrict__ type_emb,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int pad_id, int S,
+                    int V, int P, uint16_t *__restrict__ out) {
+    constexpr int H = VPL * 128;
+    const int r = blockIdx.y;
+    const int s0 = blockIdx.x * kEmbTok;
+    const int32_t *idr = ids + (size_t)r * S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // non-pad tokens strictly before the chunk
+    int before = 0;
+    for (int base = 0; base < s0; base += 128) {
+        const int t = base + threadIdx.x;
+        before += __syncthreads_count(t < s0 && idr[t] != pad_id);
+    }
+    const int tl = s0 + (lane & (kEmbTok - 1));
+    const int my_id = (tl < S) ? idr[tl] : pad_id;
+    const unsigned nonpad = __ballot_sync(0xffffffffu, my_id != pad_id) & 0xffffu;
+#pragma unroll
+    for (int q = 0; q < kEmbTok / 4; ++q) {
+        const int local = warp * (kEmbTok / 4) + q;
+        const int sidx = s0 + local;
+        if (sidx >= S) break;
+        const int id = __shfl_sync(0xffffffffu, my_id, local);
+        int p = pad_id;
+        if (id != pad_id) p = before + __popc(nonpad & ((2u << local) - 1u)) + pad_id;
+        if (id < 0 || id >= V || p >= P) {      // corrupt input: fail loudly instead of reading out of bounds
+            if (lane == 0) printf("kbner embed_ln: id %d / position %d out of range (V=%d P=%d)\n", id, p, V, P);
+            __trap();
+        }
+        const float4 *wr = reinterpret_cast<const float4 *>(word_emb + (size_t)id * H);
+        const float4 *pr = reinterpret_cast<const float4 *>(pos_emb + (size_t)p * H);
+        const float4 *tr = reinterpret_cast<const float4 *>(type_emb);
+        float4 v[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 a = __ldg(wr + i * 32 + lane), b = __ldg(tr + i * 32 + lane), c = __ldg(pr + i * 32 + lane);
+            v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = warp_sum(sum) * (1.0f / H);
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+        uint16_t *yr = out + ((size_t)r * S + sidx) * H;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(beta) + i * 32 + lane);
+            uint2 o;
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            *reinterpret_cast<uint2 *>(yr + (i * 32 + lane) * 4) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// First-sub-token gather + word dropout + Linear(H -> L), fp32 logits.
+// Replaces /root/reference/flair/embeddings.py:3288-3345 + :108-124 (pooling, .cpu() round trip),
+// flair/nn.py:176-183 (WordDropout) and sequence_tagger_model.py:1027 (self.linear).
+// W (fp32, [L,H]) is staged once per block in shared memory; one warp per word.
+// ------------------------------------------------------------------------------------------
+template <int CPL>   // 8-element (16-byte bf16) chunks per lane: H = CPL * 256
+__global__ void __launch_bounds__(256)
+gather_tagproj_fwd_kernel(const uint16_t *__restrict__ hidden, const int32_t *__restrict__ row_of,
+                          const int32_t *__restrict__ first_idx, const uint8_t *__restrict__ drop_keep,
+                          const float *__restrict__ W, const float *__restrict__ bias, int B, int T, int S, int L,
+                          float *__restrict__ logits) {
+    constexpr int H = CPL * 256;
+    extern __shared__ __align__(16) float w_s[];     // [L][H]
+    for (int i = threadIdx.x; i < L * H / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const float my_bias = (lane < L) ? bias[lane] : 0.0f;
+    for (int w = blockIdx.x * (blockDim.x >> 5) + warp; w < B * T; w += nwarps) {
+        const int b = w / T, t = w - b * T;
+        const int fi = first_idx[w];
+        const bool live = fi >= 0 && (!drop_keep || drop_keep[t] != 0);
+        float res = my_bias;                       // zero vector (0 sub-tokens / dropped word) => bias only
+        if (live) {                                // warp-uniform
+            const uint16_t *hr = hidden + ((size_t)row_of[b] * S + fi) * H;
+            float x[CPL * 8];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const uint4 u = ld_nc_v4(hr + c * 256 + lane * 8);
+                unpack_bf16x2(u.x, x[c * 8 + 0], x[c * 8 + 1]);
+                unpack_bf16x2(u.y, x[c * 8 + 2], x[c * 8 + 3]);
+                unpack_bf16x2(u.z, x[c * 8 + 4], x[c * 8 + 5]);
+                unpack_bf16x2(u.w, x[c * 8 + 6], x[c * 8 + 7]);
+            }
+            for (int l = 0; l < L; ++l) {
+                const float *wl = w_s + (size_t)l * H;
+                float acc = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8 + 4);
+                    acc = fmaf(x[c * 8 + 0], w0.x, acc); acc = fmaf(x[c * 8 + 1], w0.y, acc);
+                    acc = fmaf(x[c * 8 + 2], w0.z, acc); acc = fmaf(x[c * 8 + 3], w0.w, acc);
+                    acc = fmaf(x[c * 8 + 4], w1.x, acc); acc = fmaf(x[c * 8 + 5], w1.y, acc);
+                    acc = fmaf(x[c * 8 + 6], w1.z, acc); acc = fmaf(x[c * 8 + 7], w1.w, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == l) res += acc;
+            }
+        }
+        if (lane < L) logits[(size_t)w * L + lane] = res;
+    }
+}
+
+}  // namespace kbner
+
+using namespace kbner;
+
+#define DISPATCH_VPL(H, CALL)                                                                   \
+    switch ((H) / 128) {                                                                        \
+        case 2: { constexpr int VPL = 2; CALL; } break;                                         \
+        case 4: { constexpr int VPL = 4; CALL; } break;                                         \
+        case 6: { constexpr int VPL = 6; CALL; } break;                                         \
+        case 8: { constexpr int VPL = 8; CALL; } break;                                         \
+        case 16: { constexpr int VPL = 16; CALL; } break;                                       \
+        default: set_error("hidden size %d not built (supported: 256, 512, 768, 1024, 2048)", (H)); \
+                 return KBNER_EUNSUPPORTED;                                                     \
+    }
+
+extern "C" int kbner_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int M, int H,
+                                   uint16_t *y, float *mean, float *rstd, void *stream) {
+    KBNER_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
+    KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 128 == 0, "layernorm_fwd: H=%d must be a multiple of 128", H);
+    KBNER_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
+    if (M == 0) return KBNER_OK;
+    const int blocks = (M + kLnWarps - 1) / kLnWarps;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_VPL(H, (layernorm_fwd_kernel<VPL><<<blocks, kLnWarps * 32, 0, st>>>(x, gamma, beta, eps, M, y, mean, rstd)));
+    KBNER_CHECK_LAUNCH("layernorm_fwd");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_embed_ln_fwd(const int32_t *ids, const float *word_emb, const float *pos_emb,
+                                  const float *type_emb, const float *gamma, const float *beta, float eps,
+                                  int pad_id, int R, int S, int H, int V, int P, uint16_t *out, void *stream) {
+    KBNER_CHECK_ARG(ids && word_emb && pos_emb && type_emb && gamma && beta && out, "embed_ln_fwd: null pointer");
+    KBNER_CHECK_ARG(R >= 0 && S > 0 && H % 128 == 0 && V > 0 && P > 0, "embed_ln_fwd: bad shape");
+    if (R == 0) return KBNER_OK;
+    dim3 grid((S + kEmbTok - 1) / kEmbTok, R);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_VPL(H, (embed_ln_fwd_kernel<VPL><<<grid, 128, 0, st>>>(ids, word_emb, pos_emb, type_emb, gamma, beta, eps,
+                                                                     pad_id, S, V, P, out)));
+    KBNER_CHECK_LAUNCH("embed_ln_fwd");
+    return KBNER_OK;
+}
+
+template <int CPL>
+static int launch_tagproj(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
+                          const uint8_t *drop_keep, const float *W, const float *bias, int B, int T, int S, int L,
+                          float *logits, cudaStream_t st) {
+    const size_t smem = (size_t)L * CPL * 256 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gather_tagproj_fwd_kernel<CPL>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("gather_tagproj: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return KBNER_ECUDA;
+        }
+        configured = smem;
+    }
+    const int words = B * T;
+    int blocks = (words + 7) / 8;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    gather_tagproj_fwd_kernel<CPL><<<blocks, 256, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L,
+                                                              logits);
+    KBNER_CHECK_LAUNCH("gather_tagproj_fwd");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_gather_tagproj_fwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
+                                        const uint8_t *drop_keep, const float *W, const float *bias, int B, int T,
+                                        int S, int H, int L, float *logits, void *stream) {
+    KBNER_CHECK_ARG(hidden && row_of && first_idx && W && bias && logits, "gather_tagproj_fwd: null pointer");
+    KBNER_CHECK_ARG(B >= 0 && T > 0 && S > 0 && L >= 1 && L <= 32, "gather_tagproj_fwd: need 1 <= L <= 32 (L=%d)", L);
+    KBNER_CHECK_ARG(H % 256 == 0 && (size_t)L * H * 4 <= 200 * 1024,
+                    "gather_tagproj_fwd: H=%d must be a multiple of 256 with L*H*4 <= 200 KB", H);
+    if (B == 0) return KBNER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (H / 256) {
+        case 1: return launch_tagproj<1>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L, logits, st);
+        case 2: return launch_tagproj<2>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L, logits, st);
+        case 3: return launch_tagproj<3>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L, logits, st);
+        case 4: return launch_tagproj<4>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L, logits, st);
+        default: set_error("gather_tagproj_fwd: hidden size %d not built", H); return KBNER_EUNSUPPORTED;
+    }
+}

@@ -1,0 +1,118 @@
+// Library-level plumbing of the C ABI: error text, launch counter, device check, TMA maps.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "tma_host.cuh"
+
+namespace kbner {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void *base;
+    uint64_t rows, cols, ld;
+    uint32_t br, bc;
+    bool operator==(const TmapKey &o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && br == o.br && bc == o.bc;
+    }
+};
+struct TmapHash {
+    size_t operator()(const TmapKey &k) const {
+        size_t h = (size_t)k.base;
+        h = h * 1000003u ^ k.rows;
+        h = h * 1000003u ^ k.cols;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ ((uint64_t)k.br << 32 | k.bc);
+        return h;
+    }
+};
+
+int make_tmap_bf16_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+    TmapKey key{base, rows, cols, ld, box_rows, box_cols};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return KBNER_OK;
+        }
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+        return KBNER_ECUDA;
+    }
+    if (((uintptr_t)base & 15u) != 0 || (ld * 2) % 16 != 0 || box_cols * 2 != 128 || box_rows > 256) {
+        set_error("tensor map: base must be 16-B aligned, ld*2 a multiple of 16, box 64 x <=256 (got ld=%llu box=%ux%u)",
+                  (unsigned long long)ld, box_rows, box_cols);
+        return KBNER_EINVAL;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return KBNER_ECUDA;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return KBNER_OK;
+}
+
+}  // namespace kbner
+
+extern "C" int kbner_abi_version(void) { return 1; }
+extern "C" const char *kbner_last_error(void) { return kbner::g_err; }
+extern "C" uint64_t kbner_launch_count(void) { return kbner::g_launches.load(); }
+extern "C" int kbner_device_check(int dev) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) {
+        kbner::set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+        return KBNER_ENODEVICE;
+    }
+    if (p.major != 10) {
+        kbner::set_error("device %d is sm_%d%d; kbner_b200 kernels are built for sm_100a only", dev, p.major, p.minor);
+        return KBNER_ENODEVICE;
+    }
+    return KBNER_OK;
+}

@@ -1,0 +1,172 @@
+"""Tensor-level wrappers over the C ABI (include/kbner_b200.h).
+
+torch is used only for device memory and the current CUDA stream; every function here ends in
+exactly one call into libkbner_b200.so.  No function has a PyTorch / CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID_F32, EPI_NONE_F32 = 0, 1, 2, 3
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name, ndim=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.KbnerError("%s must be a CUDA tensor (kbner_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise _lib.KbnerError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.KbnerError("%s must be contiguous" % name)
+    if ndim is not None and t.dim() != ndim:
+        raise _lib.KbnerError("%s must have %d dims, got %d" % (name, ndim, t.dim()))
+
+
+# ---- CRF ---------------------------------------------------------------------------------------
+def crf_compact(keep):
+    """keep [B,T] uint8 -> (pos [B,T] int32, klen [B] int32)."""
+    _chk(keep, torch.uint8, "keep", 2)
+    B, T = keep.shape
+    pos = torch.empty((B, T), dtype=torch.int32, device=keep.device)
+    klen = torch.empty((B,), dtype=torch.int32, device=keep.device)
+    _lib.check(_lib.load().kbner_crf_compact(_ptr(keep), B, T, _ptr(pos), _ptr(klen), _stream()), "crf_compact")
+    return pos, klen
+
+
+def crf_viterbi(emis, trans, klen, slen, start_idx, stop_idx, x_idx=0, pos=None):
+    """Returns (tags [B,T] int32, conf [B,T] float32)."""
+    _chk(emis, torch.float32, "emis", 3)
+    _chk(trans, torch.float32, "trans", 2)
+    _chk(klen, torch.int32, "klen", 1)
+    _chk(slen, torch.int32, "slen", 1)
+    _chk(pos, torch.int32, "pos", 2)
+    B, T, L = emis.shape
+    tags = torch.empty((B, T), dtype=torch.int32, device=emis.device)
+    conf = torch.empty((B, T), dtype=torch.float32, device=emis.device)
+    _lib.check(_lib.load().kbner_crf_viterbi(_ptr(emis), _ptr(pos), _ptr(klen), _ptr(slen), _ptr(trans), B, T, L,
+                                             int(start_idx), int(stop_idx), int(x_idx), _ptr(tags), _ptr(conf),
+                                             _stream()), "crf_viterbi")
+    return tags, conf
+
+
+def crf_nll_fwd(emis, tags, trans, klen, start_idx, stop_idx, pos=None, want_alpha=False):
+    """Returns (logz [B], gold [B], alpha [B,T,L] or None)."""
+    _chk(emis, torch.float32, "emis", 3)
+    _chk(tags, torch.int32, "tags", 2)
+    _chk(trans, torch.float32, "trans", 2)
+    _chk(klen, torch.int32, "klen", 1)
+    _chk(pos, torch.int32, "pos", 2)
+    B, T, L = emis.shape
+    logz = torch.empty((B,), dtype=torch.float32, device=emis.device)
+    gold = torch.empty((B,), dtype=torch.float32, device=emis.device)
+    alpha = torch.empty((B, T, L), dtype=torch.float32, device=emis.device) if want_alpha else None
+    _lib.check(_lib.load().kbner_crf_nll_fwd(_ptr(emis), _ptr(tags), _ptr(pos), _ptr(klen), _ptr(trans), B, T, L,
+                                             int(start_idx), int(stop_idx), _ptr(logz), _ptr(gold), _ptr(alpha),
+                                             _stream()), "crf_nll_fwd")
+    return logz, gold, alpha
+
+
+def crf_nll_bwd(emis, tags, trans, klen, alpha, logz, w, start_idx, stop_idx, pos=None):
+    """Returns (d_emis [B,T,L], d_trans [L,L]) of sum_b w[b]*(logZ_b - gold_b)."""
+    _chk(alpha, torch.float32, "alpha", 3)
+    _chk(logz, torch.float32, "logz", 1)
+    _chk(w, torch.float32, "w", 1)
+    B, T, L = emis.shape
+    d_emis = torch.empty_like(emis)
+    d_trans = torch.zeros((L, L), dtype=torch.float32, device=emis.device)
+    _lib.check(_lib.load().kbner_crf_nll_bwd(_ptr(emis), _ptr(tags), _ptr(pos), _ptr(klen), _ptr(trans), _ptr(alpha),
+                                             _ptr(logz), _ptr(w), B, T, L, int(start_idx), int(stop_idx),
+                                             _ptr(d_emis), _ptr(d_trans), _stream()), "crf_nll_bwd")
+    return d_emis, d_trans
+
+
+# ---- encoder -----------------------------------------------------------------------------------
+def embed_ln_fwd(ids, word_emb, pos_emb, type_emb, gamma, beta, eps, pad_id, out=None):
+    _chk(ids, torch.int32, "ids", 2)
+    for n, t in (("word_emb", word_emb), ("pos_emb", pos_emb), ("type_emb", type_emb), ("gamma", gamma),
+                 ("beta", beta)):
+        _chk(t, torch.float32, n)
+    R, S = ids.shape
+    V, H = word_emb.shape
+    P = pos_emb.shape[0]
+    if out is None:
+        out = torch.empty((R * S, H), dtype=torch.bfloat16, device=ids.device)
+    _lib.check(_lib.load().kbner_embed_ln_fwd(_ptr(ids), _ptr(word_emb), _ptr(pos_emb), _ptr(type_emb), _ptr(gamma),
+                                              _ptr(beta), float(eps), int(pad_id), R, S, H, V, P, _ptr(out),
+                                              _stream()), "embed_ln_fwd")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, out=None, save_stats=False):
+    _chk(x, torch.float32, "x", 2)
+    _chk(gamma, torch.float32, "gamma", 1)
+    _chk(beta, torch.float32, "beta", 1)
+    M, H = x.shape
+    if out is None:
+        out = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().kbner_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), M, H, _ptr(out),
+                                               _ptr(mean), _ptr(rstd), _stream()), "layernorm_fwd")
+    return (out, mean, rstd) if save_stats else out
+
+
+def gather_tagproj_fwd(hidden, row_of, first_idx, W, bias, S, drop_keep=None):
+    _chk(hidden, torch.bfloat16, "hidden", 2)
+    _chk(row_of, torch.int32, "row_of", 1)
+    _chk(first_idx, torch.int32, "first_idx", 2)
+    _chk(W, torch.float32, "W", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(drop_keep, torch.uint8, "drop_keep", 1)
+    B, T = first_idx.shape
+    L, H = W.shape
+    logits = torch.empty((B, T, L), dtype=torch.float32, device=hidden.device)
+    _lib.check(_lib.load().kbner_gather_tagproj_fwd(_ptr(hidden), _ptr(row_of), _ptr(first_idx), _ptr(drop_keep),
+                                                    _ptr(W), _ptr(bias), B, T, int(S), H, L, _ptr(logits),
+                                                    _stream()), "gather_tagproj_fwd")
+    return logits
+
+
+def gemm_bf16_tn(A, B, bias=None, residual=None, epilogue=EPI_BIAS, out=None):
+    """C[M,N] = epilogue(A[M,K] @ B[N,K]^T).  bf16 out for EPI_BIAS / EPI_BIAS_GELU, fp32 otherwise."""
+    _chk(A, torch.bfloat16, "A", 2)
+    _chk(B, torch.bfloat16, "B", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(residual, torch.bfloat16, "residual", 2)
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise _lib.KbnerError("gemm: K mismatch %d vs %d" % (K, K2))
+    odt = torch.bfloat16 if epilogue in (EPI_BIAS, EPI_BIAS_GELU) else torch.float32
+    if out is None:
+        out = torch.empty((M, N), dtype=odt, device=A.device)
+    else:
+        _chk(out, odt, "out", 2)
+    _lib.check(_lib.load().kbner_gemm_bf16_tn(_ptr(A), _ptr(B), _ptr(bias), _ptr(residual), _ptr(out), M, N, K,
+                                              K, K, N, int(epilogue), _stream()), "gemm_bf16_tn")
+    return out
+
+
+def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False):
+    _chk(qkv, torch.bfloat16, "qkv", 2)
+    _chk(key_len, torch.int32, "key_len", 1)
+    H = heads * 64
+    if qkv.shape != (R * S, 3 * H):
+        raise _lib.KbnerError("attention: qkv must be [R*S, 3*H] = [%d, %d], got %s" % (R * S, 3 * H, tuple(qkv.shape)))
+    if out is None:
+        out = torch.empty((R * S, H), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device) if want_lse else None
+    _lib.check(_lib.load().kbner_attention_fwd(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), _ptr(lse),
+                                               _stream()), "attention_fwd")
+    return (out, lse) if want_lse else out
