@@ -64,20 +64,21 @@ int kbner_crf_viterbi(const float *emis /*[B,T,L]*/, const int32_t *pos /*[B,T] 
 
 /* log-partition + gold-path score of every sentence.
  * Replaces _forward_alg (:1329-1394) and FastSequenceTagger._score_sentence (:2544-2591).
- * alpha (optional, [B,T,L], compacted time index) is what crf_nll_bwd consumes. */
+ * alpha / alpha_scale (optional, together; compacted time index) are what crf_nll_bwd consumes:
+ * alpha_t[j] = alpha_scale[b][t] (fp64) + alpha[b][t][j] (fp32, max_j = 0). */
 int kbner_crf_nll_fwd(const float *emis /*[B,T,L]*/, const int32_t *tags /*[B,T]*/,
                       const int32_t *pos /*[B,T] or NULL*/, const int32_t *klen /*[B]*/,
                       const float *trans /*[L,L]*/, int B, int T, int L,
                       int start_idx, int stop_idx,
                       float *logz /*[B]*/, float *gold /*[B]*/, float *alpha /*[B,T,L] or NULL*/,
-                      void *stream);
+                      double *alpha_scale /*[B,T] or NULL*/, void *stream);
 
 /* Gradient of sum_b w[b]*(logZ_b - gold_b): what autograd derives from the two functions
  * above (loss = mean, :2499-2506, means w[b] = 1/B).  d_emis is fully written (zeros at
  * un-kept positions); d_trans is ACCUMULATED into (caller zeroes it). */
 int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const int32_t *pos,
                       const int32_t *klen, const float *trans, const float *alpha,
-                      const float *logz, const float *w /*[B]*/, int B, int T, int L,
+                      const double *alpha_scale, const float *w /*[B]*/, int B, int T, int L,
                       int start_idx, int stop_idx,
                       float *d_emis /*[B,T,L]*/, float *d_trans /*[L,L]*/, void *stream);
 

@@ -19,7 +19,7 @@ SIGNATURES = {
     "kbner_launch_count": ([], ctypes.c_uint64),
     "kbner_crf_compact": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "kbner_crf_viterbi": ([_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p] * 3, _c_int),
-    "kbner_crf_nll_fwd": ([_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p] * 4, _c_int),
+    "kbner_crf_nll_fwd": ([_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p] * 5, _c_int),
     "kbner_crf_nll_bwd": ([_c_void_p] * 8 + [_c_int] * 5 + [_c_void_p] * 3, _c_int),
     "kbner_embed_ln_fwd": ([_c_void_p] * 6 + [_c_float, _c_int] + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
     "kbner_layernorm_fwd": ([_c_void_p] * 3 + [_c_float, _c_int, _c_int] + [_c_void_p] * 4, _c_int),

@@ -189,17 +189,21 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
 
 // ------------------------------------------------------------------------------------------
 // log Z and gold score.  The reference evaluates alpha'[j] = max_k x + log sum_k exp(x - max),
-// x = (e[j] + A[j][k]) + alpha[k]  (L^2 exps per step).  Here the same quantity is evaluated as
-//   alpha'[j] = e[j] + rmax_j + M + log sum_k E[j][k] * exp(alpha[k] - M),
-// E[j][k] = exp(A[j][k] - rmax_j), M = max_k alpha[k]: one exp per lane per step and an FMA per
-// pair; differs from the reference by fp32 rounding only (tests: 1e-5 relative).
+// x = (e[j] + A[j][k]) + alpha[k]  (L^2 exps per step).  Here the same quantity is carried in a
+// normalised form  alpha_t[j] = S_t + ahat_t[j],  max_j ahat_t[j] = 0,  S_t accumulated in fp64:
+//   r[j]        = e[j] + rmax_j + log sum_k E[j][k] * exp(ahat[k]),   E[j][k] = exp(A[j][k] - rmax_j)
+//   ahat'[j]    = r[j] - max_j r[j],      S' = S + max_j r[j]
+// one exp per lane per step and an FMA per pair.  Keeping the O(T) magnitude in a separate fp64
+// scalar is what keeps the marginals of the backward pass accurate at T = 512 (alpha ~ 2000 would
+// otherwise carry ~1e-4 absolute error per step into exp(alpha + beta - logZ)).
 // ------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(128)
 crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
                    const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
                    const float *__restrict__ trans, int B, int T, int L, int start, int stop,
-                   float *__restrict__ logz, float *__restrict__ gold, float *__restrict__ alpha_out) {
+                   float *__restrict__ logz, float *__restrict__ gold, float *__restrict__ alpha_out,
+                   double *__restrict__ ascale_out) {
     constexpr int SPW = 32 / G;
     const int W = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,7 +222,8 @@ crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
     for (int k = 0; k < G; ++k) E[k] = (j < L && k < L) ? expf(trans[j * L + k] - rmax) : 0.0f;
     if (j >= L) rmax = 0.0f;
 
-    float a = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
+    float a = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;   // ahat_0 (max = 0)
+    double S = 0.0;
     constexpr int U = 4;
     float e_cur[U], e_nxt[U];
     auto load_block = [&](int i0, float (&dst)[U]) {
@@ -240,15 +245,17 @@ crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
         for (int u = 0; u < U; ++u) {
             const int i = i0 + u;
             if (i < nmax) {
-                const float M = group_max<G>(a);
-                const float p = expf(a - M);
+                const float p = expf(a);
                 float s = 0.0f;
 #pragma unroll
                 for (int k = 0; k < G; ++k) s = fmaf(E[k], __shfl_sync(0xffffffffu, p, k, G), s);
-                const float an = (e_cur[u] + rmax) + (M + logf(s));
+                const float r = (j < L) ? (e_cur[u] + rmax) + logf(s) : -CUDART_INF_F;
+                const float m = group_max<G>(r);
                 if (i < n) {
-                    a = an;
+                    a = r - m;
+                    S += (double)m;
                     if (alpha_out && j < L) alpha_out[(rowbase + i) * L + j] = a;
+                    if (ascale_out && j == 0) ascale_out[rowbase + i] = S;
                 }
             }
         }
@@ -278,23 +285,23 @@ crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
             const int tl = pos ? pos[rowbase + n - 1] : n - 1;
             last = tags[rowbase + tl];
         }
-        logz[b] = M2 + logf(s2);
+        logz[b] = (float)(S + (double)M2 + (double)logf(s2));
         gold[b] = g + trans[stop * L + last];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// gradient of sum_b w[b] (logZ_b - gold_b).  Reverse (beta) recursion in the same scaled form;
-// unary marginals -> d_emis, pairwise marginals accumulated per lane as
-//   acc[j][k] += c * q_j * a_k   (dT[j][k] = E[j][k] * acc[j][k]),
-// persistent over sentences, reduced through shared memory, one global atomic set per block.
+// gradient of sum_b w[b] (logZ_b - gold_b).  Reverse (beta) recursion in the same normalised form
+// (beta_t = Sb_t + bhat_t, Sb in fp64); unary marginals -> d_emis, pairwise marginals accumulated
+// per lane as  acc[j][k] += c * q_j * a_k   (dT[j][k] = E[j][k] * acc[j][k]), persistent over
+// sentences, reduced through shared memory, one global atomic set per block.
 // ------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(128)
 crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
                    const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
                    const float *__restrict__ trans, const float *__restrict__ alpha,
-                   const float *__restrict__ logz, const float *__restrict__ w, int B, int T, int L,
+                   const double *__restrict__ ascale, const float *__restrict__ w, int B, int T, int L,
                    int start, int stop, float *__restrict__ d_emis, float *__restrict__ d_trans) {
     __shared__ float s_dt[32 * 32];
     constexpr int SPW = 32 / G;
@@ -333,26 +340,35 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
         const int n = valid ? klen[b] : 0;
         const int nmax = warp_max_int(n);
         const size_t rowbase = (size_t)(valid ? b : 0) * T;
-        const float lz = valid ? logz[b] : 0.0f;
         const float wb = valid ? w[b] : 0.0f;
         if (nmax == 0) continue;   // warp-uniform
 
-        float beta = (j < L) ? trans[stop * L + j] : -CUDART_INF_F;   // beta_n[k] = A[STOP][k]
+        // beta_n[k] = A[STOP][k], normalised; logZ re-derived in fp64 from the stored alpha
+        const float astop = (j < L) ? trans[stop * L + j] : -CUDART_INF_F;
+        const float mb0 = group_max<G>(astop);
+        float beta = astop - mb0;                                   // bhat_n
+        double Sb = (double)mb0;
+        const float a_n = (n > 0 && j < L) ? alpha[(rowbase + n - 1) * L + j] : -CUDART_INF_F;
+        const double Sa_n = (n > 0) ? ascale[rowbase + n - 1] : 0.0;
+        const float xt = (j < L) ? a_n + astop : -CUDART_INF_F;
+        const float Mt = group_max<G>(xt);
+        const float st = group_sum<G>(expf(xt - Mt));
+        const double lz = Sa_n + (double)Mt + (double)logf(st);
         // terminal pairwise term: dT[STOP][k] += w * exp(alpha_n[k] + A[STOP][k] - logZ)
-        if (n > 0 && j < L) {
-            const float an = alpha[(rowbase + n - 1) * L + j];
-            atomicAdd(&s_dt[stop * L + j], wb * expf(an + beta - lz));
-        }
+        if (n > 0 && j < L) atomicAdd(&s_dt[stop * L + j], wb * expf(xt - Mt) / st);
         for (int i = nmax - 1; i >= 0; --i) {
             const bool act = i < n;
             float e = 0.0f, anext = -CUDART_INF_F, aprev = -CUDART_INF_F;
+            double Sa_next = 0.0, Sa_prev = 0.0;
             int t = 0, y = -1, yprev = start;
             if (act) {
                 t = pos ? pos[rowbase + i] : i;
                 y = tags[rowbase + t];
+                Sa_next = ascale[rowbase + i];
                 if (i > 0) {
                     const int tp = pos ? pos[rowbase + i - 1] : i - 1;
                     yprev = tags[rowbase + tp];
+                    Sa_prev = ascale[rowbase + i - 1];
                 }
                 if (j < L) {
                     e = emis[(rowbase + t) * L + j];
@@ -360,17 +376,17 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
                     aprev = (i > 0) ? alpha[(rowbase + i - 1) * L + j] : ((j == start) ? 0.0f : kNeg);
                 }
             }
-            // unary marginal
+            // unary marginal: exp(ahat_{i+1}[j] + bhat_{i+1}[j] + (Sa_{i+1} + Sb_{i+1} - logZ))
             if (act && j < L) {
-                const float pj = expf(anext + beta - lz);
+                const float off = (float)(Sa_next + Sb - lz);
+                const float pj = expf(anext + beta + off);
                 d_emis[(rowbase + t) * L + j] = wb * (pj - ((j == y) ? 1.0f : 0.0f));
             }
             const float u = (j < L && act) ? (e + beta + rmax) : -CUDART_INF_F;
             const float Mb = group_max<G>(u);
-            const float Ma = group_max<G>(aprev);
             const float q = (act && j < L) ? expf(u - Mb) : 0.0f;
-            const float av = (act && j < L) ? expf(aprev - Ma) : 0.0f;
-            const float c = act ? wb * expf(fminf(Ma + Mb - lz, 80.0f)) : 0.0f;
+            const float av = (act && j < L) ? expf(aprev) : 0.0f;      // ahat is normalised: max = 0
+            const float c = act ? wb * expf(fminf((float)(Sa_prev + Sb + (double)Mb - lz), 80.0f)) : 0.0f;
             const float cq = c * q;
             float s = 0.0f;
 #pragma unroll
@@ -378,7 +394,12 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
                 acc[k] = fmaf(cq, __shfl_sync(0xffffffffu, av, k, G), acc[k]);
                 s = fmaf(Ecol[k], __shfl_sync(0xffffffffu, q, k, G), s);
             }
-            if (act) beta = Mb + logf(s);
+            const float tk = (j < L) ? logf(s) : -CUDART_INF_F;
+            const float mt = group_max<G>(tk);
+            if (act) {
+                beta = tk - mt;
+                Sb += (double)Mb + (double)mt;
+            }
             // gold transition count
             if (act && j == 0) atomicAdd(&s_dt[y * L + yprev], -wb);
         }
@@ -465,21 +486,22 @@ extern "C" int kbner_crf_viterbi(const float *emis, const int32_t *pos, const in
 extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const int32_t *pos,
                                  const int32_t *klen, const float *trans, int B, int T, int L,
                                  int start_idx, int stop_idx, float *logz, float *gold, float *alpha,
-                                 void *stream) {
+                                 double *alpha_scale, void *stream) {
     KBNER_CHECK_ARG(emis && tags && klen && trans && logz && gold, "crf_nll_fwd: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_fwd: need L in [2,32], got %d", L);
     KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,
                     "crf_nll_fwd: start/stop index out of range");
+    KBNER_CHECK_ARG((alpha == nullptr) == (alpha_scale == nullptr), "crf_nll_fwd: alpha and alpha_scale go together");
     if (B == 0) return KBNER_OK;
     const int W = 4;
     cudaStream_t st = (cudaStream_t)stream;
     if (L <= 16) {
         const int per_block = W * 2;
         crf_nll_fwd_kernel<16><<<(B + per_block - 1) / per_block, W * 32, 0, st>>>(
-            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha);
+            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha, alpha_scale);
     } else {
         crf_nll_fwd_kernel<32><<<(B + W - 1) / W, W * 32, 0, st>>>(
-            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha);
+            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha, alpha_scale);
     }
     KBNER_CHECK_LAUNCH("crf_nll_fwd");
     return KBNER_OK;
@@ -487,10 +509,10 @@ extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const i
 
 extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const int32_t *pos,
                                  const int32_t *klen, const float *trans, const float *alpha,
-                                 const float *logz, const float *w, int B, int T, int L,
+                                 const double *alpha_scale, const float *w, int B, int T, int L,
                                  int start_idx, int stop_idx, float *d_emis, float *d_trans,
                                  void *stream) {
-    KBNER_CHECK_ARG(emis && tags && klen && trans && alpha && logz && w && d_emis && d_trans,
+    KBNER_CHECK_ARG(emis && tags && klen && trans && alpha && alpha_scale && w && d_emis && d_trans,
                     "crf_nll_bwd: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_bwd: need L in [2,32], got %d", L);
     if (B == 0) return KBNER_OK;
@@ -505,10 +527,10 @@ extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const i
     int blocks = (B + W * spw - 1) / (W * spw);
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;   // persistent over sentences beyond that
     if (L <= 16)
-        crf_nll_bwd_kernel<16><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, logz, w,
+        crf_nll_bwd_kernel<16><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, alpha_scale, w,
                                                           B, T, L, start_idx, stop_idx, d_emis, d_trans);
     else
-        crf_nll_bwd_kernel<32><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, logz, w,
+        crf_nll_bwd_kernel<32><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, alpha_scale, w,
                                                           B, T, L, start_idx, stop_idx, d_emis, d_trans);
     KBNER_CHECK_LAUNCH("crf_nll_bwd");
     return KBNER_OK;

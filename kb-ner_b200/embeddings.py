@@ -1,0 +1,343 @@
+"""``TransformerWordEmbeddings`` / ``StackedEmbeddings`` on the B200 encoder.
+
+Mirror of ``/root/reference/flair/embeddings.py``: ``TransformerWordEmbeddings`` (:2906-3416, same constructor
+keywords and attribute surface), ``Embeddings.embed`` (:75-101), ``assign_batch_features`` (:108-124) and
+``StackedEmbeddings`` (:155-211).  What changes is where the work happens:
+
+* sub-tokenisation and the word -> first-sub-token map are host logic (cached per sentence -- the reference
+  re-tokenises every word on every call, :3103-3109);
+* the encoder runs on the sm_100a kernels (``encoder.XLMRobertaEncoderB200``), once per batch, producing only
+  the last hidden state;
+* word pooling is *not* a Python loop over tokens with a ``.cpu()`` round trip (:3288-3345, :122): the batch
+  keeps an ``EncodedBatch`` (device hidden state + index tensors) and the tagger fuses gather + word dropout
+  + projection into one kernel.  Per-token ``Token._embeddings`` vectors are materialised only on request
+  (``materialize_token_embeddings``), which is what ``embeddings_storage_mode='none'`` configs never need.
+
+Target configs use ``layers='-1'``, ``pooling_operation='first'`` (config/*.yaml embeddings block); other
+values raise instead of silently computing something else.
+"""
+import re
+from typing import List, Optional
+
+import torch
+
+from .data import BatchedData
+from .encoder import EncoderConfig, XLMRobertaEncoderB200
+
+
+class SyntheticTokenizer:
+    """Deterministic stand-in for the SentencePiece tokenizer (no tokenizer files exist offline).
+
+    SentencePiece-style surface: words are split into pieces of <= ``piece_len`` characters, the first piece
+    of every word carries the U+2581 prefix; ids are a stable hash into [3, vocab).  Exposes exactly the
+    members the reference touches (embeddings.py:2951-2966, :3139-3181)."""
+
+    bos_token, eos_token, pad_token, unk_token = "<s>", "</s>", "<pad>", "<unk>"
+    _bos_token, _eos_token, _sep_token, _cls_token = "<s>", "</s>", "</s>", "<s>"
+    bos_token_id, pad_token_id, eos_token_id, unk_token_id = 0, 1, 2, 3
+
+    def __init__(self, vocab_size=250002, piece_len=4, model_max_length=512):
+        self.vocab_size = vocab_size
+        self.piece_len = piece_len
+        self.model_max_length = model_max_length
+
+    def tokenize(self, text: str) -> List[str]:
+        out = []
+        for w in text.split():
+            if w in (self.eos_token, self.bos_token):
+                out.append(w)
+                continue
+            for i in range(0, len(w), self.piece_len):
+                out.append(("▁" if i == 0 else "") + w[i:i + self.piece_len])
+        return out
+
+    def convert_tokens_to_ids(self, tokens: List[str]) -> List[int]:
+        ids = []
+        for t in tokens:
+            if t == self.eos_token:
+                ids.append(self.eos_token_id)
+            elif t == self.bos_token:
+                ids.append(self.bos_token_id)
+            else:
+                h = 2166136261
+                for ch in t.encode("utf-8"):
+                    h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+                ids.append(4 + h % (self.vocab_size - 4))
+        return ids
+
+
+def _strip_markup(piece: str) -> str:
+    """Sub-token -> surface text (the markers the reference strips, embeddings.py:3093-3101)."""
+    piece = re.sub("^Ġ", "", piece)
+    piece = re.sub("^##", "", piece)
+    piece = re.sub("^▁", "", piece)
+    return re.sub("</w>$", "", piece)
+
+
+class EncodedBatch:
+    """Device-side result of embedding one batch: what the fused pooling kernel consumes."""
+
+    def __init__(self, hidden, S, row_of, first_idx, lengths, key_len, ids):
+        self.hidden = hidden          # [R*S, H] bf16
+        self.S = S
+        self.row_of = row_of          # [B] int32: window row that starts each sentence
+        self.first_idx = first_idx    # [B,T] int32: sub-token index (row-relative, may span rows) or -1
+        self.lengths = lengths        # python list of word counts
+        self.key_len = key_len
+        self.ids = ids
+
+
+class TransformerWordEmbeddings(torch.nn.Module):
+    def __init__(self, model="xlm-roberta-large", layers: str = "-1", pooling_operation: str = "first",
+                 batch_size: int = 1, use_scalar_mix: bool = False, fine_tune: bool = False,
+                 allow_long_sentences: bool = True, stride: int = -1, maximum_window: bool = False,
+                 document_extraction: bool = False, embedding_name: Optional[str] = None, doc_batch_size: int = 32,
+                 maximum_subtoken_length: int = 999, v2_doc: bool = False, ext_doc: bool = False,
+                 sentence_feat: bool = False, use_internal_doc: bool = False, tokenizer=None, config=None,
+                 device=None, **kwargs):
+        super().__init__()
+        if pooling_operation != "first" or [int(x) for x in str(layers).split(",")] != [-1]:
+            raise NotImplementedError("kbner_b200 implements the KB-NER configuration: layers='-1', "
+                                      "pooling_operation='first' (got layers=%r pooling=%r)" % (layers, pooling_operation))
+        if document_extraction or v2_doc or ext_doc or use_internal_doc or sentence_feat or use_scalar_mix:
+            raise NotImplementedError("document-context / sentence_feat / scalar-mix variants are outside the hot path")
+        self.device_ = torch.device(device if device is not None else "cuda")
+        # ---- encoder + tokenizer ---------------------------------------------------------------
+        if isinstance(model, XLMRobertaEncoderB200):
+            self.model = model
+            name = model.config.name
+        else:
+            name = str(model)
+            if config is None:
+                import os
+                if os.path.isdir(name) and os.path.exists(os.path.join(name, "config.json")):
+                    self.model = XLMRobertaEncoderB200.from_pretrained(name)
+                else:
+                    config = EncoderConfig.xlmr_base() if "base" in name else EncoderConfig.xlmr_large()
+                    config.name = name
+            if not hasattr(self, "model"):
+                with torch.device(self.device_):
+                    self.model = XLMRobertaEncoderB200(config)
+        self.model.to(self.device_)
+        if tokenizer is None:
+            try:
+                from transformers import AutoTokenizer
+                tokenizer = AutoTokenizer.from_pretrained(name, local_files_only=True, **kwargs)
+            except Exception as e:       # no tokenizer files offline: say so, do not guess silently
+                raise RuntimeError("no tokenizer files for %r are available locally (%s); pass tokenizer=... "
+                                   "(e.g. kbner_b200.embeddings.SyntheticTokenizer for synthetic data)" % (name, e))
+        self.tokenizer = tokenizer
+        # ---- the attribute surface the reference's callers read -------------------
+        self.allow_long_sentences = allow_long_sentences
+        mml = min(getattr(tokenizer, "model_max_length", 512) or 512, 512)
+        self.max_subtokens_sequence_length = mml
+        self.stride = mml // 2 if allow_long_sentences else 0
+        if allow_long_sentences and stride != -1:
+            if not maximum_window:
+                self.max_subtokens_sequence_length = stride * 2
+            self.stride = stride
+        self.name = str(name) if embedding_name is None else embedding_name
+        self.layer_indexes = [-1]
+        self.pooling_operation = pooling_operation
+        self.use_scalar_mix = use_scalar_mix
+        self.fine_tune = fine_tune
+        self.static_embeddings = not fine_tune
+        self.batch_size = batch_size
+        self.sentence_feat = sentence_feat
+        self.use_internal_doc = use_internal_doc
+        self.document_extraction = document_extraction
+        self.v2_doc, self.ext_doc = v2_doc, ext_doc
+        self.doc_batch_size = doc_batch_size
+        self.begin_offset = 1
+        self.maximum_subtoken_length = maximum_subtoken_length
+        self.embedding_type = "word-level"
+        self._tok_cache = {}
+        self.model.eval()
+
+    @property
+    def embedding_length(self) -> int:
+        return len(self.layer_indexes) * self.model.config.hidden_size
+
+    def train(self, mode=True):
+        # not fine-tuning ("feature-based"): never in training mode (embeddings.py:3410-3416)
+        if self.fine_tune:
+            super().train(mode)
+        return self
+
+    # ---- host logic: sub-tokenisation -----------------------------------------------------------
+    def _eos_text(self):
+        eos = getattr(self.tokenizer, "_eos_token", None) or getattr(self.tokenizer, "_sep_token", None)
+        return getattr(eos, "content", eos)
+
+    def _word_text(self, text: str) -> str:
+        return "".join(_strip_markup(p) for p in self.tokenizer.tokenize(text)).lower()
+
+    def subtokenize(self, sentence):
+        """-> (sub-token ids without specials, n_sub per word).  '<EOS>' words become the tokenizer's EOS
+        (embeddings.py:3139-3163); words are matched to sub-tokens by reconstructing their surface text
+        (:3347-3408); words longer than maximum_subtoken_length are cut (:3183-3197)."""
+        words = [t.text for t in sentence.tokens]
+        key = tuple(words)
+        hit = self._tok_cache.get(key)
+        if hit is not None:
+            return hit
+        eos = self._eos_text()
+        words = [eos if (w == "<EOS>" and eos) else w for w in words]
+        pieces = self.tokenizer.tokenize(" ".join(words))
+        n_sub, wi, acc, cnt = [], 0, "", 0
+        targets = [self._word_text(w) for w in words]
+        for pc in pieces:
+            surface = _strip_markup(pc).lower()
+            # tokenizers may drop a word entirely: it gets 0 sub-tokens (zero vector later)
+            while wi < len(words) and cnt == 0 and not targets[wi].startswith(surface):
+                n_sub.append(0)
+                wi += 1
+            if wi >= len(words):
+                break
+            acc += surface
+            cnt += 1
+            if acc == targets[wi]:
+                n_sub.append(cnt)
+                wi, acc, cnt = wi + 1, "", 0
+        while len(n_sub) < len(words):
+            n_sub.append(cnt)
+            cnt = 0
+        if any(n > self.maximum_subtoken_length for n in n_sub):
+            kept, i = [], 0
+            for n in n_sub:
+                kept += pieces[i:i + min(n, self.maximum_subtoken_length)]
+                i += n
+            pieces = kept
+            n_sub = [min(n, self.maximum_subtoken_length) for n in n_sub]
+        ids = self.tokenizer.convert_tokens_to_ids(pieces)
+        out = (ids, n_sub)
+        if len(self._tok_cache) < 200000:
+            self._tok_cache[key] = out
+        return out
+
+    def windows(self, n_ids: int):
+        """Window starts for a sentence of n_ids sub-tokens: [<s>] ids[start:start+W-2] [</s>] with overlap
+        `stride` (encode_plus(max_length, stride, return_overflowing_tokens), embeddings.py:3203-3227)."""
+        cap = self.max_subtokens_sequence_length - 2
+        starts = [0]
+        if self.allow_long_sentences:
+            while starts[-1] + cap < n_ids:
+                starts.append(starts[-1] + cap - self.stride)
+        return starts, cap
+
+    def build_batch(self, sentences):
+        """Host side of _add_embeddings_to_sentences (:3135-3260): ids / key_len / first-sub-token map.
+        The reference pads input_ids with 0 (:3247-3251); so do we (pads are masked as keys)."""
+        tok = self.tokenizer
+        bos, eos = getattr(tok, "bos_token_id", 0), getattr(tok, "eos_token_id", 2)
+        rows, row_of, firsts, lengths = [], [], [], []
+        for s in sentences:
+            ids, n_sub = self.subtokenize(s)
+            starts, cap = self.windows(len(ids))
+            if not self.allow_long_sentences:
+                ids = ids[:cap]
+            row_of.append(len(rows))
+            for st in starts:
+                rows.append([bos] + ids[st:st + cap] + [eos])
+            # stitched index of sub-token g: window w owns [own_lo, own_hi) after dropping stride//2 (+1 special)
+            # on each inner edge (:3292-3299); index is expressed relative to the sentence's first row.
+            half = self.stride // 2
+            fi, g = [], 0
+            for n in n_sub:
+                if n == 0 or g >= len(ids):
+                    fi.append(-1)
+                else:
+                    w = 0
+                    while w + 1 < len(starts) and g >= starts[w + 1] + half:
+                        w += 1
+                    fi.append((w, 1 + g - starts[w]))
+                g += n
+            firsts.append(fi)
+            lengths.append(len(s.tokens))
+        S = max(len(r) for r in rows)
+        R, B, T = len(rows), len(sentences), max(lengths)
+        ids_t = torch.zeros((R, S), dtype=torch.int32)
+        key_len = torch.zeros((R,), dtype=torch.int32)
+        for r, row in enumerate(rows):
+            ids_t[r, :len(row)] = torch.tensor(row, dtype=torch.int32)
+            key_len[r] = len(row)
+        first_idx = torch.full((B, T), -1, dtype=torch.int32)
+        for b, fi in enumerate(firsts):
+            for t, v in enumerate(fi):
+                if v != -1:
+                    first_idx[b, t] = v[0] * S + v[1]     # rows of one sentence are consecutive
+        return ids_t, key_len, torch.tensor(row_of, dtype=torch.int32), first_idx, lengths, S
+
+    # ---- device side ----------------------------------------------------------------------------------
+    def encode(self, sentences) -> EncodedBatch:
+        ids, key_len, row_of, first_idx, lengths, S = self.build_batch(sentences)
+        dev = self.device_
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        ids_d = pin(ids).to(dev, non_blocking=True)
+        key_d = pin(key_len).to(dev, non_blocking=True)
+        row_d = pin(row_of).to(dev, non_blocking=True)
+        first_d = pin(first_idx).to(dev, non_blocking=True)
+        hidden = self.model.forward_hidden(ids_d, key_d)
+        return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d)
+
+    def embed(self, sentences):
+        """Embeddings.embed (:75-101): afterwards ``sentences.features[self.name]`` holds the batch.  Here the
+        feature is an EncodedBatch (device resident) instead of a padded [B,T,D] CPU tensor."""
+        if not isinstance(sentences, (list, BatchedData)):
+            sentences = [sentences]
+        if not hasattr(sentences, "features"):
+            sentences = BatchedData(sentences)
+        if (not self.fine_tune) and self.name in sentences.features:
+            return sentences
+        sentences.features[self.name] = self.encode(sentences)
+        return sentences
+
+    def materialize_token_embeddings(self, sentences):
+        """Optional: write per-token vectors into Token._embeddings (what :3343 does for every token)."""
+        enc = sentences.features[self.name]
+        H = self.embedding_length
+        hid = enc.hidden.float()
+        for b, s in enumerate(sentences):
+            base = int(enc.row_of[b]) * enc.S
+            for t, tok in enumerate(s.tokens):
+                fi = int(enc.first_idx[b, t])
+                tok.set_embedding(self.name, hid[base + fi].clone() if fi >= 0 else torch.zeros(H, device=hid.device))
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["tokenizer"] = None if not isinstance(self.tokenizer, SyntheticTokenizer) else self.tokenizer
+        state["_tok_cache"] = {}
+        return state
+
+    def __setstate__(self, d):
+        self.__dict__ = d
+        if self.tokenizer is None:
+            from transformers import AutoTokenizer
+            self.tokenizer = AutoTokenizer.from_pretrained(self.name.split("/")[-1])
+
+    def extra_repr(self):
+        return "model=%s" % self.name
+
+
+class StackedEmbeddings(torch.nn.Module):
+    """flair/embeddings.py:155-211: the tagger always receives a stack, here of exactly one member."""
+
+    def __init__(self, embeddings: List[TransformerWordEmbeddings]):
+        super().__init__()
+        if len(embeddings) != 1:
+            raise NotImplementedError("the KB-NER configs stack exactly one TransformerWordEmbeddings")
+        self.embeddings = embeddings
+        for i, e in enumerate(embeddings):
+            self.add_module("list_embedding_%d" % i, e)
+        self.name = "Stack"
+        self.static_embeddings = all(e.static_embeddings for e in embeddings)
+        self.embedding_type = embeddings[0].embedding_type
+        self.embedding_length = sum(e.embedding_length for e in embeddings)
+
+    def embed(self, sentences, static_embeddings: bool = True, embedding_mask=None):
+        for e in self.embeddings:
+            sentences = e.embed(sentences)
+        return sentences
+
+    def forward(self, sentences):
+        return self.embed(sentences)

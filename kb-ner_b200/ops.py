@@ -59,7 +59,7 @@ def crf_viterbi(emis, trans, klen, slen, start_idx, stop_idx, x_idx=0, pos=None)
 
 
 def crf_nll_fwd(emis, tags, trans, klen, start_idx, stop_idx, pos=None, want_alpha=False):
-    """Returns (logz [B], gold [B], alpha [B,T,L] or None)."""
+    """Returns (logz [B], gold [B], alpha) ; alpha = (ahat [B,T,L] f32, scale [B,T] f64) or None."""
     _chk(emis, torch.float32, "emis", 3)
     _chk(tags, torch.int32, "tags", 2)
     _chk(trans, torch.float32, "trans", 2)
@@ -68,23 +68,25 @@ def crf_nll_fwd(emis, tags, trans, klen, start_idx, stop_idx, pos=None, want_alp
     B, T, L = emis.shape
     logz = torch.empty((B,), dtype=torch.float32, device=emis.device)
     gold = torch.empty((B,), dtype=torch.float32, device=emis.device)
-    alpha = torch.empty((B, T, L), dtype=torch.float32, device=emis.device) if want_alpha else None
+    ahat = torch.empty((B, T, L), dtype=torch.float32, device=emis.device) if want_alpha else None
+    scale = torch.empty((B, T), dtype=torch.float64, device=emis.device) if want_alpha else None
     _lib.check(_lib.load().kbner_crf_nll_fwd(_ptr(emis), _ptr(tags), _ptr(pos), _ptr(klen), _ptr(trans), B, T, L,
-                                             int(start_idx), int(stop_idx), _ptr(logz), _ptr(gold), _ptr(alpha),
-                                             _stream()), "crf_nll_fwd")
-    return logz, gold, alpha
+                                             int(start_idx), int(stop_idx), _ptr(logz), _ptr(gold), _ptr(ahat),
+                                             _ptr(scale), _stream()), "crf_nll_fwd")
+    return logz, gold, ((ahat, scale) if want_alpha else None)
 
 
-def crf_nll_bwd(emis, tags, trans, klen, alpha, logz, w, start_idx, stop_idx, pos=None):
-    """Returns (d_emis [B,T,L], d_trans [L,L]) of sum_b w[b]*(logZ_b - gold_b)."""
-    _chk(alpha, torch.float32, "alpha", 3)
-    _chk(logz, torch.float32, "logz", 1)
+def crf_nll_bwd(emis, tags, trans, klen, alpha, w, start_idx, stop_idx, pos=None):
+    """Returns (d_emis [B,T,L], d_trans [L,L]) of sum_b w[b]*(logZ_b - gold_b); alpha from crf_nll_fwd."""
+    ahat, scale = alpha
+    _chk(ahat, torch.float32, "alpha", 3)
+    _chk(scale, torch.float64, "alpha_scale", 2)
     _chk(w, torch.float32, "w", 1)
     B, T, L = emis.shape
     d_emis = torch.empty_like(emis)
     d_trans = torch.zeros((L, L), dtype=torch.float32, device=emis.device)
-    _lib.check(_lib.load().kbner_crf_nll_bwd(_ptr(emis), _ptr(tags), _ptr(pos), _ptr(klen), _ptr(trans), _ptr(alpha),
-                                             _ptr(logz), _ptr(w), B, T, L, int(start_idx), int(stop_idx),
+    _lib.check(_lib.load().kbner_crf_nll_bwd(_ptr(emis), _ptr(tags), _ptr(pos), _ptr(klen), _ptr(trans), _ptr(ahat),
+                                             _ptr(scale), _ptr(w), B, T, L, int(start_idx), int(stop_idx),
                                              _ptr(d_emis), _ptr(d_trans), _stream()), "crf_nll_bwd")
     return d_emis, d_trans
 

@@ -1,0 +1,363 @@
+"""``SequenceTagger`` / ``FastSequenceTagger`` on the B200 kernels.
+
+Mirror of ``/root/reference/flair/models/sequence_tagger_model.py`` for the KB-NER configuration
+(``use_crf=True, use_rnn=False``): same constructor keywords (:100-163), same methods and attribute names
+(SURVEY.md 8(b)), same arithmetic (Appendix A) -- executed as
+
+    forward            :844-1052   first-sub-token gather + WordDropout + Linear   -> 1 kernel
+    _calculate_loss    :2426-2539  remove-X compaction + log Z + gold score         -> 2 kernels (+1 backward)
+    _obtain_labels     :1157-1246  per-sentence Viterbi + S-X padding               -> 1 kernel for the batch
+    _viterbi_decode    :1248-1327  kept for callers that decode one sentence
+
+instead of Python loops over sentences and tokens with a ``.item()`` sync per token (:1296-1300).
+"""
+import logging
+import time
+from typing import List, Optional, Union
+
+import torch
+
+from . import ops
+from .data import BatchedData, Dictionary, Label, Sentence
+
+log = logging.getLogger("kbner_b200")
+
+START_TAG = "<START>"
+STOP_TAG = "<STOP>"
+
+
+class _CrfNll(torch.autograd.Function):
+    """sum_b w_b (logZ_b - gold_b) with the hand-written backward kernel."""
+
+    @staticmethod
+    def forward(ctx, emis, trans, tags, pos, klen, start, stop):
+        emis = emis.contiguous()
+        trans_c = trans.contiguous()
+        logz, gold, alpha = ops.crf_nll_fwd(emis, tags, trans_c, klen, start, stop, pos=pos, want_alpha=True)
+        ctx.save_for_backward(emis, trans_c, tags, pos, klen, alpha[0], alpha[1])
+        ctx.start, ctx.stop = start, stop
+        return logz - gold
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        emis, trans, tags, pos, klen, ahat, scale = ctx.saved_tensors
+        d_emis, d_trans = ops.crf_nll_bwd(emis, tags, trans, klen, (ahat, scale), grad_out.contiguous().float(),
+                                          ctx.start, ctx.stop, pos=pos)
+        return d_emis, d_trans, None, None, None, None, None
+
+
+class SequenceTagger(torch.nn.Module):
+    def __init__(self, hidden_size: int, embeddings, tag_dictionary: Dictionary, tag_type: str,
+                 use_crf: bool = True, use_mfvi: bool = False, use_rnn: bool = True, use_cnn: bool = False,
+                 rnn_layers: int = 1, dropout: float = 0.0, word_dropout: float = 0.05, locked_dropout: float = 0.5,
+                 train_initial_hidden_state: bool = False, pickle_module: str = "pickle", interpolation: float = 0.5,
+                 sentence_loss: bool = False, distill_crf: bool = False, crf_attention: bool = False,
+                 biaf_attention: bool = False, use_language_attention: bool = False,
+                 token_level_attention: bool = False, target_languages: int = 1, config=None, word_map=None,
+                 char_map=None, use_decoder_timer: bool = True, debug: bool = False, temperature: float = 1,
+                 testing: bool = False, remove_x: bool = False, multi_view_training: bool = False, **kwargs):
+        super().__init__()
+        if not use_crf or use_rnn or use_cnn or use_mfvi:
+            raise NotImplementedError("kbner_b200 implements the KB-NER tagger head: use_crf=True, use_rnn=False, "
+                                      "use_cnn=False (config/*.yaml `model:` block)")
+        off = dict(distill_crf=distill_crf, crf_attention=crf_attention, biaf_attention=biaf_attention,
+                   use_language_attention=use_language_attention, token_level_attention=token_level_attention,
+                   multi_view_training=multi_view_training)
+        for k in ("enhanced_crf", "posterior_constraint", "predict_posterior", "distill_posterior", "use_language_vector",
+                  "use_transition_attention", "unlabel_entropy_loss", "relearn_embeddings", "map_embeddings",
+                  "embedding_selector", "use_rl", "use_gumbel", "use_embedding_masks", "embedding_attention"):
+            off[k] = kwargs.get(k, False)
+        bad = [k for k, v in off.items() if v]
+        if bad:
+            raise NotImplementedError("options outside the hot path (KD / multi-view / ACE variants): %s" % bad)
+        if dropout or (locked_dropout and use_rnn):
+            raise NotImplementedError("dropout / locked_dropout apply to the RNN path only")
+        # ---- attribute surface read by ModelFinetuner / train.py -----------------------
+        self.debug, self.use_language_attention, self.biaf_attention = debug, False, False
+        self.token_level_attention, self.use_language_vector, self.use_crf = False, False, True
+        self.use_decoder_timer, self.sentence_level_loss = use_decoder_timer, sentence_loss
+        self.temperature = temperature
+        self.use_rnn, self.use_cnn, self.use_mfvi, self.use_bert = False, False, False, False
+        self.hidden_size, self.rnn_layers = hidden_size, rnn_layers
+        self.embeddings = embeddings
+        self.config, self.word_map, self.char_map = config, word_map, char_map
+        self.lemma_map = self.postag_map = None
+        self.tag_dictionary: Dictionary = tag_dictionary
+        self.tag_type: str = tag_type
+        self.tagset_size: int = len(tag_dictionary)
+        if self.tagset_size > 32:
+            raise NotImplementedError("CRF kernels map one tag per warp lane: tagset must be <= 32 (got %d); every "
+                                      "shipped KB-NER dictionary has <= 29 tags" % self.tagset_size)
+        self.remove_x = remove_x
+        self.target_languages = target_languages
+        self.multi_view_training = False
+        self.distill_crf = self.distill_posterior = self.distill_prob = self.distill_exact = False
+        self.distill_emission = self.crf_attention = self.enhanced_crf = self.predict_posterior = False
+        self.posterior_constraint = self.use_transition_attention = self.unlabel_entropy_loss = False
+        self.relearn_embeddings = self.map_embeddings = self.embedding_selector = self.use_rl = False
+        self.use_dropout, self.use_word_dropout, self.use_locked_dropout = 0.0, word_dropout, locked_dropout
+        self.pickle_module = pickle_module
+        self.interpolation = interpolation
+        self.time = 0.0
+        self.mask = None
+        self._keep = None
+        # ---- parameters: names `linear.*` / `transitions` drive the trainer's LR groups (:552-553) ---
+        self.linear = torch.nn.Linear(self.embeddings.embedding_length, self.tagset_size)
+        self.start_idx = tag_dictionary.get_idx_for_item(START_TAG)
+        self.stop_idx = tag_dictionary.get_idx_for_item(STOP_TAG)
+        self.x_idx = tag_dictionary.get_idx_for_item("S-X")
+        trans = torch.randn(self.tagset_size, self.tagset_size)
+        trans[self.start_idx, :] = -1e12          # nothing transitions INTO <START>   (:402-410; [to, from])
+        trans[:, self.stop_idx] = -1e12           # nothing transitions FROM <STOP>
+        self.transitions = torch.nn.Parameter(trans)
+        if not testing:
+            dev = getattr(getattr(embeddings, "embeddings", [None])[0], "device_", None) or "cuda"
+            self.to(dev)
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.transitions.device
+
+    def _encoded(self, sentences):
+        """The device-side batch left behind by embeddings.embed (one stacked embedding)."""
+        return sentences.features[self.embeddings.embeddings[0].name]
+
+    @staticmethod
+    def sequence_mask(lengths, max_len=None):
+        lengths = torch.as_tensor(lengths)
+        max_len = int(max_len or lengths.max())
+        return torch.arange(max_len, device=lengths.device)[None, :] < lengths[:, None]
+
+    # ---- forward (:844-1052) -------------------------------------------------------------------------
+    def forward(self, sentences, prediction_mode: bool = False):
+        if not isinstance(sentences, BatchedData):
+            sentences = BatchedData(sentences if isinstance(sentences, list) else [sentences])
+        self._batch = sentences
+        self.embeddings.embed(sentences)
+        enc = self._encoded(sentences)
+        lengths = enc.lengths
+        T = max(lengths)
+        if self.use_decoder_timer:
+            self.time = time.time()
+        drop_keep = None
+        if self.training and self.use_word_dropout > 0.0:
+            # WordDropout on [T,B,D]: one Bernoulli(1-p) draw per time step, shared by the batch, no rescale
+            # (flair/nn.py:176-183)
+            drop_keep = torch.empty(T, device=self.device).bernoulli_(1.0 - self.use_word_dropout).to(torch.uint8)
+        features = ops.gather_tagproj_fwd(enc.hidden, enc.row_of, enc.first_idx, self.linear.weight.float().contiguous(),
+                                          self.linear.bias.float().contiguous(), enc.S, drop_keep=drop_keep)
+        if self.training and (self.linear.weight.requires_grad or self.linear.bias.requires_grad):
+            features = _TagProjGrad.apply(features, self.linear.weight, self.linear.bias, enc, drop_keep)
+        self.lengths_t = torch.tensor(lengths, dtype=torch.int32, device=self.device)
+        self.mask = self.sequence_mask(self.lengths_t, T).to(features.dtype)        # (:1028)
+        self._keep = None
+        return features
+
+    # ---- loss (:1899-1921, :2426-2539) ------------------------------------------------------------------
+    def forward_loss(self, data_points: Union[List[Sentence], Sentence], sort=True, return_features=False):
+        features = self.forward(data_points)
+        loss = self._calculate_loss(features, self._batch, self.mask)
+        return (loss, features) if return_features else loss
+
+    def _gold_tags(self, sentences, T):
+        rows = []
+        for s in sentences:
+            tg = getattr(s, self.tag_type + "_tags", None)
+            if tg is None:
+                tg = torch.tensor([self.tag_dictionary.get_idx_for_item(tok.get_tag(self.tag_type).value)
+                                   for tok in s.tokens], dtype=torch.int32)
+            tg = torch.as_tensor(tg).to(torch.int32)
+            if tg.numel() < T:
+                tg = torch.cat([tg, torch.zeros(T - tg.numel(), dtype=torch.int32)])     # pad with 0 = <unk>
+            rows.append(tg[:T])
+        return torch.stack(rows, 0).to(self.device, non_blocking=True)
+
+    def _calculate_loss(self, features: torch.Tensor, sentences, mask: torch.Tensor):
+        B, T, L = features.shape
+        tags = self._gold_tags(sentences, T)
+        keep = mask.bool()
+        if self.remove_x:
+            keep = keep & (tags != self.x_idx)                   # (:2448-2453)
+            self.mask = keep.to(features.dtype)
+        keep_u8 = keep.to(torch.uint8).contiguous()
+        pos, klen = ops.crf_compact(keep_u8)                      # (:2474-2488)
+        self._keep = (pos, klen)
+        nll = _CrfNll.apply(features, self.transitions, tags.contiguous(), pos, klen, self.start_idx, self.stop_idx)
+        labelled = torch.tensor([0.0 if getattr(s, "is_unlabel", False) else 1.0 for s in sentences],
+                                device=nll.device)
+        if float(labelled.sum()) == 0:
+            return nll.sum() * 0.0
+        if float(labelled.min()) == 0:
+            return (nll * labelled).sum() / labelled.sum()        # (:2499-2504)
+        return nll.mean()                                          # (:2506)
+
+    # ---- decode (:1157-1246) ---------------------------------------------------------------------------
+    def _decode_batch(self, feature: torch.Tensor):
+        B, T, L = feature.shape
+        slen = self.lengths_t
+        if self.remove_x and self._keep is not None:
+            pos, klen = self._keep                                 # the keep-mask side channel (Appendix B.8)
+        else:
+            pos, klen = None, slen
+        return ops.crf_viterbi(feature.detach().float().contiguous(), self.transitions.detach().contiguous(), klen,
+                               slen, self.start_idx, self.stop_idx, self.x_idx, pos=pos)
+
+    def _obtain_labels(self, feature, sentences, get_all_tags: bool = False):
+        if get_all_tags:
+            raise NotImplementedError("get_all_tags (per-tag score dump, :1306-1325) is outside the hot path")
+        tags, conf = self._decode_batch(feature)
+        tags_h, conf_h = tags.cpu(), conf.cpu()                    # ONE device->host read for the batch
+        out = []
+        for b, s in enumerate(sentences):
+            n = len(s.tokens)
+            out.append([Label(self.tag_dictionary.get_item_for_index(int(tags_h[b, t])), float(conf_h[b, t]))
+                        for t in range(n)])
+        return out, []
+
+    def _viterbi_decode(self, feats, all_scores: bool = False, current_idx=0):
+        """Single-sentence API of the reference (:1248-1327): feats [T,L] -> (confidences, tag_seq, scores)."""
+        if all_scores:
+            raise NotImplementedError("all_scores")
+        T = feats.shape[0]
+        ln = torch.tensor([T], dtype=torch.int32, device=self.device)
+        tags, conf = ops.crf_viterbi(feats.detach().float().contiguous()[None], self.transitions.detach().contiguous(),
+                                     ln, ln, self.start_idx, self.stop_idx, self.x_idx)
+        return conf[0].tolist(), tags[0].tolist(), []
+
+    def _forward_alg(self, feats, lens_, distill_mode=False, T=1):
+        if distill_mode or T != 1:
+            raise NotImplementedError("distill_mode / temperature")
+        B, Tm, L = feats.shape
+        lens_ = torch.as_tensor(lens_).to(torch.int32).to(self.device)
+        dummy = torch.zeros((B, Tm), dtype=torch.int32, device=self.device)
+        logz, _, _ = ops.crf_nll_fwd(feats.detach().float().contiguous(), dummy, self.transitions.detach().contiguous(),
+                                     lens_, self.start_idx, self.stop_idx)
+        return logz
+
+    def _score_sentence(self, feats, tags, lens_, mask=None):
+        lens_ = torch.as_tensor(lens_).to(torch.int32).to(self.device)
+        _, gold, _ = ops.crf_nll_fwd(feats.detach().float().contiguous(), tags.to(torch.int32).contiguous(),
+                                     self.transitions.detach().contiguous(), lens_, self.start_idx, self.stop_idx)
+        return gold
+
+    # ---- evaluate (:2593-2729) / predict (:786-841) -----------------------------------------------------
+    @torch.no_grad()
+    def predict(self, sentences, mini_batch_size: int = 32, **_kw):
+        if isinstance(sentences, Sentence):
+            sentences = [sentences]
+        self.eval()
+        for i in range(0, len(sentences), mini_batch_size):
+            batch = BatchedData(sentences[i:i + mini_batch_size])
+            feature = self.forward(batch, prediction_mode=True)
+            tags, _ = self._obtain_labels(feature, batch)
+            for s, st in zip(batch, tags):
+                for tok, lab in zip(s.tokens, st):
+                    tok.add_tag_label(self.tag_type, lab)
+        return sentences
+
+    @torch.no_grad()
+    def evaluate(self, data_loader, out_path=None, embeddings_storage_mode: str = "none", prediction_mode=False,
+                 speed_test=False):
+        """-> (Result-like dict, eval_loss).  Span micro-F1 with the remove-X filter (:2644-2686);
+        P/R/F rounded to 4 dp like Metric (training_utils.py:67-93)."""
+        self.eval()
+        eval_loss, batches, lines = 0.0, 0, []
+        tp = fp = fn = 0
+        n_sent, t0 = 0, time.time()
+        for batch in data_loader:
+            if not isinstance(batch, BatchedData):
+                batch = BatchedData(batch)
+            batches += 1
+            n_sent += len(batch)
+            features = self.forward(batch, prediction_mode=prediction_mode)
+            if not speed_test:
+                eval_loss += float(self._calculate_loss(features, batch, self.mask))     # (:2619-2621)
+            tags, _ = self._obtain_labels(features, batch)
+            if speed_test:
+                continue
+            for s, st in zip(batch, tags):
+                gold_x = [tok.get_tag(self.tag_type).value == "S-X" for tok in s.tokens]
+                gold_spans = [(ty, a, e, tx) for (ty, a, e, tx) in s.get_spans(self.tag_type) if ty != "X"]
+                for tok, lab in zip(s.tokens, st):
+                    tok.add_tag_label("predicted", lab)
+                    lines.append("%s %s %s %s\n" % (tok.text, tok.get_tag(self.tag_type).value, lab.value, lab.score))
+                lines.append("\n")
+                pred_spans = [(ty, a, e, tx) for (ty, a, e, tx) in s.get_spans("predicted")
+                              if ty != "X" and not any(gold_x[a:e])]
+                gs, ps = set(gold_spans), set(pred_spans)
+                tp += len(gs & ps)
+                fp += len(ps - gs)
+                fn += len(gs - ps)
+        if speed_test:
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            log.info("speed_test: %d sentences, %.2f sentences/s", n_sent, n_sent / max(dt, 1e-9))
+            return {"sentences_per_sec": n_sent / max(dt, 1e-9)}, 0.0
+        if out_path is not None:
+            with open(out_path, "w", encoding="utf-8") as f:
+                f.write("".join(lines))
+        p = round(tp / (tp + fp), 4) if tp + fp else 0.0
+        r = round(tp / (tp + fn), 4) if tp + fn else 0.0
+        f1 = round(2 * p * r / (p + r), 4) if p + r else 0.0
+        result = {"main_score": f1, "precision": p, "recall": r, "tp": tp, "fp": fp, "fn": fn,
+                  "log_line": "%s\t%s\t%s" % (p, r, f1)}
+        return result, eval_loss / max(batches, 1)
+
+    # ---- checkpoint (:435-477, :1824-1897; flair/nn.py:60-108) ----------------------------------------------
+    def _get_state_dict(self):
+        return {"state_dict": self.state_dict(), "embeddings": self.embeddings, "hidden_size": self.hidden_size,
+                "tag_dictionary": self.tag_dictionary, "tag_type": self.tag_type, "use_crf": self.use_crf,
+                "use_rnn": self.use_rnn, "use_cnn": self.use_cnn, "rnn_layers": self.rnn_layers,
+                "use_word_dropout": self.use_word_dropout, "use_locked_dropout": self.use_locked_dropout,
+                "remove_x": self.remove_x, "sentence_level_loss": self.sentence_level_loss,
+                "target_languages": self.target_languages, "config": self.config}
+
+    @classmethod
+    def _init_model_with_state_dict(cls, state, testing=False):
+        model = cls(hidden_size=state["hidden_size"], embeddings=state["embeddings"],
+                    tag_dictionary=state["tag_dictionary"], tag_type=state["tag_type"], use_crf=state["use_crf"],
+                    use_rnn=state["use_rnn"], use_cnn=state.get("use_cnn", False), rnn_layers=state["rnn_layers"],
+                    word_dropout=state.get("use_word_dropout", 0.05), locked_dropout=state.get("use_locked_dropout", 0.5),
+                    remove_x=state.get("remove_x", False), sentence_loss=state.get("sentence_level_loss", False),
+                    target_languages=state.get("target_languages", 1), config=state.get("config"), testing=testing)
+        model.load_state_dict(state["state_dict"])
+        return model
+
+    def save(self, model_file):
+        torch.save(self._get_state_dict(), str(model_file), pickle_protocol=4)
+
+    @classmethod
+    def load(cls, model_file, device=None):
+        state = torch.load(str(model_file), map_location="cpu", weights_only=False)
+        model = cls._init_model_with_state_dict(state)
+        model.eval()
+        model.to(device or "cuda")
+        return model
+
+
+class _TagProjGrad(torch.autograd.Function):
+    """Gradient of the fused gather + word-dropout + Linear w.r.t. linear.weight / linear.bias.
+    (The gradient into the encoder hidden state is the round-2 backward path, see DESIGN.md.)"""
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, enc, drop_keep):
+        ctx.enc, ctx.drop_keep = enc, drop_keep
+        return features.view_as(features)
+
+    @staticmethod
+    def backward(ctx, g):
+        enc, dk = ctx.enc, ctx.drop_keep
+        B, T, L = g.shape
+        idx = enc.row_of.long()[:, None] * enc.S + enc.first_idx.long().clamp(min=0)
+        live = (enc.first_idx >= 0).to(g.dtype)
+        if dk is not None:
+            live = live * dk.to(g.dtype)[None, :]
+        x = enc.hidden[idx.view(-1)].float() * live.view(-1, 1)
+        gw = g.reshape(B * T, L).t() @ x
+        return g, gw, g.sum((0, 1)), None, None
+
+
+class FastSequenceTagger(SequenceTagger):
+    """The class the KB-NER YAMLs instantiate (config/*.yaml `model: FastSequenceTagger`,
+    sequence_tagger_model.py:1823); identical arithmetic to SequenceTagger on this path."""

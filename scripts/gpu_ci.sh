@@ -10,3 +10,5 @@ for grp in crf gemm "layernorm or embed or tagproj" attention; do
 done
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "== smoke: exit $?" | tee -a gpurun_out/summary.txt
 tail -n 5 gpurun_out/smoke.log
+timeout 900 python -m pytest tests/test_api_gpu.py -q -x -m gpu -s > gpurun_out/test_api.log 2>&1; echo "== api: exit $?" | tee -a gpurun_out/summary.txt
+tail -n 30 gpurun_out/test_api.log

@@ -57,7 +57,7 @@ def test_crf_golden_nll_and_grad(ops, golden):
         assert abs(loss - float(G("loss"))) <= 1e-5 * abs(float(G("loss"))) + 1e-4, n
         B = emis.shape[0]
         w = torch.full((B,), 1.0 / B, device="cuda")
-        de, dt = ops.crf_nll_bwd(emis, tags, trans, klen, alpha, logz, w, st, sp, pos=pos)
+        de, dt = ops.crf_nll_bwd(emis, tags, trans, klen, alpha, w, st, sp, pos=pos)
         np.testing.assert_allclose(de.cpu().numpy(), G("d_emis"), atol=2e-4, err_msg=str(n))
         scale = max(1.0, float(np.abs(G("d_trans")).max()))
         assert np.abs(dt.cpu().numpy() - G("d_trans")).max() / scale < 2e-4, n
@@ -125,7 +125,7 @@ def test_crf_nll_vs_oracle(ops, L):
     np.testing.assert_allclose(logz.cpu().numpy(), rz, rtol=1e-5)
     np.testing.assert_allclose(gold.cpu().numpy(), rg, rtol=1e-5, atol=1e-3)
     w = rng.rand(B).astype(np.float32)
-    de, dt = ops.crf_nll_bwd(dev(emis), dev(tags), dev(trans), dev(lens), alpha, logz, dev(w), L - 2, L - 1)
+    de, dt = ops.crf_nll_bwd(dev(emis), dev(tags), dev(trans), dev(lens), alpha, dev(w), L - 2, L - 1)
     rde, rdt = O.crf_nll_bwd(emis, tags, trans, lens, w)
     np.testing.assert_allclose(de.cpu().numpy(), rde, atol=2e-4)
     assert np.abs(dt.cpu().numpy() - rdt).max() / max(1.0, np.abs(rdt).max()) < 2e-4

@@ -1,0 +1,45 @@
+"""CPU: the fp32 encoder restatement (oracle/encoder_oracle.py) pinned against the installed
+transformers XLMRobertaModel (the architecture the reference calls, flair/embeddings.py:3269)."""
+import pytest
+import torch
+
+import encoder_oracle as E
+
+
+def test_encoder_oracle_matches_hf_xlmr():
+    transformers = pytest.importorskip("transformers")
+    cfg = dict(hidden=128, heads=2, ffn=256, layers=3, vocab=1000, max_pos=66, eps=1e-5, pad_id=1)
+    hf_cfg = transformers.XLMRobertaConfig(
+        vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+        num_attention_heads=cfg["heads"], intermediate_size=cfg["ffn"], max_position_embeddings=cfg["max_pos"],
+        type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1, bos_token_id=0, eos_token_id=2,
+        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    hf_cfg._attn_implementation = "eager"
+    model = transformers.XLMRobertaModel(hf_cfg, add_pooling_layer=False).eval()
+    params = E.init_params(cfg, seed=5)
+    missing, unexpected = model.load_state_dict(params, strict=False)
+    assert not unexpected and all("position_ids" in m or "token_type_ids" in m for m in missing), (missing, unexpected)
+    torch.manual_seed(0)
+    R, S = 3, 64
+    ids = torch.randint(3, cfg["vocab"], (R, S))
+    ids[:, 0] = 0
+    lens = torch.tensor([64, 40, 7])
+    for r in range(R):
+        ids[r, lens[r] - 1] = 2
+        ids[r, lens[r]:] = 0                    # reference pads with 0 (embeddings.py:3247-3251)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, output_hidden_states=True)
+        mine = E.encoder_forward(params, ids, lens, cfg, all_layers=True)
+    assert len(out.hidden_states) == len(mine) == cfg["layers"] + 1
+    for a, b in zip(out.hidden_states, mine):
+        for r in range(R):      # only real (non-padded) sub-tokens are observable through the API
+            torch.testing.assert_close(a[r, :lens[r]], b[r, :lens[r]], rtol=1e-4, atol=1e-5)
+
+
+def test_first_subtoken_pool_semantics():
+    hidden = torch.arange(2 * 6 * 4, dtype=torch.float32).view(2, 6, 4)
+    first = torch.tensor([[1, 3, -1], [1, 2, 4]])
+    pooled = E.first_subtoken_pool(hidden, torch.tensor([0, 1]), first)
+    assert torch.equal(pooled[0, 0], hidden[0, 1]) and torch.equal(pooled[0, 2], torch.zeros(4))
+    assert torch.equal(pooled[1, 2], hidden[1, 4])
