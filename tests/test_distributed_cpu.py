@@ -1,0 +1,65 @@
+"""CPU, gloo, world_size 2: the N>1 path -- sentence sharding (no data-path collective), metric-count reduction,
+and the gradient all-reduce semantics of fine-tuning (mean over ranks == global batch)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kbner_b200.distributed import GradBucketReducer, allreduce_counts, global_grad_norm, shard_indices
+    n = 11
+    mine = shard_indices(n, rank, world)
+    allidx = [None] * world
+    dist.all_gather_object(allidx, mine)
+    counts = allreduce_counts([len(set(mine)), rank + 1, 7])
+    # gradient averaging: each rank holds the gradient of its own shard's mean loss
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 3))
+    x = torch.randn(4 * world, 8)
+    y = torch.randn(4 * world, 3)
+    loss = ((model(x[rank * 4:(rank + 1) * 4]) - y[rank * 4:(rank + 1) * 4]) ** 2).mean()
+    loss.backward()
+    GradBucketReducer(model.parameters(), bucket_mb=0.0005).reduce()      # tiny buckets: several per model
+    norm = float(global_grad_norm(model.parameters()))
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 3))
+    ref.load_state_dict(model.state_dict())
+    ((ref(x) - y) ** 2).mean().backward()
+    err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
+    q.put((rank, allidx, counts, err, norm))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    world, port = 2, 29500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    for rank, allidx, counts, err, norm in res:
+        assert sorted(set(sum(allidx, []))) == list(range(11))          # every sentence covered
+        assert len(allidx[0]) == len(allidx[1]) == 6                    # same number of steps on every rank
+        assert counts[1] == 3 and counts[2] == 14
+        assert err < 1e-6                                               # mean of rank grads == global-batch grad
+    assert abs(res[0][4] - res[1][4]) < 1e-7                            # identical clip norm on both ranks
+
+
+def test_shard_indices_edge_cases():
+    from kbner_b200.distributed import shard_indices
+    assert shard_indices(0, 0, 4) == []
+    assert shard_indices(3, 3, 4) == [3 % 3]                             # fewer items than ranks: padded by wrapping
+    assert shard_indices(8, 1, 4, pad=False) == [1, 5]
