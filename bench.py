@@ -45,7 +45,7 @@ def _peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -56,12 +56,14 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples whose timestamp falls inside the timed region [t0, t1] (epoch seconds)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -74,8 +76,13 @@ class ClockSampler:
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) >= 7:
-                    rows.append(f)
+                if len(f) >= 8:
+                    try:
+                        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except Exception:
+                        ts = None
+                    if ts is None or t0 is None or (t0 - 0.05 <= ts <= t1 + 0.05):
+                        rows.append(f[1:])
             os.unlink(self.path)
         except Exception:
             pass
@@ -174,12 +181,15 @@ def run_b200(args):
         logits = ops.gather_tagproj_fwd(hidden, row_of, first_idx, Wt, bt, S_LEN)
         return ops.crf_viterbi(logits, trans, slen, slen, tagger.start_idx, tagger.stop_idx, tagger.x_idx)
 
-    def api_step(i):
-        batch = batches[i % len(batches)]
-        batch.features = {}
-        feats = tagger.forward(batch, prediction_mode=True)
-        labels, _ = tagger._obtain_labels(feats, batch)
-        return labels
+    def api_run(k, offset=0):
+        """The call a user of the reference makes for throughput: FastSequenceTagger.evaluate(loader, speed_test=True)
+        (train.py:147-156 -> sequence_tagger_model.py:2611-2612,2698-2700): forward + _obtain_labels per batch."""
+        loader = []
+        for i in range(k):
+            b = batches[(offset + i) % len(batches)]
+            b.features = {}
+            loader.append(b)
+        tagger.evaluate(loader, embeddings_storage_mode="none", prediction_mode=True, speed_test=True)
 
     def barrier():
         if dist is not None:
@@ -209,13 +219,25 @@ def run_b200(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+            time.sleep(0.3)
+            for i in range(W):
+                device_step(i)
         l0 = kbner_b200._lib.launch_count()
+        tw0 = time.time()
         ms_dev, _ = timed(device_step, K)
+        tw1 = time.time()
         launches = kbner_b200._lib.launch_count() - l0
-        clocks = sampler.stop() if rank == 0 else {}
-        for i in range(W):
-            api_step(i)
-        ms_e2e_dev, wall_e2e = timed(api_step, K)
+        clocks = sampler.stop(tw0, tw1) if rank == 0 else {}
+        api_run(W)
+        barrier()
+        t0 = time.perf_counter()
+        api_run(K, offset=W)
+        torch.cuda.synchronize()
+        wall_e2e = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([wall_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall_e2e = float(t[0])
 
         # ---- roofline of the dominant kernel: events around every GEMM launch of one instrumented step
         gemm_events = []
@@ -256,7 +278,7 @@ def run_b200(args):
                    "encoder": cfg.name},
         "e2e": {"value": round(e2e_val, 2), "unit": "sentences/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(wall_e2e * 1e3 / K, 3),
-                "api": "FastSequenceTagger.forward + _obtain_labels (reference evaluate(speed_test=True) body)"},
+                "api": "FastSequenceTagger.evaluate(loader, speed_test=True): forward + _obtain_labels per batch, Label objects built"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, %d launches/step)" % len(gemm_events),
@@ -274,6 +296,44 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def usable_cores():
+    """Threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, int(q / p + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
+def pick_threads():
+    """Thread count for the CPU legs: the usable cores, or fewer if a 512x1024x4096 fp32 matmul proxy runs faster
+    with fewer (shared hosts oversubscribe badly).  Returns the count it set."""
+    import torch
+    cores = usable_cores()
+    a, b = torch.randn(512, 1024), torch.randn(1024, 4096)
+    best, best_t = cores, None
+    for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        torch.set_num_threads(n)
+        (a @ b)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            (a @ b)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t * 0.9:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_port_baseline(emb, tagger, n_sentences, warm, seed=99):
     """The oracle port of the reference's CPU path on this box's host cores: fp32 encoder restatement
     (oracle/encoder_oracle.py, all torch threads) + C Viterbi (oracle/crf_oracle.c, 1 thread), 512-token sentences."""
@@ -281,8 +341,7 @@ def cpu_port_baseline(emb, tagger, n_sentences, warm, seed=99):
     import torch
     import crf_oracle as O
     import encoder_oracle as E
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_threads()
     c = emb.model.config
     cfg = dict(hidden=c.hidden_size, heads=c.num_attention_heads, ffn=c.intermediate_size, layers=c.num_hidden_layers,
                vocab=c.vocab_size, max_pos=c.max_position_embeddings, eps=c.layer_norm_eps, pad_id=c.pad_token_id)
@@ -321,8 +380,7 @@ def run_reference(args):
     import numpy as np
     import crf_oracle as O
     import encoder_oracle as E
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_threads()
     cfg = dict(E.XLMR_BASE if args.base else E.XLMR_LARGE)
     params = E.init_params(cfg, seed=1234)
     L = N_TAGS
@@ -364,7 +422,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--base", action="store_true", help="xlm-roberta-base shapes (debug)")

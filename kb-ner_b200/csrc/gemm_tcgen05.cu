@@ -13,6 +13,8 @@
 //   warps 2..9  epilogue     : tcgen05.ld 32 lanes x 32 columns -> registers -> bias /
 //                              GELU(erf) / residual -> bf16 or fp32 -> global
 // Tiles are walked m-fastest so the 148 concurrently running CTAs share one B (weight) tile.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
@@ -230,9 +232,21 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const flo
     return KBNER_OK;
 }
 
+int gemm2_dispatch(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *residual, void *C, int M,
+                   int N, int K, int lda, int ldb, int ldc, int epilogue, cudaStream_t st);   // gemm2_tcgen05.cu
+
 }  // namespace kbner
 
 using namespace kbner;
+
+static int gemm_impl_choice() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("KBNER_GEMM");
+        v = (e && e[0] == '2') ? 2 : 1;
+    }
+    return v;
+}
 
 extern "C" int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias,
                                   const uint16_t *residual, void *C, int M, int N, int K, int lda, int ldb,
@@ -247,6 +261,8 @@ extern "C" int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const fl
     KBNER_CHECK_ARG(((uintptr_t)C & 15u) == 0 && (!bias || ((uintptr_t)bias & 15u) == 0) &&
                         (!residual || ((uintptr_t)residual & 15u) == 0),
                     "gemm: C / bias / residual must be 16-byte aligned");
+    if (gemm_impl_choice() == 2)
+        return gemm2_dispatch(A, B, bias, residual, C, M, N, K, lda, ldb, ldc, epilogue, (cudaStream_t)stream);
     CUtensorMap tmA, tmB;
     int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (rc) return rc;

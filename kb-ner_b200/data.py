@@ -67,9 +67,12 @@ class Dictionary:
 
 
 class Label:
+    __slots__ = ("value", "score")
+
     def __init__(self, value: Optional[str], score: float = 1.0):
         self.value = value if value else ""
-        self.score = float(min(max(score, 0.0), 1.0)) if score is not None else 1.0
+        # score clamped to [0, 1] (flair/data.py:118-125)
+        self.score = score if 0.0 <= score <= 1.0 else (1.0 if score > 1.0 else 0.0)
 
     def to_dict(self):
         return {"value": self.value, "confidence": self.score}

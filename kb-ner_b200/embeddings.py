@@ -19,6 +19,7 @@ values raise instead of silently computing something else.
 import re
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from .data import BatchedData
@@ -152,6 +153,8 @@ class TransformerWordEmbeddings(torch.nn.Module):
         self.maximum_subtoken_length = maximum_subtoken_length
         self.embedding_type = "word-level"
         self._tok_cache = {}
+        self._plan_cache = {}
+        self._stage = None
         self.model.eval()
 
     @property
@@ -225,58 +228,99 @@ class TransformerWordEmbeddings(torch.nn.Module):
                 starts.append(starts[-1] + cap - self.stride)
         return starts, cap
 
+    def _sentence_plan(self, sentence):
+        """Cached per sentence: window rows (np.int32 arrays incl. <s> </s>) and, per word, the first-sub-token
+        position as (window, index-in-window) or -1."""
+        key = tuple(t.text for t in sentence.tokens)
+        hit = self._plan_cache.get(key)
+        if hit is not None:
+            return hit
+        tok = self.tokenizer
+        bos, eos = getattr(tok, "bos_token_id", 0), getattr(tok, "eos_token_id", 2)
+        ids, n_sub = self.subtokenize(sentence)
+        starts, cap = self.windows(len(ids))
+        if not self.allow_long_sentences:
+            ids = ids[:cap]
+        rows = [np.asarray([bos] + ids[st:st + cap] + [eos], dtype=np.int32) for st in starts]
+        # stitched index of sub-token g: window w owns [starts[w]+half, starts[w+1]+half) after dropping stride//2
+        # (+1 special) on each inner edge (:3292-3299)
+        half = self.stride // 2
+        n_sub_a = np.asarray(n_sub, dtype=np.int64)
+        g = np.concatenate([[0], np.cumsum(n_sub_a)[:-1]]) if len(n_sub) else np.zeros(0, np.int64)
+        starts_a = np.asarray(starts, dtype=np.int64)
+        w = np.searchsorted(starts_a[1:] + half, g, side="right") if len(starts) > 1 else np.zeros_like(g)
+        inwin = 1 + g - starts_a[w]
+        valid = (n_sub_a > 0) & (g < len(ids))
+        plan = (rows, np.where(valid, w, -1).astype(np.int64), inwin.astype(np.int64))
+        if len(self._plan_cache) < 200000:
+            self._plan_cache[key] = plan
+        return plan
+
     def build_batch(self, sentences):
         """Host side of _add_embeddings_to_sentences (:3135-3260): ids / key_len / first-sub-token map.
         The reference pads input_ids with 0 (:3247-3251); so do we (pads are masked as keys)."""
-        tok = self.tokenizer
-        bos, eos = getattr(tok, "bos_token_id", 0), getattr(tok, "eos_token_id", 2)
-        rows, row_of, firsts, lengths = [], [], [], []
-        for s in sentences:
-            ids, n_sub = self.subtokenize(s)
-            starts, cap = self.windows(len(ids))
-            if not self.allow_long_sentences:
-                ids = ids[:cap]
-            row_of.append(len(rows))
-            for st in starts:
-                rows.append([bos] + ids[st:st + cap] + [eos])
-            # stitched index of sub-token g: window w owns [own_lo, own_hi) after dropping stride//2 (+1 special)
-            # on each inner edge (:3292-3299); index is expressed relative to the sentence's first row.
-            half = self.stride // 2
-            fi, g = [], 0
-            for n in n_sub:
-                if n == 0 or g >= len(ids):
-                    fi.append(-1)
-                else:
-                    w = 0
-                    while w + 1 < len(starts) and g >= starts[w + 1] + half:
-                        w += 1
-                    fi.append((w, 1 + g - starts[w]))
-                g += n
-            firsts.append(fi)
-            lengths.append(len(s.tokens))
-        S = max(len(r) for r in rows)
-        R, B, T = len(rows), len(sentences), max(lengths)
-        ids_t = torch.zeros((R, S), dtype=torch.int32)
-        key_len = torch.zeros((R,), dtype=torch.int32)
-        for r, row in enumerate(rows):
-            ids_t[r, :len(row)] = torch.tensor(row, dtype=torch.int32)
-            key_len[r] = len(row)
-        first_idx = torch.full((B, T), -1, dtype=torch.int32)
-        for b, fi in enumerate(firsts):
-            for t, v in enumerate(fi):
-                if v != -1:
-                    first_idx[b, t] = v[0] * S + v[1]     # rows of one sentence are consecutive
-        return ids_t, key_len, torch.tensor(row_of, dtype=torch.int32), first_idx, lengths, S
+        plans = [self._sentence_plan(s) for s in sentences]
+        lengths = [len(s.tokens) for s in sentences]
+        B, T = len(sentences), max(lengths)
+        R = sum(len(p[0]) for p in plans)
+        S = max(len(r) for p in plans for r in p[0])
+        ids = np.zeros((R, S), dtype=np.int32)
+        key_len = np.zeros((R,), dtype=np.int32)
+        row_of = np.zeros((B,), dtype=np.int32)
+        first_idx = np.full((B, T), -1, dtype=np.int32)
+        r = 0
+        for b, (rows, w, inwin) in enumerate(plans):
+            row_of[b] = r
+            for row in rows:
+                ids[r, :len(row)] = row
+                key_len[r] = len(row)
+                r += 1
+            fi = np.where(w >= 0, w * S + inwin, -1)          # rows of one sentence are consecutive
+            first_idx[b, :len(fi)] = fi
+        return (torch.from_numpy(ids), torch.from_numpy(key_len), torch.from_numpy(row_of),
+                torch.from_numpy(first_idx), lengths, S)
 
     # ---- device side ----------------------------------------------------------------------------------
+    def _staging(self, n):
+        """Rotating pinned int32 staging buffers (one H2D copy per batch; a buffer is reused only after the copy
+        that last read it has completed)."""
+        if not hasattr(self, "_stage") or self._stage is None:
+            self._stage, self._stage_i = [], 0
+        if len(self._stage) < 4:
+            buf = torch.empty(max(n, 1 << 16), dtype=torch.int32)
+            if torch.cuda.is_available():
+                buf = buf.pin_memory()
+            self._stage.append([buf, None])
+            return self._stage[-1]
+        slot = self._stage[self._stage_i % 4]
+        self._stage_i += 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0].numel() < n:
+            slot[0] = torch.empty(n, dtype=torch.int32).pin_memory()
+        return slot
+
     def encode(self, sentences) -> EncodedBatch:
         ids, key_len, row_of, first_idx, lengths, S = self.build_batch(sentences)
         dev = self.device_
-        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
-        ids_d = pin(ids).to(dev, non_blocking=True)
-        key_d = pin(key_len).to(dev, non_blocking=True)
-        row_d = pin(row_of).to(dev, non_blocking=True)
-        first_d = pin(first_idx).to(dev, non_blocking=True)
+        parts = (ids, key_len, row_of, first_idx)
+        sizes = [t.numel() for t in parts]
+        n = sum(sizes)
+        slot = self._staging(n)
+        host = slot[0][:n]
+        off = 0
+        for t, k in zip(parts, sizes):
+            host[off:off + k] = t.reshape(-1)
+            off += k
+        packed = host.to(dev, non_blocking=True)
+        if dev.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            slot[1] = ev
+        o0, o1, o2 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
+        ids_d = packed[:o0].view(ids.shape)
+        key_d, row_d = packed[o0:o1], packed[o1:o2]
+        first_d = packed[o2:].view(first_idx.shape)
         hidden = self.model.forward_hidden(ids_d, key_d)
         return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d)
 
@@ -307,6 +351,8 @@ class TransformerWordEmbeddings(torch.nn.Module):
         state = self.__dict__.copy()
         state["tokenizer"] = None if not isinstance(self.tokenizer, SyntheticTokenizer) else self.tokenizer
         state["_tok_cache"] = {}
+        state["_plan_cache"] = {}
+        state["_stage"] = None
         return state
 
     def __setstate__(self, d):

@@ -206,14 +206,49 @@ class SequenceTagger(torch.nn.Module):
     def _obtain_labels(self, feature, sentences, get_all_tags: bool = False):
         if get_all_tags:
             raise NotImplementedError("get_all_tags (per-tag score dump, :1306-1325) is outside the hot path")
+        return self._labels_from_handle(self._decode_async(feature), sentences), []
+
+    def _decode_async(self, feature):
+        """Launch the batched Viterbi and the device->host copies of its result (pinned, non-blocking); returns a
+        handle `_labels_from_handle` turns into Label lists.  Lets `evaluate` overlap the host-side Label
+        construction of batch i with the kernels of batch i+1."""
         tags, conf = self._decode_batch(feature)
-        tags_h, conf_h = tags.cpu(), conf.cpu()                    # ONE device->host read for the batch
+        B, T = tags.shape
+        pool = getattr(self, "_d2h_pool", None)
+        if pool is None:
+            pool = self._d2h_pool = []
+        slot = None
+        for s in pool:
+            if not s["busy"] and s["tags"].numel() >= B * T:
+                slot = s
+                break
+        if slot is None:
+            n = max(B * T, 1 << 15)
+            slot = {"tags": torch.empty(n, dtype=torch.int32).pin_memory(),
+                    "conf": torch.empty(n, dtype=torch.float32).pin_memory(), "busy": False}
+            pool.append(slot)
+        slot["busy"] = True
+        slot["tags"][:B * T].copy_(tags.view(-1), non_blocking=True)
+        slot["conf"][:B * T].copy_(conf.view(-1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return (slot, ev, B, T)
+
+    def _labels_from_handle(self, handle, sentences):
+        slot, ev, B, T = handle
+        ev.synchronize()
+        tags_l = slot["tags"][:B * T].view(B, T).tolist()          # ONE device->host read per batch
+        conf_l = slot["conf"][:B * T].view(B, T).tolist()
+        slot["busy"] = False
+        names = getattr(self, "_tag_names", None)
+        if names is None:
+            names = self._tag_names = self.tag_dictionary.get_items()
         out = []
         for b, s in enumerate(sentences):
             n = len(s.tokens)
-            out.append([Label(self.tag_dictionary.get_item_for_index(int(tags_h[b, t])), float(conf_h[b, t]))
-                        for t in range(n)])
-        return out, []
+            tb, cb = tags_l[b], conf_l[b]
+            out.append([Label(names[tb[t]], cb[t]) for t in range(n)])
+        return out
 
     def _viterbi_decode(self, feats, all_scores: bool = False, current_idx=0):
         """Single-sentence API of the reference (:1248-1327): feats [T,L] -> (confidences, tag_seq, scores)."""
@@ -265,6 +300,24 @@ class SequenceTagger(torch.nn.Module):
         eval_loss, batches, lines = 0.0, 0, []
         tp = fp = fn = 0
         n_sent, t0 = 0, time.time()
+        if speed_test:
+            # forward + _obtain_labels only (:2611-2612, :2698-2700), software-pipelined: the Label lists of batch i
+            # are built on the host while the kernels of batch i+1 run
+            pending = None
+            for batch in data_loader:
+                if not isinstance(batch, BatchedData):
+                    batch = BatchedData(batch)
+                n_sent += len(batch)
+                features = self.forward(batch, prediction_mode=prediction_mode)
+                handle = self._decode_async(features)
+                if pending is not None:
+                    self._labels_from_handle(*pending)
+                pending = (handle, batch)
+            if pending is not None:
+                self.last_labels = self._labels_from_handle(*pending)
+            dt = time.time() - t0
+            log.info("speed_test: %d sentences, %.2f sentences/s", n_sent, n_sent / max(dt, 1e-9))
+            return {"sentences_per_sec": n_sent / max(dt, 1e-9), "sentences": n_sent}, 0.0
         for batch in data_loader:
             if not isinstance(batch, BatchedData):
                 batch = BatchedData(batch)
