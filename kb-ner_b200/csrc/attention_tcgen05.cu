@@ -3,16 +3,18 @@
 // flash-style: the [S,S] score matrix the reference's transformers-3.0.0 path materialises in
 // fp32 (call site /root/reference/flair/embeddings.py:3269) never leaves the SM.
 //
-// One CTA = one (window r, head h, block of 128 query rows).  S <= 512 so the whole K and V of
-// the head (<= 4 blocks of 128 keys) are TMA-loaded once into shared memory.
-//   warp 4        TMA + MMA issuer (one lane): S_j = Q.K_j^T  -> TMEM (2 buffers of 128 cols),
-//                 O_j = P_j.V_j -> TMEM (2 buffers of 64 cols); tcgen05.mma kind::f16,
-//                 V is consumed MN-major straight from its row-major [key][d] tile
-//   warps 0..3    softmax: thread = query row = TMEM lane; tcgen05.ld the score row, online
-//                 max / exp2 / sum in fp32 registers, P_j -> bf16 -> shared memory in the
-//                 SWIZZLE_128B K-major layout the MMA reads; running O kept in registers
-//                 (O = O*alpha + P_j.V_j), so no TMEM read-modify-write correction pass.
-// Pipeline: S_{j+1} is issued before softmax(j) finishes, P/O buffers are double-buffered.
+// One CTA = one (window r, head h, block of 128 query rows); TWO CTAs are resident per SM (96 KB of shared
+// memory, 256 TMEM columns, <= 200 registers each) so the softmax of one overlaps the MMAs of the other --
+// the round-1 version (1 CTA/SM, 1 softmax warp per scheduler) was latency-bound at 162 us per layer.
+//   warp 4        TMA + MMA issuer (one lane): K/V stream through a 3-stage ring of 64-key blocks;
+//                 S_j = Q.K_j^T -> TMEM (2 buffers x 64 cols), O_j = P_j.V_j -> TMEM (2 buffers x 64 cols);
+//                 tcgen05.mma kind::f16, V consumed MN-major straight from its row-major [key][d] tile
+//   warps 0..3    softmax: thread = query row = TMEM lane; tcgen05.ld the 64 scores, online max / ex2 / sum
+//                 in fp32 registers, P_j -> bf16 -> shared memory in the SWIZZLE_128B K-major layout the MMA
+//                 reads; running O in registers (O = O*alpha + P_j.V_j): no TMEM read-modify-write pass.
+// Pipeline inside a CTA: S_{j+1} is issued before softmax(j) finishes; P / O are double-buffered and the
+// accumulation of O_{j-1} is deferred until P_j has been published.
+// Bound: MUFU (one ex2 per score: 16/clk/SM => 512 clk per 128x64 block), not the tensor pipe.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -22,28 +24,38 @@
 namespace kbner {
 
 constexpr int kAttnD = 64;
-constexpr int kBQ = 128, kBKV = 128, kMaxKB = 4;
+constexpr int kBQ = 128, kBKV = 64, kKVStages = 3, kMaxS = 512;
 constexpr int kAttnThreads = 160;
-constexpr uint32_t kTileBytes = 128 * 64 * 2;   // one [128 rows][64 bf16] SWIZZLE_128B tile
+constexpr uint32_t kQBytes = 128 * 64 * 2;     // [128 rows][64 bf16], SWIZZLE_128B
+constexpr uint32_t kKVBytes = 64 * 64 * 2;     // [64 keys][64 bf16]
+constexpr uint32_t kAttnTmemCols = 256;
 
 struct AttnSmem {
-    uint8_t q[kTileBytes];
-    uint8_t k[kMaxKB][kTileBytes];
-    uint8_t v[kMaxKB][kTileBytes];
-    uint8_t p[2][2][kTileBytes];       // [buffer][64-key half][128 rows x 64 keys]
+    uint8_t q[kQBytes];
+    uint8_t k[kKVStages][kKVBytes];
+    uint8_t v[kKVStages][kKVBytes];
+    uint8_t p[2][kQBytes];             // [buffer][128 rows x 64 keys]
     uint64_t bar_q;
-    uint64_t bar_kv[kMaxKB];
+    uint64_t kv_full[kKVStages];
+    uint64_t kv_free[kKVStages];       // P_j.V_j retired: stage may be refilled
     uint64_t bar_s[2];                 // S_j ready in TMEM buffer j&1
     uint64_t bar_p[2];                 // P_j written to smem buffer j&1 (128 arrivals)
     uint64_t bar_o[2];                 // O_j ready in TMEM buffer j&1
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ key_len, int S, int H,
-                     int heads, uint16_t *__restrict__ out, float *__restrict__ lse_out) {
-    extern __shared__ uint8_t smem_raw[];
-    AttnSmem &s = *reinterpret_cast<AttnSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const int32_t *__restrict__ key_len, int S, int H, int heads, uint16_t *__restrict__ out,
+                     float *__restrict__ lse_out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    AttnSmem &s = *reinterpret_cast<AttnSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
     const int klen = min(key_len[r], S);
@@ -51,9 +63,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *_
     const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
 
     if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&tmQKV);
+        if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
+            printf("kbner attention: dynamic shared memory is not 1024-byte aligned\n");
+            __trap();
+        }
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmKV);
         ptx::mbar_init(&s.bar_q, 1);
-        for (int i = 0; i < kMaxKB; ++i) ptx::mbar_init(&s.bar_kv[i], 1);
+        for (int i = 0; i < kKVStages; ++i) {
+            ptx::mbar_init(&s.kv_full[i], 1);
+            ptx::mbar_init(&s.kv_free[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s.bar_s[i], 1);
             ptx::mbar_init(&s.bar_p[i], 128);
@@ -61,36 +81,39 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *_
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc<512>(&s.tmem_base);
+    if (warp == 4) ptx::tmem_alloc<kAttnTmemCols>(&s.tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const uint32_t tmem_s = tmem_base;            // 2 x 128 columns
-    const uint32_t tmem_o = tmem_base + 256;      // 2 x 64 columns
+    const uint32_t tmem_s = tmem_base;            // 2 x 64 columns
+    const uint32_t tmem_o = tmem_base + 128;      // 2 x 64 columns
 
     if (warp == 4) {
         if (lane == 0 && nkb > 0) {
-            // ---- loads: Q tile, then K_j / V_j per key block (separate barriers: compute starts early)
-            ptx::mbar_expect_tx(&s.bar_q, kTileBytes);
-            ptx::tma_load_2d(s.q, &tmQKV, &s.bar_q, h * kAttnD, row0 + qb * kBQ);
-            for (int j = 0; j < nkb; ++j) {
-                ptx::mbar_expect_tx(&s.bar_kv[j], 2 * kTileBytes);
-                ptx::tma_load_2d(s.k[j], &tmQKV, &s.bar_kv[j], H + h * kAttnD, row0 + j * kBKV);
-                ptx::tma_load_2d(s.v[j], &tmQKV, &s.bar_kv[j], 2 * H + h * kAttnD, row0 + j * kBKV);
-            }
-            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);   // S = Q.K^T : both K-major
-            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);    // O = P.V   : V is MN-major
+            auto load_kv = [&](int j) {
+                const int st = j % kKVStages;
+                ptx::mbar_expect_tx(&s.kv_full[st], 2 * kKVBytes);
+                ptx::tma_load_2d(s.k[st], &tmKV, &s.kv_full[st], H + h * kAttnD, row0 + j * kBKV);
+                ptx::tma_load_2d(s.v[st], &tmKV, &s.kv_full[st], 2 * H + h * kAttnD, row0 + j * kBKV);
+            };
+            ptx::mbar_expect_tx(&s.bar_q, kQBytes);
+            ptx::tma_load_2d(s.q, &tmQ, &s.bar_q, h * kAttnD, row0 + qb * kBQ);
+            for (int j = 0; j < nkb && j < kKVStages; ++j) load_kv(j);
+
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);   // S = Q.K^T : both K-major
+            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);   // O = P.V   : V is MN-major
             const uint32_t q_addr = ptx::smem_u32(s.q);
             auto issue_s = [&](int j) {
-                ptx::mbar_wait(&s.bar_kv[j], 0);
+                const int st = j % kKVStages;
+                ptx::mbar_wait(&s.kv_full[st], (j / kKVStages) & 1);
                 ptx::tc_fence_after();
-                const uint32_t k_addr = ptx::smem_u32(s.k[j]);
+                const uint32_t k_addr = ptx::smem_u32(s.k[st]);
 #pragma unroll
                 for (int kk = 0; kk < kAttnD / 16; ++kk) {
                     const uint64_t da = ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024);
                     const uint64_t db = ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024);
-                    ptx::mma_f16_ss(tmem_s + (j & 1) * 128, da, db, idesc_s, kk != 0);
+                    ptx::mma_f16_ss(tmem_s + (j & 1) * 64, da, db, idesc_s, kk != 0);
                 }
                 ptx::mma_commit(&s.bar_s[j & 1]);
             };
@@ -98,20 +121,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *_
             issue_s(0);
             if (nkb > 1) issue_s(1);
             for (int j = 0; j < nkb; ++j) {
-                // P_j in smem (written by the softmax warps; they passed fence.proxy.async first)
+                const int st = j % kKVStages;
+                // P_j in smem (the softmax warps executed fence.proxy.async before arriving)
                 ptx::mbar_wait(&s.bar_p[j & 1], (j >> 1) & 1);
                 ptx::tc_fence_after();
-                const uint32_t v_addr = ptx::smem_u32(s.v[j]);
+                const uint32_t v_addr = ptx::smem_u32(s.v[st]);
+                const uint32_t p_addr = ptx::smem_u32(s.p[j & 1]);
 #pragma unroll
                 for (int kk = 0; kk < kBKV / 16; ++kk) {
-                    const uint32_t p_addr = ptx::smem_u32(s.p[j & 1][kk >> 2]) + (kk & 3) * 32;
-                    const uint64_t da = ptx::make_sw128_desc(p_addr, 16, 1024);
+                    const uint64_t da = ptx::make_sw128_desc(p_addr + kk * 32, 16, 1024);
                     // V tile [key][d]: 16 keys per MMA = two 8-row swizzle atoms, 1024 B apart (SBO)
                     const uint64_t db = ptx::make_sw128_desc(v_addr + kk * 16 * 128, 16, 1024);
                     ptx::mma_f16_ss(tmem_o + (j & 1) * 64, da, db, idesc_o, kk != 0);
                 }
                 ptx::mma_commit(&s.bar_o[j & 1]);
+                ptx::mma_commit(&s.kv_free[st]);
                 if (j + 2 < nkb) issue_s(j + 2);   // S buffer j&1 was drained before P_j was published
+                if (j + kKVStages < nkb) {         // refill this stage once P_j.V_j has retired
+                    ptx::mbar_wait(&s.kv_free[st], (j / kKVStages) & 1);
+                    load_kv(j + kKVStages);
+                }
             }
         }
     } else {
@@ -144,47 +173,42 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *_
             ptx::tc_fence_after();
             float sc[kBKV];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t rs[32];
-                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 128 + c * 32, rs);
+                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 64 + c * 32, rs);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) sc[c * 32 + i] = __uint_as_float(rs[i]);
             }
             ptx::tc_fence_before();
-            // scale, key-padding mask, row max
             const int kbase = j * kBKV;
-            float m_blk = -CUDART_INF_F;
+            if (kbase + kBKV > klen) {       // only the last block of the window is ragged (CTA-uniform)
 #pragma unroll
-            for (int i = 0; i < kBKV; ++i) {
-                const float x = (kbase + i < klen) ? sc[i] * scale_log2 : -CUDART_INF_F;
-                sc[i] = x;
-                m_blk = fmaxf(m_blk, x);
+                for (int i = 0; i < kBKV; ++i)
+                    if (kbase + i >= klen) sc[i] = -CUDART_INF_F;
             }
-            const float m_new = fmaxf(m_run, m_blk);     // finite: every processed block has >= 1 valid key
-            const float alpha = exp2f(m_run - m_new);    // first block: exp2(-inf) = 0
-            float l_blk = 0.0f;
-            // P_j (bf16) into the SWIZZLE_128B K-major tile pair; row-sum over the ROUNDED values so that
-            // normalisation matches what the tensor core actually multiplies
-            uint8_t *pbase = s.p[j & 1][0];
+            float m_blk = sc[0];
 #pragma unroll
-            for (int ci = 0; ci < 16; ++ci) {
+            for (int i = 1; i < kBKV; ++i) m_blk = fmaxf(m_blk, sc[i]);
+            const float m_new = fmaxf(m_run, m_blk * scale_log2);     // finite: the block has >= 1 valid key
+            const float alpha = ex2_approx(m_run - m_new);           // first block: ex2(-inf) = 0
+            const float neg_m = -m_new;
+            float l_blk = 0.0f;
+            uint8_t *prow = s.p[j & 1] + row * 128;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
                 float pv[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) pv[e] = exp2f(sc[ci * 8 + e] - m_new);
+                for (int e = 0; e < 8; ++e) {
+                    pv[e] = ex2_approx(fmaf(sc[cc * 8 + e], scale_log2, neg_m));
+                    l_blk += pv[e];
+                }
                 uint4 pk;
                 pk.x = pack_bf16x2(pv[0], pv[1]);
                 pk.y = pack_bf16x2(pv[2], pv[3]);
                 pk.z = pack_bf16x2(pv[4], pv[5]);
                 pk.w = pack_bf16x2(pv[6], pv[7]);
-                float a0, a1;
-                unpack_bf16x2(pk.x, a0, a1); l_blk += a0 + a1;
-                unpack_bf16x2(pk.y, a0, a1); l_blk += a0 + a1;
-                unpack_bf16x2(pk.z, a0, a1); l_blk += a0 + a1;
-                unpack_bf16x2(pk.w, a0, a1); l_blk += a0 + a1;
-                const int half = ci >> 3, cc = ci & 7;
-                uint8_t *dst = pbase + half * kTileBytes + row * 128 + ((cc ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4 *>(dst) = pk;
+                *reinterpret_cast<uint4 *>(prow + ((cc ^ (row & 7)) << 4)) = pk;
             }
             l_run = l_run * alpha + l_blk;
             m_run = m_new;
@@ -217,7 +241,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *_
     __syncthreads();
     if (warp == 4) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<512>(tmem_base);
+        ptx::tmem_dealloc<kAttnTmemCols>(tmem_base);
     }
 }
 
@@ -229,13 +253,14 @@ extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, 
                                    uint16_t *out, float *lse, void *stream) {
     KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
     KBNER_CHECK_ARG(R > 0 && S > 0 && heads > 0, "attention_fwd: empty problem");
-    KBNER_CHECK_ARG(S <= kMaxKB * kBKV, "attention_fwd: S=%d exceeds the %d-sub-token window of XLM-R", S,
-                    kMaxKB * kBKV);
+    KBNER_CHECK_ARG(S <= kMaxS, "attention_fwd: S=%d exceeds the %d-sub-token window of XLM-R", S, kMaxS);
     const int H = heads * kAttnD;
-    CUtensorMap tm;
-    int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)R * S, (uint64_t)3 * H, (uint64_t)3 * H, 128, 64);
+    CUtensorMap tmQ, tmKV;
+    int rc = make_tmap_bf16_2d(&tmQ, qkv, (uint64_t)R * S, (uint64_t)3 * H, (uint64_t)3 * H, kBQ, 64);
     if (rc) return rc;
-    const size_t smem = sizeof(AttnSmem) + 1024;
+    rc = make_tmap_bf16_2d(&tmKV, qkv, (uint64_t)R * S, (uint64_t)3 * H, (uint64_t)3 * H, kBKV, 64);
+    if (rc) return rc;
+    const size_t smem = sizeof(AttnSmem);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -246,7 +271,7 @@ extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, 
         configured = true;
     }
     dim3 grid((S + kBQ - 1) / kBQ, heads, R);
-    attention_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tm, key_len, S, H, heads, out, lse);
+    attention_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse);
     KBNER_CHECK_LAUNCH("attention_fwd");
     return KBNER_OK;
 }
