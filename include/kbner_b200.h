@@ -115,7 +115,22 @@ int kbner_gather_tagproj_fwd(const uint16_t *hidden /*[R*S,H] bf16*/, const int3
 #define KBNER_EPI_BIAS            0  /* C(bf16)  = A.B^T + bias                         (QKV)          */
 #define KBNER_EPI_BIAS_GELU       1  /* C(bf16)  = gelu_erf(A.B^T + bias)               (FFN up)       */
 #define KBNER_EPI_BIAS_RESID_F32  2  /* C(fp32)  = A.B^T + bias + residual(bf16)        (attn-out, FFN down; LN follows) */
-#define KBNER_EPI_NONE_F32        3  /* C(fp32)  = A.B^T                                (tests / wgrad) */
+#define KBNER_EPI_NONE_F32        3  /* C(fp32)  = A.B^T                                (tests)        */
+#define KBNER_EPI_DGELU_BF16      4  /* C(bf16)  = (A.B^T) * gelu'(aux)                 (dgrad through the FFN GELU) */
+#define KBNER_EPI_ACCUM_F32       5  /* C(fp32) += A.B^T                                (wgrad into the fp32 gradient) */
+
+/* General form: C[M,N] = epilogue(sum_k A(m,k) * B(n,k)), bf16 operands, fp32 accumulation in TMEM.
+ * Operand layouts: a_mn_major = 0 -> A stored [M][K] (K-major), 1 -> A stored [K][M] (MN-major); same for B with
+ * N.  The tensor core reads either straight from the row-major global tensor, so
+ *   forward  Y  = X  . W^T        : A = X  [M,K]  K-major,  B = W  [N,K]  K-major
+ *   dgrad    dX = dY . W          : A = dY [M,N'] K-major,  B = W  [N',K'] read MN-major  (no W^T copy)
+ *   wgrad    dW += dY^T . X       : A = dY [M',N] read MN-major, B = X [M',K'] read MN-major (no transposes)
+ * bias [N] may be NULL.  aux (bf16 [M,N], ld = ldc): residual for BIAS_RESID_F32, saved pre-activation for
+ * DGELU_BF16.  aux_out (bf16 [M,N], optional): BIAS_GELU additionally stores the pre-activation (training).
+ * M, N, K multiples of 8; ragged tile edges are handled by TMA zero-fill and guarded stores. */
+int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *aux,
+                    uint16_t *aux_out, void *C, int M, int N, int K, int lda, int ldb, int ldc,
+                    int a_mn_major, int b_mn_major, int epilogue, void *stream);
 
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T): both operands K-major bf16 ("TN" GEMM, the layout of
  * torch.nn.Linear).  M, N, K arbitrary multiples of 8 (TMA handles ragged tile edges);
@@ -131,6 +146,43 @@ int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias /
 int kbner_attention_fwd(const uint16_t *qkv /*[R*S,3H]*/, const int32_t *key_len /*[R]*/,
                         int R, int S, int heads, uint16_t *out /*[R*S,H]*/,
                         float *lse /*[R,heads,S] or NULL*/, void *stream);
+
+/* ---- fine-tuning step: HBM-bound backward kernels, gradient norm, optimizer ----------------------
+ * The reference obtains these from autograd + transformers.AdamW
+ * (flair/trainers/finetune_trainer.py:939-957 backward, :1007-1023 clip_grad_norm_(5.0) / step / zero_grad). */
+
+/* LayerNorm backward: x = saved fp32 pre-LN sum, dout = grad w.r.t. the LN output (fp32);
+ * dx (bf16) = grad w.r.t. the pre-LN sum; dgamma / dbeta are ACCUMULATED into. */
+int kbner_layernorm_bwd(const float *x /*[M,H]*/, const float *dout /*[M,H]*/, const float *gamma,
+                        const float *mean /*[M]*/, const float *rstd /*[M]*/, int M, int H,
+                        uint16_t *dx /*[M,H] bf16*/, float *dgamma /*[H]*/, float *dbeta /*[H]*/, void *stream);
+
+/* Bias gradient: db[n] += sum_m dY[m][n]. */
+int kbner_colsum_bf16(const uint16_t *dY /*[M,N] bf16*/, int M, int N, float *db /*[N]*/, void *stream);
+
+/* Backward of kbner_embed_ln_fwd: LayerNorm backward on the recomputed sum, scatter-add into the embedding
+ * tables' gradients (all outputs ACCUMULATED into). */
+int kbner_embed_ln_bwd(const int32_t *ids, const float *word_emb, const float *pos_emb, const float *type_emb,
+                       const float *gamma, float eps, int pad_id, int R, int S, int H,
+                       const float *dout /*[R*S,H] fp32*/, float *d_word /*[V,H]*/, float *d_pos /*[P,H]*/,
+                       float *d_type /*[H]*/, float *dgamma, float *dbeta, void *stream);
+
+/* Backward of kbner_gather_tagproj_fwd: d_hidden (fp32 [R*S,H], pre-zeroed by the caller; touched rows are
+ * written), dW / db ACCUMULATED into. */
+int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
+                             const uint8_t *drop_keep, const float *W, const float *dlogits /*[B,T,L]*/,
+                             int B, int T, int S, int H, int L,
+                             float *d_hidden, float *dW /*[L,H]*/, float *db /*[L]*/, void *stream);
+
+/* out[0] += sum_i g[i]^2 (gradient norm over a flat arena). */
+int kbner_sumsq_f32(const float *g, size_t n, float *out, void *stream);
+/* coef[0] = min(1, max_norm / (sqrt(sumsq[0]) * pre_scale + 1e-6))  -- torch.nn.utils.clip_grad_norm_ on the device. */
+int kbner_clip_coef(const float *sumsq, float pre_scale, float max_norm, float *coef, void *stream);
+/* Fused AdamW (transformers-3.0.0 AdamW semantics: bias correction, eps outside the sqrt, decoupled decay) over a
+ * flat fp32 arena; the gradient is read as g * gscale_host * (gscale_dev ? *gscale_dev : 1). */
+int kbner_adamw_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, const float *gscale_dev, float gscale_host,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,16 @@ SIGNATURES = {
     "kbner_layernorm_fwd": ([_c_void_p] * 3 + [_c_float, _c_int, _c_int] + [_c_void_p] * 4, _c_int),
     "kbner_gather_tagproj_fwd": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
     "kbner_gemm_bf16_tn": ([_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p], _c_int),
+    "kbner_gemm_bf16": ([_c_void_p] * 6 + [_c_int] * 9 + [_c_void_p], _c_int),
     "kbner_attention_fwd": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p] * 3, _c_int),
+    "kbner_layernorm_bwd": ([_c_void_p] * 5 + [_c_int] * 2 + [_c_void_p] * 4, _c_int),
+    "kbner_colsum_bf16": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
+    "kbner_embed_ln_bwd": ([_c_void_p] * 5 + [_c_float] + [_c_int] * 4 + [_c_void_p] * 7, _c_int),
+    "kbner_gather_tagproj_bwd": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 4, _c_int),
+    "kbner_sumsq_f32": ([_c_void_p, ctypes.c_size_t, _c_void_p, _c_void_p], _c_int),
+    "kbner_clip_coef": ([_c_void_p, _c_float, _c_float, _c_void_p, _c_void_p], _c_int),
+    "kbner_adamw_step": ([_c_void_p] * 4 + [ctypes.c_size_t] + [_c_float] * 5 + [_c_int, _c_void_p, _c_float, _c_void_p],
+                         _c_int),
 }
 
 _lib = None

@@ -1,18 +1,27 @@
-// bf16 "TN" GEMM on the 5th-gen tensor cores:  C[M,N] = epilogue(A[M,K] . B[N,K]^T).
-// This is every dense projection of the XLM-R encoder the reference runs through
-// transformers' torch.nn.Linear (call site /root/reference/flair/embeddings.py:3269;
-// SURVEY.md E2 QKV, E4 attention-out, E5 FFN-up + GELU, E6 FFN-down).
+// bf16 GEMM on the 5th-gen tensor cores, CTA-pair version (tcgen05.mma.cta_group::2, UMMA M=256 N=256 K=16):
+//     C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+// This is every dense projection of the XLM-R encoder the reference runs through transformers' torch.nn.Linear
+// (call site /root/reference/flair/embeddings.py:3269; SURVEY.md E2 QKV, E4 attention-out, E5 FFN-up + GELU,
+// E6 FFN-down) and, with the operand-layout flags, their dgrad / wgrad in the fine-tuning step.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (B) bf16 tiles,
-//                              SWIZZLE_128B, 4-stage mbarrier ring
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                              (M=128, N=256, K=16) x4 per stage, accumulators in TMEM,
-//                              2 accumulator buffers (2 x 256 columns) so the epilogue of
-//                              tile i overlaps the main loop of tile i+1
-//   warps 2..9  epilogue     : tcgen05.ld 32 lanes x 32 columns -> registers -> bias /
-//                              GELU(erf) / residual -> bf16 or fp32 -> global
-// Tiles are walked m-fastest so the 148 concurrently running CTAs share one B (weight) tile.
+// Operand layouts (runtime flags; the tensor core consumes both straight from row-major global tensors):
+//   K-major  : operand stored [rows = M or N][cols = K]   (activations, torch Linear weights in the forward)
+//   MN-major : operand stored [rows = K][cols = M or N]   (dY / X in wgrad, W in dgrad: no transposes are materialised)
+//
+// Why CTA pairs: the single-CTA 128x256 kernel of the first profile (profiles/r01) moved 48 KB of operands per
+// 128x256x64 block (85 FLOP/B); a pair computes 256x256 with each CTA staging its own 128 rows of A and HALF of B
+// (32 KB per CTA per k-block, 131 FLOP/B) and the tensor cores of both SMs read B from both shared memories.
+//
+// Cluster (2,1,1), persistent; cluster c walks tiles c, c+C, ... in n-fastest order (concurrent clusters share one A
+// row panel, B stays L2-resident).  Warp roles -- every role branch is WARP-UNIFORM and only the instruction that
+// must be issued once is under elect.sync (a lane-0 branch made ptxas wrap every UTCHMMA in an ELECT / R2UR loop,
+// ~100 instructions per k-block, which capped the tensor pipe at ~63 %):
+//   warp 0      TMA producer (both CTAs): A + B stage tiles, SWIZZLE_128B, 6-stage ring; transaction bytes of BOTH
+//               CTAs complete on the leader's `full` barrier
+//   warp 1      MMA issuer (leader CTA): 4 x tcgen05.mma per stage; tcgen05.commit multicast frees the stage in both
+//               CTAs / publishes the accumulator
+//   warps 2..9  epilogue (both CTAs, own 128 accumulator rows): operand rows (residual / GELU input) prefetched before
+//               the accumulator is ready, bias loads overlapped with tcgen05.ld, TMEM double-buffered (2 x 256 cols)
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -21,14 +30,13 @@
 
 namespace kbner {
 
-constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
+constexpr int BM = 256, BN = 256, BK = 64, kStages = 6;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+constexpr uint32_t kABytes = 128 * BK * 2, kBBytes = 128 * BK * 2;   // per CTA per stage
 constexpr uint32_t kTmemCols = 512;
 
 struct GemmSmem {
-    // tiles first: SWIZZLE_128B needs 1024-B alignment (every tile size is a multiple of 1024)
     uint8_t a[kStages][kABytes];
     uint8_t b[kStages][kBBytes];
     uint64_t full[kStages];
@@ -38,24 +46,108 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    // HF "gelu": x * 0.5 * (1 + erf(x / sqrt(2)))
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's smem, transaction bytes complete on the barrier at `bar_cluster_addr`
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the barrier at the same smem offset in every CTA of `mask` when all prior MMAs have retired
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar_addr, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar_addr), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 output ulp): 2 MUFU + ~12 FMA-pipe ops,
+// about half of erff().  HF "gelu" = x * 0.5 * (1 + erf(x / sqrt(2))).
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float e = exp2f(-1.4426950408889634f * ax * ax);
+    return copysignf(fmaf(-p, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+// d/dx gelu(x) = 0.5 (1 + erf(x/sqrt2)) + x * exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float gelu_grad(float x) {
+    return fmaf(x * 0.3989422804014327f, exp2f(-0.7213475204444817f * x * x), 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f)));
+}
+
+struct GemmArgs {
+    const float *bias;        // [N] or NULL
+    const uint16_t *aux;      // bf16 [M,N]: residual (RESID), saved pre-activation (DGELU); NULL otherwise
+    uint16_t *aux_out;        // bf16 [M,N]: pre-activation written by BIAS_GELU when non-NULL (training forward)
+    void *C;
+    int M, N, K, ldc;
+    int a_mn, b_mn;           // operand layouts (0 = K-major, 1 = MN-major)
+};
+
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const float *__restrict__ bias, const uint16_t *__restrict__ resid, void *__restrict__ Cv,
-                    int M, int N, int K, int ldc) {
-    extern __shared__ uint8_t smem_raw[];
-    GemmSmem &s = *reinterpret_cast<GemmSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    GemmSmem &s = *reinterpret_cast<GemmSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int M = g.M, N = g.N, ldc = g.ldc;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int num_kb = (K + BK - 1) / BK;
+    const int num_kb = (g.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
+        if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
+            printf("kbner gemm: dynamic shared memory is not 1024-byte aligned\n");
+            __trap();
+        }
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
         for (int i = 0; i < kStages; ++i) {
@@ -64,40 +156,64 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s.tmem_full[i], 1);
-            ptx::mbar_init(&s.tmem_empty[i], kEpiWarps);
+            ptx::mbar_init(&s.tmem_empty[i], 2 * kEpiWarps);   // epilogue warps of BOTH CTAs arrive on the leader's
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc<kTmemCols>(&s.tmem_base);
+    if (warp == 1) tmem_alloc_2sm(&s.tmem_base);
     ptx::tc_fence_before();
-    __syncthreads();
+    cluster_sync();            // barriers of the peer are initialised, TMEM allocated in both CTAs
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % num_m, n_blk = tile / num_m;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(&s.empty[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&s.full[stage], kABytes + kBBytes);
-                    ptx::tma_load_2d(s.a[stage], &tmA, &s.full[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(s.b[stage], &tmB, &s.full[stage], kb * BK, n_blk * BN);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+        // ===================== TMA producer (both CTAs; warp-uniform, elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t a_smem0 = ptx::smem_u32(s.a[0]), b_smem0 = ptx::smem_u32(s.b[0]);
+        const uint32_t full0_leader = mapa(ptx::smem_u32(&s.full[0]), 0);
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int am0 = m_blk * BM + (int)rank * 128, bn0 = n_blk * BN + (int)rank * 128;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&s.empty[stage], phase ^ 1);
+                if (ptx::elect_one()) {
+                    if (leader) ptx::mbar_expect_tx(&s.full[stage], 2 * (kABytes + kBBytes));
+                    const uint32_t bar = full0_leader + stage * 8;
+                    const uint32_t a_dst = a_smem0 + stage * kABytes, b_dst = b_smem0 + stage * kBBytes;
+                    if (!g.a_mn) {
+                        tma_load_2d_2sm(a_dst, &tmA, bar, kb * BK, am0);
+                    } else {             // [K rows][M cols]: two 64-wide MN slabs of 64 k-rows each
+                        tma_load_2d_2sm(a_dst, &tmA, bar, am0, kb * BK);
+                        tma_load_2d_2sm(a_dst + 8192, &tmA, bar, am0 + 64, kb * BK);
+                    }
+                    if (!g.b_mn) {
+                        tma_load_2d_2sm(b_dst, &tmB, bar, kb * BK, bn0);
+                    } else {
+                        tma_load_2d_2sm(b_dst, &tmB, bar, bn0, kb * BK);
+                        tma_load_2d_2sm(b_dst + 8192, &tmB, bar, bn0 + 64, kb * BK);
+                    }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+        // ===================== MMA issuer (leader CTA; warp-uniform, elected lane issues) =====================
+        if (leader) {
+            const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, (uint32_t)g.a_mn, (uint32_t)g.b_mn);
+            // descriptor: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version(1)<<14 | SWIZZLE_128B(2)<<29
+            //   K-major : LBO unused (1), SBO = 1024 (8-row groups), k-step = +32 B
+            //   MN-major: LBO = 8192 (next 64-wide MN slab), SBO = 1024 (8 k-rows), k-step = 16 rows * 128 B = +2048 B
+            const uint32_t hi = 0x40004040u;
+            const uint32_t a_lo0 = ((ptx::smem_u32(s.a[0]) >> 4) & 0x3FFFu) | ((g.a_mn ? 512u : 1u) << 16);
+            const uint32_t b_lo0 = ((ptx::smem_u32(s.b[0]) >> 4) & 0x3FFFu) | ((g.b_mn ? 512u : 1u) << 16);
+            const uint32_t a_kstep = g.a_mn ? 128u : 2u, b_kstep = g.b_mn ? 128u : 2u;
+            const uint32_t empty0 = ptx::smem_u32(&s.empty[0]), tfull0 = ptx::smem_u32(&s.tmem_full[0]);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
@@ -106,175 +222,210 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&s.full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(s.a[stage]);
-                    const uint32_t b_addr = ptx::smem_u32(s.b[stage]);
+                    if (ptx::elect_one()) {
+                        const uint32_t a_lo = a_lo0 + stage * (kABytes >> 4), b_lo = b_lo0 + stage * (kBBytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = ptx::make_sw128_desc(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
-                        ptx::mma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k)
+                            mma_f16_ss_2sm(d_tmem, pack_desc(a_lo + k * a_kstep, hi), pack_desc(b_lo + k * b_kstep, hi),
+                                           idesc, (kb | k) != 0);
+                        mma_commit_mc(empty0 + stage * 8, 0b11);
                     }
-                    ptx::mma_commit(&s.empty[stage]);      // smem slot free once these MMAs retire
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::mma_commit(&s.tmem_full[acc]);         // accumulator complete -> epilogue
+                if (ptx::elect_one()) mma_commit_mc(tfull0 + acc * 8, 0b11);
+                __syncwarp();
             }
         }
     } else {
-        // ===================== epilogue =====================
-        const int ew = warp - 2;                 // 0..7
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                // which 128 of the 256 accumulator columns
+        // ===================== epilogue (both CTAs; own 128 rows of the 256-row tile) =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t tempty_leader = mapa(ptx::smem_u32(&s.tmem_empty[0]), 0);
+        const bool has_bias = g.bias != nullptr;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const int row = m_blk * BM + (int)rank * 128 + quarter * 32 + lane;
+            const bool row_ok = row < M;
+            const int colbase = n_blk * BN + half * (BN / 2);
+            // operand rows that do not depend on the accumulator: fetch them while the main loop still runs
+            uint4 raux[16];
+            if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
+                const uint16_t *rrow = g.aux + (size_t)(row_ok ? row : 0) * ldc + colbase;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    raux[i] = (row_ok && colbase + i * 8 < N) ? ld_nc_v4(rrow + i * 8) : make_uint4(0, 0, 0, 0);
+            }
             ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + quarter * 32 + lane;
-            const bool row_ok = row < M;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < (BN / 2) / 32; ++c) {
-                const int col0 = n_blk * BN + half * (BN / 2) + c * 32;
+                const int col0 = colbase + c * 32;
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * 32;
                 ptx::tmem_ld_32x32b_x32(taddr, r);
+                float bv[32];
+                if (has_bias) {                        // bias loads overlap the TMEM load
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col0 + i < N) t = __ldg(reinterpret_cast<const float4 *>(g.bias + col0 + i));
+                        bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) bv[i] = 0.0f;
+                }
+                float cold[32];
+                if (EPI == KBNER_EPI_ACCUM_F32) {      // C += acc : old values fetched while the TMEM load flies
+                    const float *crow = reinterpret_cast<const float *>(g.C) + (size_t)(row_ok ? row : 0) * ldc + col0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok && col0 + i < N) t = *reinterpret_cast<const float4 *>(crow + i);
+                        cold[i] = t.x; cold[i + 1] = t.y; cold[i + 2] = t.z; cold[i + 3] = t.w;
+                    }
+                }
                 ptx::tmem_ld_wait();
-                if (col0 < N) {      // warp-uniform
+                if (col0 < N && row_ok) {
                     float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (EPI != KBNER_EPI_NONE_F32) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (col0 + i < N) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + col0 + i));
-                                v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-                            }
-                        }
-                    }
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
                     if (EPI == KBNER_EPI_BIAS_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                    }
-                    if (row_ok) {
-                        if (EPI == KBNER_EPI_BIAS || EPI == KBNER_EPI_BIAS_GELU) {
-                            uint16_t *crow = reinterpret_cast<uint16_t *>(Cv) + (size_t)row * ldc + col0;
+                        if (g.aux_out) {               // training forward: keep the pre-activation for the backward pass
+                            uint16_t *prow = g.aux_out + (size_t)row * ldc + col0;
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
                                 if (col0 + i < N) {
                                     uint4 o;
-                                    o.x = pack_bf16x2(v[i], v[i + 1]);
-                                    o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                                    o.z = pack_bf16x2(v[i + 4], v[i + 5]);
-                                    o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                                    *reinterpret_cast<uint4 *>(crow + i) = o;
+                                    o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                                    o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                                    *reinterpret_cast<uint4 *>(prow + i) = o;
                                 }
                             }
-                        } else {
-                            if (EPI == KBNER_EPI_BIAS_RESID_F32) {
-                                const uint16_t *rrow = resid + (size_t)row * ldc + col0;
+                        }
 #pragma unroll
-                                for (int i = 0; i < 32; i += 8) {
-                                    if (col0 + i < N) {
-                                        const uint4 rv = *reinterpret_cast<const uint4 *>(rrow + i);
-                                        float a0, a1;
-                                        unpack_bf16x2(rv.x, a0, a1); v[i] += a0; v[i + 1] += a1;
-                                        unpack_bf16x2(rv.y, a0, a1); v[i + 2] += a0; v[i + 3] += a1;
-                                        unpack_bf16x2(rv.z, a0, a1); v[i + 4] += a0; v[i + 5] += a1;
-                                        unpack_bf16x2(rv.w, a0, a1); v[i + 6] += a0; v[i + 7] += a1;
-                                    }
-                                }
-                            }
-                            float *crow = reinterpret_cast<float *>(Cv) + (size_t)row * ldc + col0;
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                    }
+                    if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                if (col0 + i < N)
-                                    *reinterpret_cast<float4 *>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < 32; i += 8) {
+                            const uint4 rv = raux[c * 4 + i / 8];
+                            float a[8];
+                            unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
+                            unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                if (EPI == KBNER_EPI_BIAS_RESID_F32) v[i + e] += a[e];
+                                else v[i + e] *= gelu_grad(a[e]);
                             }
+                        }
+                    }
+                    if (EPI == KBNER_EPI_BIAS || EPI == KBNER_EPI_BIAS_GELU || EPI == KBNER_EPI_DGELU_BF16) {
+                        uint16_t *crow = reinterpret_cast<uint16_t *>(g.C) + (size_t)row * ldc + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            if (col0 + i < N) {
+                                uint4 o;
+                                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                                *reinterpret_cast<uint4 *>(crow + i) = o;
+                            }
+                        }
+                    } else {
+                        if (EPI == KBNER_EPI_ACCUM_F32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += cold[i];
+                        }
+                        float *crow = reinterpret_cast<float *>(g.C) + (size_t)row * ldc + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (col0 + i < N)
+                                *reinterpret_cast<float4 *>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         }
                     }
                 }
             }
-            // this warp has drained its part of the accumulator
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s.tmem_empty[acc]);
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    cluster_sync();            // nobody leaves while the peer may still touch this CTA's smem / barriers / TMEM
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<kTmemCols>(tmem_base);
+        tmem_dealloc_2sm(tmem_base);
     }
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const float *bias, const uint16_t *resid,
-                       void *C, int M, int N, int K, int ldc, cudaStream_t st) {
-    const size_t smem = sizeof(GemmSmem) + 1024;
+static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &g, cudaStream_t st) {
+    const size_t smem = sizeof(GemmSmem);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return KBNER_ECUDA;
         }
         configured = true;
     }
-    const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-    gemm_bf16_tn_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, bias, resid, C, M, N, K, ldc);
-    KBNER_CHECK_LAUNCH("gemm_bf16_tn");
+    const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+    gemm_bf16_kernel<EPI><<<clusters * 2, kGemmThreads, smem, st>>>(tmA, tmB, g);
+    KBNER_CHECK_LAUNCH("gemm_bf16");
     return KBNER_OK;
 }
-
-int gemm2_dispatch(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *residual, void *C, int M,
-                   int N, int K, int lda, int ldb, int ldc, int epilogue, cudaStream_t st);   // gemm2_tcgen05.cu
 
 }  // namespace kbner
 
 using namespace kbner;
 
-static int gemm_impl_choice() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("KBNER_GEMM");
-        v = (e && e[0] == '2') ? 2 : 1;
-    }
-    return v;
-}
-
-extern "C" int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias,
-                                  const uint16_t *residual, void *C, int M, int N, int K, int lda, int ldb,
-                                  int ldc, int epilogue, void *stream) {
+extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *aux,
+                               uint16_t *aux_out, void *C, int M, int N, int K, int lda, int ldb, int ldc,
+                               int a_mn_major, int b_mn_major, int epilogue, void *stream) {
     KBNER_CHECK_ARG(A && B && C, "gemm: null pointer");
     KBNER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     KBNER_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0,
                     "gemm: N, K and leading dimensions must be multiples of 8 (N=%d K=%d lda=%d ldb=%d ldc=%d)", N, K,
                     lda, ldb, ldc);
-    KBNER_CHECK_ARG(epilogue == KBNER_EPI_NONE_F32 || bias, "gemm: epilogue %d needs a bias", epilogue);
-    KBNER_CHECK_ARG(epilogue != KBNER_EPI_BIAS_RESID_F32 || residual, "gemm: residual epilogue without residual");
+    KBNER_CHECK_ARG(!a_mn_major || M % 8 == 0, "gemm: MN-major A needs M %% 8 == 0 (M=%d)", M);
+    KBNER_CHECK_ARG((epilogue != KBNER_EPI_BIAS_RESID_F32 && epilogue != KBNER_EPI_DGELU_BF16) || aux,
+                    "gemm: epilogue %d needs the aux operand", epilogue);
     KBNER_CHECK_ARG(((uintptr_t)C & 15u) == 0 && (!bias || ((uintptr_t)bias & 15u) == 0) &&
-                        (!residual || ((uintptr_t)residual & 15u) == 0),
-                    "gemm: C / bias / residual must be 16-byte aligned");
-    if (gemm_impl_choice() == 2)
-        return gemm2_dispatch(A, B, bias, residual, C, M, N, K, lda, ldb, ldc, epilogue, (cudaStream_t)stream);
+                        (!aux || ((uintptr_t)aux & 15u) == 0) && (!aux_out || ((uintptr_t)aux_out & 15u) == 0),
+                    "gemm: C / bias / aux must be 16-byte aligned");
     CUtensorMap tmA, tmB;
-    int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    int rc;
+    // K-major operand: tensor [rows = M|N][cols = K], box 128 rows x 64 k.  MN-major: [rows = K][cols = M|N], box 64 k x 64 mn.
+    rc = a_mn_major ? make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64)
+                    : make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, BK);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
+    rc = b_mn_major ? make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
+                    : make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, BK);
     if (rc) return rc;
+    GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, bias, residual, C, M, N, K, ldc, st);
-        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(tmA, tmB, bias, residual, C, M, N, K, ldc, st);
-        case KBNER_EPI_BIAS_RESID_F32:
-            return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(tmA, tmB, bias, residual, C, M, N, K, ldc, st);
-        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(tmA, tmB, bias, residual, C, M, N, K, ldc, st);
+        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, g, st);
+        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(tmA, tmB, g, st);
+        case KBNER_EPI_BIAS_RESID_F32: return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(tmA, tmB, g, st);
+        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(tmA, tmB, g, st);
+        case KBNER_EPI_DGELU_BF16: return launch_gemm<KBNER_EPI_DGELU_BF16>(tmA, tmB, g, st);
+        case KBNER_EPI_ACCUM_F32: return launch_gemm<KBNER_EPI_ACCUM_F32>(tmA, tmB, g, st);
         default: set_error("gemm: unknown epilogue %d", epilogue); return KBNER_EINVAL;
     }
+}
+
+// The forward "TN" call of round 1 (both operands K-major, torch.nn.Linear layout).
+extern "C" int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias,
+                                  const uint16_t *residual, void *C, int M, int N, int K, int lda, int ldb,
+                                  int ldc, int epilogue, void *stream) {
+    KBNER_CHECK_ARG(epilogue == KBNER_EPI_NONE_F32 || bias, "gemm: epilogue %d needs a bias", epilogue);
+    return kbner_gemm_bf16(A, B, bias, residual, nullptr, C, M, N, K, lda, ldb, ldc, 0, 0, epilogue, stream);
 }

@@ -1,0 +1,445 @@
+// HBM-bound kernels of the fine-tuning step (backward of LayerNorm / embedding / tag projection, bias gradients,
+// gradient norm, fused AdamW).  The reference gets all of these from autograd + transformers.AdamW
+// (/root/reference/flair/trainers/finetune_trainer.py:939-957 backward, :1007-1023 clip / step / zero_grad);
+// here each is one coalesced pass.
+#include "common.cuh"
+
+namespace kbner {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm backward.  x = saved fp32 pre-LN sum, dout = grad w.r.t. the LN output (fp32),
+//   xhat = (x - mean) * rstd,  g = dout * gamma,
+//   dx   = rstd * (g - mean_H(g) - xhat * mean_H(g * xhat))          -> bf16 (operand of the dgrad / wgrad GEMMs)
+//   dgamma += sum_rows dout * xhat,  dbeta += sum_rows dout          (fp32, accumulated)
+// One warp per row, rows strided over a persistent grid; per-lane partial dgamma/dbeta in registers, reduced
+// through shared memory, one atomic per column per block.
+// ------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout, const float *__restrict__ gamma,
+                     const float *__restrict__ mean, const float *__restrict__ rstd, int M,
+                     uint16_t *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    constexpr int H = VPL * 128;
+    __shared__ float s_red[2][H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    __syncthreads();
+    float4 gm[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+    float4 ag[VPL], ab[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+    for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
+        const float mu = mean[row], rs = rstd[row];
+        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * H);
+        const float4 *dr = reinterpret_cast<const float4 *>(dout + (size_t)row * H);
+        float4 xh[VPL], g[VPL];
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const uint4 ux = ld_nc_v4(xr + i * 32 + lane), ud = ld_nc_v4(dr + i * 32 + lane);
+            const float4 xv = make_float4(__uint_as_float(ux.x), __uint_as_float(ux.y), __uint_as_float(ux.z), __uint_as_float(ux.w));
+            const float4 dv = make_float4(__uint_as_float(ud.x), __uint_as_float(ud.y), __uint_as_float(ud.z), __uint_as_float(ud.w));
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
+            s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+            ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+            ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+        }
+        const float m1 = warp_sum(s1) * (1.0f / H), m2 = warp_sum(s2) * (1.0f / H);
+        uint16_t *o = dx + (size_t)row * H;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            uint2 p;
+            p.x = pack_bf16x2(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2));
+            p.y = pack_bf16x2(rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
+            *reinterpret_cast<uint2 *>(o + (i * 32 + lane) * 4) = p;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        atomicAdd(&s_red[0][c + 0], ag[i].x); atomicAdd(&s_red[0][c + 1], ag[i].y);
+        atomicAdd(&s_red[0][c + 2], ag[i].z); atomicAdd(&s_red[0][c + 3], ag[i].w);
+        atomicAdd(&s_red[1][c + 0], ab[i].x); atomicAdd(&s_red[1][c + 1], ab[i].y);
+        atomicAdd(&s_red[1][c + 2], ab[i].z); atomicAdd(&s_red[1][c + 3], ab[i].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        atomicAdd(&dgamma[i], s_red[0][i]);
+        atomicAdd(&dbeta[i], s_red[1][i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// bias gradient: db[n] += sum_m dY[m][n]   (dY bf16).  Block = 32 x 8 threads over a 256-column strip.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const uint16_t *__restrict__ dY, int M, int N, float *__restrict__ db) {
+    __shared__ float s[8][33 * 8];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + tx) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col < N) {
+        for (int r = blockIdx.y * 8 + ty; r < M; r += gridDim.y * 8) {
+            const uint4 u = ld_nc_v4(dY + (size_t)r * N + col);
+            float a, b;
+            unpack_bf16x2(u.x, a, b); acc[0] += a; acc[1] += b;
+            unpack_bf16x2(u.y, a, b); acc[2] += a; acc[3] += b;
+            unpack_bf16x2(u.z, a, b); acc[4] += a; acc[5] += b;
+            unpack_bf16x2(u.w, a, b); acc[6] += a; acc[7] += b;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[ty][tx * 8 + i + (tx >> 2)] = acc[i];
+    __syncthreads();
+    if (ty == 0 && col < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = 0.0f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += s[y][tx * 8 + i + (tx >> 2)];
+            atomicAdd(&db[col + i], t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding + LayerNorm backward: recompute x = word[id] + type[0] + pos[p] and its statistics, LayerNorm backward,
+// scatter-add dx into the word / position rows (fp32 atomics), type row and dgamma/dbeta reduced per block.
+// One warp per sub-token; position ids recomputed exactly as in the forward kernel.
+// ------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(128)
+embed_ln_bwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ word_emb,
+                    const float *__restrict__ pos_emb, const float *__restrict__ type_emb,
+                    const float *__restrict__ gamma, float eps, int pad_id, int S, const float *__restrict__ dout,
+                    float *__restrict__ d_word, float *__restrict__ d_pos, float *__restrict__ d_type,
+                    float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    constexpr int H = VPL * 128;
+    constexpr int TOK = 16;
+    __shared__ float s_red[3][H];
+    const int r = blockIdx.y, s0 = blockIdx.x * TOK;
+    const int32_t *idr = ids + (size_t)r * S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    int before = 0;
+    for (int base = 0; base < s0; base += 128) {
+        const int t = base + threadIdx.x;
+        before += __syncthreads_count(t < s0 && idr[t] != pad_id);
+    }
+    __syncthreads();
+    const int tl = s0 + (lane & (TOK - 1));
+    const int my_id = (tl < S) ? idr[tl] : pad_id;
+    const unsigned nonpad = __ballot_sync(0xffffffffu, my_id != pad_id) & 0xffffu;
+#pragma unroll 1
+    for (int q = 0; q < TOK / 4; ++q) {
+        const int local = warp * (TOK / 4) + q;
+        const int sidx = s0 + local;
+        if (sidx >= S) break;
+        const int id = __shfl_sync(0xffffffffu, my_id, local);
+        int p = pad_id;
+        if (id != pad_id) p = before + __popc(nonpad & ((2u << local) - 1u)) + pad_id;
+        const float4 *wr = reinterpret_cast<const float4 *>(word_emb + (size_t)id * H);
+        const float4 *pr = reinterpret_cast<const float4 *>(pos_emb + (size_t)p * H);
+        const float4 *tr = reinterpret_cast<const float4 *>(type_emb);
+        const float4 *dr = reinterpret_cast<const float4 *>(dout + ((size_t)r * S + sidx) * H);
+        float4 v[VPL];
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 a = __ldg(wr + i * 32 + lane), b = __ldg(tr + i * 32 + lane), c = __ldg(pr + i * 32 + lane);
+            v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(sum) * (1.0f / H);
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rs = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+        float4 g[VPL];
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 dv = __ldg(dr + i * 32 + lane);
+            const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
+            v[i] = make_float4((v[i].x - mean) * rs, (v[i].y - mean) * rs, (v[i].z - mean) * rs, (v[i].w - mean) * rs);
+            g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+            s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+            const int c = (i * 32 + lane) * 4;
+            atomicAdd(&s_red[0][c + 0], dv.x * v[i].x); atomicAdd(&s_red[0][c + 1], dv.y * v[i].y);
+            atomicAdd(&s_red[0][c + 2], dv.z * v[i].z); atomicAdd(&s_red[0][c + 3], dv.w * v[i].w);
+            atomicAdd(&s_red[1][c + 0], dv.x); atomicAdd(&s_red[1][c + 1], dv.y);
+            atomicAdd(&s_red[1][c + 2], dv.z); atomicAdd(&s_red[1][c + 3], dv.w);
+        }
+        const float m1 = warp_sum(s1) * (1.0f / H), m2 = warp_sum(s2) * (1.0f / H);
+        float *dw = d_word + (size_t)id * H, *dp = d_pos + (size_t)p * H;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            const float e0 = rs * (g[i].x - m1 - v[i].x * m2), e1 = rs * (g[i].y - m1 - v[i].y * m2);
+            const float e2 = rs * (g[i].z - m1 - v[i].z * m2), e3 = rs * (g[i].w - m1 - v[i].w * m2);
+            atomicAdd(dw + c + 0, e0); atomicAdd(dw + c + 1, e1); atomicAdd(dw + c + 2, e2); atomicAdd(dw + c + 3, e3);
+            atomicAdd(dp + c + 0, e0); atomicAdd(dp + c + 1, e1); atomicAdd(dp + c + 2, e2); atomicAdd(dp + c + 3, e3);
+            atomicAdd(&s_red[2][c + 0], e0); atomicAdd(&s_red[2][c + 1], e1);
+            atomicAdd(&s_red[2][c + 2], e2); atomicAdd(&s_red[2][c + 3], e3);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        atomicAdd(&dgamma[i], s_red[0][i]);
+        atomicAdd(&dbeta[i], s_red[1][i]);
+        atomicAdd(&d_type[i], s_red[2][i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tag-projection backward (gather + word dropout + Linear):
+//   d_hidden[row(b,t)] = keep * sum_l dlogits[b,t,l] * W[l]      (fp32 rows; the buffer is pre-zeroed, rows are unique)
+//   dW[l] += sum_{b,t} dlogits[b,t,l] * keep * x[row(b,t)],  db[l] += sum dlogits[b,t,l]
+// ------------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(256)
+gather_tagproj_bwd_kernel(const uint16_t *__restrict__ hidden, const int32_t *__restrict__ row_of,
+                          const int32_t *__restrict__ first_idx, const uint8_t *__restrict__ drop_keep,
+                          const float *__restrict__ W, const float *__restrict__ dlogits, int B, int T, int S, int L,
+                          float *__restrict__ d_hidden, float *__restrict__ dW, float *__restrict__ db) {
+    constexpr int H = CPL * 256;
+    extern __shared__ __align__(16) float sm[];     // W [L][H] then dW accumulators [L][H]
+    float *w_s = sm, *dw_s = sm + (size_t)L * H;
+    __shared__ float db_s[32];
+    for (int i = threadIdx.x; i < L * H; i += blockDim.x) { w_s[i] = W[i]; dw_s[i] = 0.0f; }
+    if (threadIdx.x < 32) db_s[threadIdx.x] = 0.0f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int w = blockIdx.x * (blockDim.x >> 5) + warp; w < B * T; w += nwarps) {
+        const int b = w / T, t = w - b * T;
+        const float dl = (lane < L) ? dlogits[(size_t)w * L + lane] : 0.0f;
+        if (lane < L && dl != 0.0f) atomicAdd(&db_s[lane], dl);
+        const int fi = first_idx[w];
+        const bool live = fi >= 0 && (!drop_keep || drop_keep[t] != 0);
+        if (!live) continue;                  // warp-uniform
+        const size_t rowi = (size_t)row_of[b] * S + fi;
+        const uint16_t *hr = hidden + rowi * H;
+        float x[CPL * 8], dh[CPL * 8];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint4 u = ld_nc_v4(hr + c * 256 + lane * 8);
+            unpack_bf16x2(u.x, x[c * 8 + 0], x[c * 8 + 1]);
+            unpack_bf16x2(u.y, x[c * 8 + 2], x[c * 8 + 3]);
+            unpack_bf16x2(u.z, x[c * 8 + 4], x[c * 8 + 5]);
+            unpack_bf16x2(u.w, x[c * 8 + 6], x[c * 8 + 7]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dh[c * 8 + e] = 0.0f;
+        }
+        for (int l = 0; l < L; ++l) {
+            const float d = __shfl_sync(0xffffffffu, dl, l);
+            const float *wl = w_s + (size_t)l * H;
+            float *dwl = dw_s + (size_t)l * H;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int col = c * 256 + lane * 8 + e;
+                    dh[c * 8 + e] = fmaf(d, wl[col], dh[c * 8 + e]);
+                    atomicAdd(&dwl[col], d * x[c * 8 + e]);
+                }
+            }
+        }
+        float *o = d_hidden + rowi * H;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            *reinterpret_cast<float4 *>(o + c * 256 + lane * 8) = make_float4(dh[c * 8], dh[c * 8 + 1], dh[c * 8 + 2], dh[c * 8 + 3]);
+            *reinterpret_cast<float4 *>(o + c * 256 + lane * 8 + 4) = make_float4(dh[c * 8 + 4], dh[c * 8 + 5], dh[c * 8 + 6], dh[c * 8 + 7]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * H; i += blockDim.x)
+        if (dw_s[i] != 0.0f) atomicAdd(&dW[i], dw_s[i]);
+    if (threadIdx.x < L && db_s[threadIdx.x] != 0.0f) atomicAdd(&db[threadIdx.x], db_s[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gradient norm (sum of squares, accumulated into out[0]) and fused AdamW over a flat parameter arena.
+// AdamW = transformers-3.0.0 `AdamW` as constructed at finetune_trainer.py:552-571 (betas 0.9/0.999, eps 1e-6,
+// correct_bias=True, weight_decay 0 applied decoupled AFTER the Adam update):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps);  p -= lr*wd*p
+// g is scaled by `gscale` first (1/accumulation x clip coefficient, :939-946, :1010).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ g, size_t n, float *__restrict__ out) {
+    float acc = 0.0f;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float t = g[n4 * 4 + threadIdx.x]; acc += t * t; }
+    acc = warp_sum(acc);
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = s[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, size_t n,
+             float lr, float b1, float b2, float eps, float wd, float step_size, const float *__restrict__ gscale_ptr,
+             float gscale_host) {
+    // clip coefficient may live on the device (computed from the norm without a host sync)
+    const float gs = gscale_host * (gscale_ptr ? *gscale_ptr : 1.0f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gs;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float pi = p[i] - step_size * mi / (sqrtf(vi) + eps);
+        if (wd != 0.0f) pi -= lr * wd * pi;
+        p[i] = pi;
+    }
+}
+
+// clip coefficient on the device: coef = min(1, max_norm / (sqrt(sumsq) * pre + 1e-6))  (torch clip_grad_norm_)
+__global__ void clip_coef_kernel(const float *__restrict__ sumsq, float pre, float max_norm, float *__restrict__ coef) {
+    const float nrm = sqrtf(*sumsq) * pre;
+    *coef = fminf(1.0f, max_norm / (nrm + 1e-6f));
+}
+
+}  // namespace kbner
+
+using namespace kbner;
+
+#define DISPATCH_VPL_T(H, CALL)                                                                   \
+    switch ((H) / 128) {                                                                          \
+        case 2: { constexpr int VPL = 2; CALL; } break;                                           \
+        case 4: { constexpr int VPL = 4; CALL; } break;                                           \
+        case 6: { constexpr int VPL = 6; CALL; } break;                                           \
+        case 8: { constexpr int VPL = 8; CALL; } break;                                           \
+        default: set_error("hidden size %d not built (supported: 256, 512, 768, 1024)", (H));     \
+                 return KBNER_EUNSUPPORTED;                                                       \
+    }
+
+extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const float *gamma, const float *mean,
+                                   const float *rstd, int M, int H, uint16_t *dx, float *dgamma, float *dbeta,
+                                   void *stream) {
+    KBNER_CHECK_ARG(x && dout && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+    KBNER_CHECK_ARG(M >= 0 && H % 128 == 0, "layernorm_bwd: bad shape");
+    if (M == 0) return KBNER_OK;
+    int blocks = (M + 7) / 8;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL><<<blocks, 256, 0, st>>>(x, dout, gamma, mean, rstd, M, dx, dgamma, dbeta)));
+    KBNER_CHECK_LAUNCH("layernorm_bwd");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_colsum_bf16(const uint16_t *dY, int M, int N, float *db, void *stream) {
+    KBNER_CHECK_ARG(dY && db && M >= 0 && N > 0 && N % 8 == 0, "colsum_bf16: bad arguments");
+    if (M == 0) return KBNER_OK;
+    dim3 grid((N + 255) / 256, 32);
+    if ((int)grid.y * 8 > M) grid.y = (M + 7) / 8;
+    colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, M, N, db);
+    KBNER_CHECK_LAUNCH("colsum_bf16");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_embed_ln_bwd(const int32_t *ids, const float *word_emb, const float *pos_emb,
+                                  const float *type_emb, const float *gamma, float eps, int pad_id, int R, int S,
+                                  int H, const float *dout, float *d_word, float *d_pos, float *d_type,
+                                  float *dgamma, float *dbeta, void *stream) {
+    KBNER_CHECK_ARG(ids && word_emb && pos_emb && type_emb && gamma && dout && d_word && d_pos && d_type && dgamma && dbeta,
+                    "embed_ln_bwd: null pointer");
+    if (R == 0) return KBNER_OK;
+    dim3 grid((S + 15) / 16, R);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_VPL_T(H, (embed_ln_bwd_kernel<VPL><<<grid, 128, 0, st>>>(ids, word_emb, pos_emb, type_emb, gamma, eps, pad_id, S,
+                                                                       dout, d_word, d_pos, d_type, dgamma, dbeta)));
+    KBNER_CHECK_LAUNCH("embed_ln_bwd");
+    return KBNER_OK;
+}
+
+template <int CPL>
+static int launch_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
+                              const uint8_t *drop_keep, const float *W, const float *dlogits, int B, int T, int S, int L,
+                              float *d_hidden, float *dW, float *db, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)L * CPL * 256 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gather_tagproj_bwd_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("gather_tagproj_bwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return KBNER_ECUDA;
+        }
+        configured = smem;
+    }
+    int blocks = (B * T + 7) / 8;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    gather_tagproj_bwd_kernel<CPL><<<blocks, 256, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L,
+                                                              d_hidden, dW, db);
+    KBNER_CHECK_LAUNCH("gather_tagproj_bwd");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
+                                        const uint8_t *drop_keep, const float *W, const float *dlogits, int B, int T,
+                                        int S, int H, int L, float *d_hidden, float *dW, float *db, void *stream) {
+    KBNER_CHECK_ARG(hidden && row_of && first_idx && W && dlogits && d_hidden && dW && db, "gather_tagproj_bwd: null pointer");
+    KBNER_CHECK_ARG(L >= 1 && L <= 32 && H % 256 == 0 && (size_t)2 * L * H * 4 <= 200 * 1024,
+                    "gather_tagproj_bwd: needs L <= 32 and 2*L*H*4 <= 200 KB (L=%d H=%d)", L, H);
+    if (B == 0) return KBNER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (H / 256) {
+        case 1: return launch_tagproj_bwd<1>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L, d_hidden, dW, db, st);
+        case 2: return launch_tagproj_bwd<2>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L, d_hidden, dW, db, st);
+        case 3: return launch_tagproj_bwd<3>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L, d_hidden, dW, db, st);
+        case 4: return launch_tagproj_bwd<4>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L, d_hidden, dW, db, st);
+        default: set_error("gather_tagproj_bwd: hidden size %d not built", H); return KBNER_EUNSUPPORTED;
+    }
+}
+
+extern "C" int kbner_sumsq_f32(const float *g, size_t n, float *out, void *stream) {
+    KBNER_CHECK_ARG(g && out, "sumsq: null pointer");
+    KBNER_CHECK_ARG(((uintptr_t)g & 15u) == 0, "sumsq: buffer must be 16-byte aligned");
+    if (n == 0) return KBNER_OK;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 8 * (size_t)kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks == 0) blocks = 1;
+    sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+    KBNER_CHECK_LAUNCH("sumsq");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_clip_coef(const float *sumsq, float pre_scale, float max_norm, float *coef, void *stream) {
+    KBNER_CHECK_ARG(sumsq && coef, "clip_coef: null pointer");
+    clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, pre_scale, max_norm, coef);
+    KBNER_CHECK_LAUNCH("clip_coef");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_adamw_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, const float *gscale_dev,
+                                float gscale_host, void *stream) {
+    KBNER_CHECK_ARG(p && g && m && v && step >= 1, "adamw_step: bad arguments");
+    if (n == 0) return KBNER_OK;
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_size,
+                                                                gscale_dev, gscale_host);
+    KBNER_CHECK_LAUNCH("adamw_step");
+    return KBNER_OK;
+}

@@ -172,3 +172,101 @@ def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False):
     _lib.check(_lib.load().kbner_attention_fwd(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), _ptr(lse),
                                                _stream()), "attention_fwd")
     return (out, lse) if want_lse else out
+
+
+# ---- fine-tuning step -----------------------------------------------------------------------------
+def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None):
+    """dx (bf16 [M,H]) of LayerNorm; dgamma / dbeta (fp32 [H]) are accumulated into."""
+    _chk(x, torch.float32, "x", 2)
+    _chk(dout, torch.float32, "dout", 2)
+    for n, t in (("gamma", gamma), ("mean", mean), ("rstd", rstd), ("dgamma", dgamma), ("dbeta", dbeta)):
+        _chk(t, torch.float32, n, 1)
+    M, H = x.shape
+    if out is None:
+        out = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().kbner_layernorm_bwd(_ptr(x), _ptr(dout), _ptr(gamma), _ptr(mean), _ptr(rstd), M, H, _ptr(out),
+                                               _ptr(dgamma), _ptr(dbeta), _stream()), "layernorm_bwd")
+    return out
+
+
+def colsum_bf16(dY, db):
+    _chk(dY, torch.bfloat16, "dY", 2)
+    _chk(db, torch.float32, "db", 1)
+    M, N = dY.shape
+    _lib.check(_lib.load().kbner_colsum_bf16(_ptr(dY), M, N, _ptr(db), _stream()), "colsum_bf16")
+    return db
+
+
+def embed_ln_bwd(ids, word_emb, pos_emb, type_emb, gamma, eps, pad_id, dout, d_word, d_pos, d_type, dgamma, dbeta):
+    _chk(ids, torch.int32, "ids", 2)
+    _chk(dout, torch.float32, "dout", 2)
+    for n, t in (("d_word", d_word), ("d_pos", d_pos), ("d_type", d_type), ("dgamma", dgamma), ("dbeta", dbeta)):
+        _chk(t, torch.float32, n)
+    R, S = ids.shape
+    H = word_emb.shape[1]
+    _lib.check(_lib.load().kbner_embed_ln_bwd(_ptr(ids), _ptr(word_emb), _ptr(pos_emb), _ptr(type_emb), _ptr(gamma),
+                                              float(eps), int(pad_id), R, S, H, _ptr(dout), _ptr(d_word), _ptr(d_pos),
+                                              _ptr(d_type), _ptr(dgamma), _ptr(dbeta), _stream()), "embed_ln_bwd")
+
+
+def gather_tagproj_bwd(hidden, row_of, first_idx, W, dlogits, S, d_hidden, dW, db, drop_keep=None):
+    _chk(hidden, torch.bfloat16, "hidden", 2)
+    _chk(dlogits, torch.float32, "dlogits", 3)
+    _chk(d_hidden, torch.float32, "d_hidden", 2)
+    _chk(dW, torch.float32, "dW", 2)
+    _chk(db, torch.float32, "db", 1)
+    B, T = first_idx.shape
+    L, H = W.shape
+    _lib.check(_lib.load().kbner_gather_tagproj_bwd(_ptr(hidden), _ptr(row_of), _ptr(first_idx), _ptr(drop_keep), _ptr(W),
+                                                    _ptr(dlogits), B, T, int(S), H, L, _ptr(d_hidden), _ptr(dW),
+                                                    _ptr(db), _stream()), "gather_tagproj_bwd")
+
+
+def sumsq_f32(g, out):
+    _chk(g, torch.float32, "g", 1)
+    _chk(out, torch.float32, "out", 1)
+    _lib.check(_lib.load().kbner_sumsq_f32(_ptr(g), g.numel(), _ptr(out), _stream()), "sumsq_f32")
+    return out
+
+
+def clip_coef(sumsq, pre_scale, max_norm, coef):
+    _lib.check(_lib.load().kbner_clip_coef(_ptr(sumsq), float(pre_scale), float(max_norm), _ptr(coef), _stream()),
+               "clip_coef")
+    return coef
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale_dev=None, gscale_host=1.0):
+    for n, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+        _chk(t, torch.float32, n, 1)
+    _lib.check(_lib.load().kbner_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1),
+                                            float(beta2), float(eps), float(weight_decay), int(step), _ptr(gscale_dev),
+                                            float(gscale_host), _stream()), "adamw_step")
+
+
+EPI_DGELU_BF16, EPI_ACCUM_F32 = 4, 5
+
+
+def gemm_bf16(A, B, M, N, K, epilogue, bias=None, aux=None, aux_out=None, out=None, a_mn=False, b_mn=False):
+    """General tensor-core GEMM  C[M,N] = epilogue(sum_k A(m,k) B(n,k)).
+    a_mn / b_mn: the operand is stored [K][M|N] (MN-major) instead of [M|N][K].  See include/kbner_b200.h."""
+    _chk(A, torch.bfloat16, "A", 2)
+    _chk(B, torch.bfloat16, "B", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(aux, torch.bfloat16, "aux", 2)
+    _chk(aux_out, torch.bfloat16, "aux_out", 2)
+    exp_a = (K, M) if a_mn else (M, K)
+    exp_b = (K, N) if b_mn else (N, K)
+    if tuple(A.shape) != exp_a or tuple(B.shape) != exp_b:
+        raise _lib.KbnerError("gemm: operand shapes %s / %s do not match M=%d N=%d K=%d (a_mn=%s b_mn=%s)" %
+                              (tuple(A.shape), tuple(B.shape), M, N, K, a_mn, b_mn))
+    odt = torch.bfloat16 if epilogue in (EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU_BF16) else torch.float32
+    if out is None:
+        if epilogue == EPI_ACCUM_F32:
+            raise _lib.KbnerError("gemm: EPI_ACCUM_F32 accumulates into `out`; pass it")
+        out = torch.empty((M, N), dtype=odt, device=A.device)
+    else:
+        _chk(out, odt, "out", 2)
+    _lib.check(_lib.load().kbner_gemm_bf16(_ptr(A), _ptr(B), _ptr(bias), _ptr(aux), _ptr(aux_out), _ptr(out), M, N, K,
+                                           A.shape[1], B.shape[1], N, int(bool(a_mn)), int(bool(b_mn)), int(epilogue),
+                                           _stream()), "gemm_bf16")
+    return out

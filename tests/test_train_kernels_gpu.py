@@ -1,0 +1,184 @@
+"""GPU parity of the fine-tuning kernels (through the C ABI) against fp32 torch restatements of the same ops:
+operand-layout variants of the tensor-core GEMM (dgrad / wgrad read W, dY, X in place), GELU-derivative and
+accumulate epilogues, LayerNorm / embedding / tag-projection backward, bias gradients, gradient norm, AdamW."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import kbner_b200
+    from kbner_b200 import ops as o
+    kbner_b200._lib.check(kbner_b200._lib.load().kbner_device_check(0), "device_check")
+    return o
+
+
+def _rand(g, *shape, scale=0.5):
+    return (torch.randn(*shape, device="cuda", generator=g) * scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 1024, 1024), (1000, 264, 200), (4096, 1024, 4096)])
+def test_gemm_dgrad_layout(ops, M, N, K):
+    """dX[M,N] = dY[M,K] . W[K,N]  -- W (torch Linear weight [out=K, in=N]) is read MN-major, no transpose."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dy = _rand(g, M, K).bfloat16()
+    w = _rand(g, K, N).bfloat16()
+    out = ops.gemm_bf16(dy, w, M, N, K, ops.EPI_NONE_F32, b_mn=True)
+    ref = dy.float() @ w.float()
+    assert bool(((out - ref).abs() <= 1e-5 * ref.abs() + 2e-3 * math.sqrt(K / 1024.0)).all())
+
+
+@pytest.mark.parametrize("T,N1,N2", [(64, 256, 256), (512, 1024, 1024), (1000, 264, 520), (4096, 4096, 1024)])
+def test_gemm_wgrad_layout_accumulate(ops, T, N1, N2):
+    """dW[N1,N2] += dY[T,N1]^T . X[T,N2]  -- both operands read MN-major in place, fp32 accumulate epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(T + N1 + N2)
+    dy = _rand(g, T, N1).bfloat16()
+    x = _rand(g, T, N2).bfloat16()
+    dw0 = _rand(g, N1, N2)
+    dw = dw0.clone()
+    ops.gemm_bf16(dy, x, N1, N2, T, ops.EPI_ACCUM_F32, out=dw, a_mn=True, b_mn=True)
+    ref = dw0 + dy.float().t() @ x.float()
+    assert bool(((dw - ref).abs() <= 1e-5 * ref.abs() + 2e-3 * math.sqrt(T / 1024.0)).all())
+
+
+def test_gemm_gelu_saves_preactivation_and_dgelu(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 512, 1024, 256
+    x = _rand(g, M, K).bfloat16()
+    w = _rand(g, N, K).bfloat16()
+    b = _rand(g, N)
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h = ops.gemm_bf16(x, w, M, N, K, ops.EPI_BIAS_GELU, bias=b, aux_out=pre)
+    ref_pre = x.float() @ w.float().t() + b
+    ref_h = torch.nn.functional.gelu(ref_pre)
+    assert bool(((pre.float() - ref_pre).abs() <= 2.0 ** -8 * ref_pre.abs() + 1e-2).all())
+    assert bool(((h.float() - ref_h).abs() <= 2.0 ** -8 * ref_h.abs() + 1e-2).all())
+    # dgrad through the GELU: d_pre = (d_h . W2) * gelu'(pre)
+    K2 = 256
+    dy = _rand(g, M, K2).bfloat16()
+    w2 = _rand(g, K2, N).bfloat16()                      # Linear(N -> K2) weight [out=K2, in=N]
+    dpre = ops.gemm_bf16(dy, w2, M, N, K2, ops.EPI_DGELU_BF16, aux=pre, b_mn=True)
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).backward(dy.float() @ w2.float())
+    assert bool(((dpre.float() - p.grad).abs() <= 2.0 ** -7 * p.grad.abs() + 2e-2).all())
+
+
+@pytest.mark.parametrize("H", [256, 1024])
+def test_layernorm_bwd(ops, H):
+    g = torch.Generator(device="cuda").manual_seed(H)
+    M = 777
+    x = (_rand(g, M, H, scale=2.0) + 0.3).requires_grad_(True)
+    gamma = (torch.rand(H, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = _rand(g, H, scale=0.1).requires_grad_(True)
+    dout = _rand(g, M, H, scale=1.0)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), gamma.detach(), beta.detach(), 1e-5, save_stats=True)
+    torch.nn.functional.layer_norm(x, (H,), gamma, beta, 1e-5).backward(dout)
+    dgamma = torch.zeros(H, device="cuda")
+    dbeta = torch.zeros(H, device="cuda")
+    dx = ops.layernorm_bwd(x.detach(), dout, gamma.detach(), mean, rstd, dgamma, dbeta)
+    assert bool(((dx.float() - x.grad).abs() <= 2.0 ** -8 * x.grad.abs() + 1e-4).all())
+    torch.testing.assert_close(dgamma, gamma.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(dbeta, beta.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_colsum(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    dy = _rand(g, 1500, 3072).bfloat16()
+    db = torch.ones(3072, device="cuda")
+    ops.colsum_bf16(dy, db)
+    torch.testing.assert_close(db, 1.0 + dy.float().sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_embed_ln_bwd(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    R, S, H, V, P, pad = 3, 70, 256, 500, 80, 1
+    ids = torch.randint(3, V, (R, S), device="cuda", generator=g, dtype=torch.int32)
+    ids[:, 0] = 0
+    ids[1, 40:] = 0
+    ids[2, 5] = pad
+    word = _rand(g, V, H, scale=0.05).requires_grad_(True)
+    posw = _rand(g, P, H, scale=0.05).requires_grad_(True)
+    typ = _rand(g, 1, H, scale=0.05).requires_grad_(True)
+    gamma = (torch.rand(H, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = _rand(g, H, scale=0.1).requires_grad_(True)
+    dout = _rand(g, R * S, H, scale=1.0)
+    mask = (ids != pad).int()
+    position = (torch.cumsum(mask, 1) * mask + pad).long()
+    x = word[ids.long()] + typ[0][None, None, :] + posw[position]
+    torch.nn.functional.layer_norm(x, (H,), gamma, beta, 1e-5).reshape(R * S, H).backward(dout)
+    d_word, d_pos = torch.zeros_like(word), torch.zeros_like(posw)
+    d_type, dg, db = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    ops.embed_ln_bwd(ids, word.detach(), posw.detach(), typ.detach()[0].contiguous(), gamma.detach(), 1e-5, pad, dout,
+                     d_word, d_pos, d_type, dg, db)
+    torch.testing.assert_close(d_word, word.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(d_pos, posw.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(d_type, typ.grad[0], rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(dg, gamma.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db, beta.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("L,H", [(13, 1024), (29, 256)])
+def test_gather_tagproj_bwd(ops, L, H):
+    g = torch.Generator(device="cuda").manual_seed(L)
+    R, S, B, T = 3, 64, 4, 30
+    hidden = _rand(g, R * S, H, scale=1.0).bfloat16()
+    row_of = torch.tensor([0, 1, 1, 2], dtype=torch.int32, device="cuda")
+    first = torch.stack([torch.randperm(S - 2, device="cuda", generator=g)[:T] + 1 for _ in range(B)]).to(torch.int32)
+    first[1] += 0
+    first[0, 3] = -1
+    first[3, 20:] = -1
+    first[2] = (first[2] % 30) + 31            # sentences 1 and 2 share a window row: keep their rows disjoint
+    first[1] = (first[1] % 30) + 1
+    # make indices within a sentence unique
+    for b in range(B):
+        vals = first[b][first[b] >= 0]
+        uniq = torch.unique(vals)
+        first[b] = -1
+        first[b, :uniq.numel()] = uniq
+    W = _rand(g, L, H, scale=0.05).requires_grad_(True)
+    bias = _rand(g, L).requires_grad_(True)
+    keep = (torch.rand(T, device="cuda", generator=g) > 0.2).to(torch.uint8)
+    dlog = _rand(g, B, T, L, scale=1.0)
+    hf = hidden.float().requires_grad_(True)
+    rows = row_of.long()[:, None] * S + first.long().clamp(min=0)
+    live = (first >= 0).float() * keep.float()[None, :]
+    ((hf[rows] * live[..., None]) @ W.t() + bias).backward(dlog)
+    d_hidden = torch.zeros(R * S, H, device="cuda")
+    dW, db = torch.zeros(L, H, device="cuda"), torch.zeros(L, device="cuda")
+    ops.gather_tagproj_bwd(hidden, row_of, first, W.detach(), dlog, S, d_hidden, dW, db, drop_keep=keep)
+    torch.testing.assert_close(d_hidden, hf.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dW, W.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(db, bias.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_adamw_sumsq_clip(ops):
+    """transformers-3.0.0 AdamW semantics (correct_bias, eps outside sqrt, decoupled decay) + clip_grad_norm_."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 1_000_003
+    p0 = _rand(g, n + 1)[:n].contiguous() if False else _rand(g, n)
+    p = p0.clone()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    rp, rm, rv = p0.double().clone(), torch.zeros(n, device="cuda", dtype=torch.float64), torch.zeros(n, device="cuda", dtype=torch.float64)
+    lr, b1, b2, eps, wd, max_norm, accum = 5e-3, 0.9, 0.999, 1e-6, 0.01, 5.0, 4
+    for step in range(1, 4):
+        grad = _rand(g, n, scale=3.0)
+        ss = torch.zeros(1, device="cuda")
+        ops.sumsq_f32(grad, ss)
+        torch.testing.assert_close(ss[0], grad.double().pow(2).sum().float(), rtol=1e-4, atol=0)
+        coef = torch.empty(1, device="cuda")
+        ops.clip_coef(ss, 1.0 / accum, max_norm, coef)
+        gn = grad.double() / accum
+        ref_coef = min(1.0, max_norm / (float(gn.norm()) + 1e-6))
+        assert abs(float(coef) - ref_coef) < 1e-5
+        ops.adamw_step(p, grad, m, v, lr, b1, b2, eps, wd, step, gscale_dev=coef, gscale_host=1.0 / accum)
+        gd = gn * ref_coef
+        rm = b1 * rm + (1 - b1) * gd
+        rv = b2 * rv + (1 - b2) * gd * gd
+        rp = rp - lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step) * rm / (rv.sqrt() + eps)
+        rp = rp - lr * wd * rp
+        torch.testing.assert_close(p.double(), rp, rtol=1e-5, atol=1e-6)
