@@ -57,6 +57,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// fast special-function-unit ops (1 MUFU each, ~2 ulp): enough for bf16-rounded results
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // 16-byte streaming loads/stores (data touched once: do not pollute L1)
 __device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
     uint4 r;

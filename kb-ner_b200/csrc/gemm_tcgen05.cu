@@ -30,7 +30,7 @@
 
 namespace kbner {
 
-constexpr int BM = 256, BN = 256, BK = 64, kStages = 6;
+constexpr int BM = 256, BN = 256, BK = 64, kStages = 5;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr uint32_t kABytes = 128 * BK * 2, kBBytes = 128 * BK * 2;   // per CTA per stage
@@ -39,6 +39,7 @@ constexpr uint32_t kTmemCols = 512;
 struct GemmSmem {
     uint8_t a[kStages][kABytes];
     uint8_t b[kStages][kBBytes];
+    uint8_t cstage[kEpiWarps][2][4096];     // per epilogue warp: 2 x (32 rows x 128 B) SWIZZLE_128B store staging
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint64_t tmem_full[2];
@@ -105,19 +106,19 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
 // about half of erff().  HF "gelu" = x * 0.5 * (1 + erf(x / sqrt(2))).
 __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_fast(fmaf(0.3275911f, ax, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
     p *= t;
-    const float e = exp2f(-1.4426950408889634f * ax * ax);
+    const float e = ex2_fast(-1.4426950408889634f * ax * ax);
     return copysignf(fmaf(-p, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 // d/dx gelu(x) = 0.5 (1 + erf(x/sqrt2)) + x * exp(-x^2/2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_grad(float x) {
-    return fmaf(x * 0.3989422804014327f, exp2f(-0.7213475204444817f * x * x), 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f)));
+    return fmaf(x * 0.3989422804014327f, ex2_fast(-0.7213475204444817f * x * x), 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f)));
 }
 
 struct GemmArgs {
@@ -131,7 +132,8 @@ struct GemmArgs {
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     GemmSmem &s = *reinterpret_cast<GemmSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmC);
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&s.full[i], 1);
             ptx::mbar_init(&s.empty[i], 1);
@@ -239,17 +242,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================== epilogue (both CTAs; own 128 rows of the 256-row tile) =====================
+        // Each warp owns 32 accumulator rows x 128 columns.  Results leave through a per-warp SWIZZLE_128B staging
+        // tile (32 rows x 128 B, double-buffered) and a TMA store: the row-per-thread register layout that
+        // tcgen05.ld produces would otherwise turn every 16-byte global store into 32 separate sectors (the LSU
+        // was the bottleneck of the N=1024 GEMMs in profiles/r01).  ACCUM uses the TMA reduce-add (C += tile in L2).
+        constexpr bool kBf16Out = (EPI == KBNER_EPI_BIAS || EPI == KBNER_EPI_BIAS_GELU || EPI == KBNER_EPI_DGELU_BF16);
+        constexpr int CW = kBf16Out ? 64 : 32;          // columns per chunk = one 128-byte row segment
+        constexpr int NCH = (BN / 2) / CW;
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int half = ew >> 2;
         const uint32_t tempty_leader = mapa(ptx::smem_u32(&s.tmem_empty[0]), 0);
         const bool has_bias = g.bias != nullptr;
+        uint8_t *stage_base = s.cstage[ew][0];
+        const uint32_t stage_u32 = ptx::smem_u32(stage_base);
+        uint32_t nstores = 0;                           // staging-buffer uses so far (lane 0 owns the bulk groups)
+        auto stage_and_store = [&](const uint4 (&q)[8], const CUtensorMap *map, int col0, int row_base, bool reduce_add) {
+            const uint32_t buf = nstores & 1;
+            if (nstores >= 2) {                         // the store that last read this buffer must have drained it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            uint8_t *dst = stage_base + buf * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4 *>(dst + ((j ^ (lane & 7)) << 4)) = q[j];
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t src = stage_u32 + buf * 4096;
+                if (reduce_add)
+                    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(col0), "r"(row_base) : "memory");
+                else
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(col0), "r"(row_base) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nstores;
+        };
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int row = m_blk * BM + (int)rank * 128 + quarter * 32 + lane;
+            const int row_base = m_blk * BM + (int)rank * 128 + quarter * 32;
+            const int row = row_base + lane;
             const bool row_ok = row < M;
             const int colbase = n_blk * BN + half * (BN / 2);
             // operand rows that do not depend on the accumulator: fetch them while the main loop still runs
@@ -263,97 +300,81 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < (BN / 2) / 32; ++c) {
-                const int col0 = colbase + c * 32;
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * 32;
-                ptx::tmem_ld_32x32b_x32(taddr, r);
-                float bv[32];
-                if (has_bias) {                        // bias loads overlap the TMEM load
+            for (int c = 0; c < NCH; ++c) {
+                const int col0 = colbase + c * CW;
+                float v[CW];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (col0 + i < N) t = __ldg(reinterpret_cast<const float4 *>(g.bias + col0 + i));
-                        bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+                for (int h2 = 0; h2 < CW / 32; ++h2) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * CW + h2 * 32;
+                    ptx::tmem_ld_32x32b_x32(taddr, r);
+                    float bv[32];
+                    if (has_bias) {                    // bias loads overlap the TMEM load
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col0 + h2 * 32 + i < N) t = __ldg(reinterpret_cast<const float4 *>(g.bias + col0 + h2 * 32 + i));
+                            bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bv[i] = 0.0f;
+                    }
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[h2 * 32 + i] = __uint_as_float(r[i]) + bv[i];
+                }
+                if (c == NCH - 1) {                    // accumulator fully drained: let the MMA warp reuse it
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                }
+                if (col0 >= N) continue;               // warp-uniform: whole chunk outside the matrix
+                if (EPI == KBNER_EPI_BIAS_GELU) {
+                    if (g.aux_out) {                   // training forward: keep the pre-activation for the backward pass
+                        uint4 q[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            q[j].x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); q[j].y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+                            q[j].z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); q[j].w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+                        }
+                        stage_and_store(q, &tmAux, col0, row_base, false);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
+                }
+                if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
+#pragma unroll
+                    for (int i = 0; i < CW; i += 8) {
+                        const uint4 rv = raux[(c * CW + i) / 8];
+                        float a[8];
+                        unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
+                        unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (EPI == KBNER_EPI_BIAS_RESID_F32) v[i + e] += a[e];
+                            else v[i + e] *= gelu_grad(a[e]);
+                        }
+                    }
+                }
+                uint4 q[8];
+                if (kBf16Out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        q[j].x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); q[j].y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+                        q[j].z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); q[j].w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) bv[i] = 0.0f;
+                    for (int j = 0; j < 8; ++j)
+                        q[j] = make_uint4(__float_as_uint(v[(j * 4 + 0) % CW]), __float_as_uint(v[(j * 4 + 1) % CW]),
+                                          __float_as_uint(v[(j * 4 + 2) % CW]), __float_as_uint(v[(j * 4 + 3) % CW]));
                 }
-                float cold[32];
-                if (EPI == KBNER_EPI_ACCUM_F32) {      // C += acc : old values fetched while the TMEM load flies
-                    const float *crow = reinterpret_cast<const float *>(g.C) + (size_t)(row_ok ? row : 0) * ldc + col0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok && col0 + i < N) t = *reinterpret_cast<const float4 *>(crow + i);
-                        cold[i] = t.x; cold[i + 1] = t.y; cold[i + 2] = t.z; cold[i + 3] = t.w;
-                    }
-                }
-                ptx::tmem_ld_wait();
-                if (col0 < N && row_ok) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
-                    if (EPI == KBNER_EPI_BIAS_GELU) {
-                        if (g.aux_out) {               // training forward: keep the pre-activation for the backward pass
-                            uint16_t *prow = g.aux_out + (size_t)row * ldc + col0;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                if (col0 + i < N) {
-                                    uint4 o;
-                                    o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                                    o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                                    *reinterpret_cast<uint4 *>(prow + i) = o;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                    }
-                    if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            const uint4 rv = raux[c * 4 + i / 8];
-                            float a[8];
-                            unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
-                            unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                if (EPI == KBNER_EPI_BIAS_RESID_F32) v[i + e] += a[e];
-                                else v[i + e] *= gelu_grad(a[e]);
-                            }
-                        }
-                    }
-                    if (EPI == KBNER_EPI_BIAS || EPI == KBNER_EPI_BIAS_GELU || EPI == KBNER_EPI_DGELU_BF16) {
-                        uint16_t *crow = reinterpret_cast<uint16_t *>(g.C) + (size_t)row * ldc + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            if (col0 + i < N) {
-                                uint4 o;
-                                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                                *reinterpret_cast<uint4 *>(crow + i) = o;
-                            }
-                        }
-                    } else {
-                        if (EPI == KBNER_EPI_ACCUM_F32) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += cold[i];
-                        }
-                        float *crow = reinterpret_cast<float *>(g.C) + (size_t)row * ldc + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (col0 + i < N)
-                                *reinterpret_cast<float4 *>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        }
-                    }
-                }
+                stage_and_store(q, &tmC, col0, row_base, EPI == KBNER_EPI_ACCUM_F32);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before smem goes away
+        __syncwarp();
     }
     ptx::tc_fence_before();
     cluster_sync();            // nobody leaves while the peer may still touch this CTA's smem / barriers / TMEM
@@ -364,7 +385,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmArgs &g, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmAux,
+                       const GemmArgs &g, cudaStream_t st) {
     const size_t smem = sizeof(GemmSmem);
     static bool configured = false;
     if (!configured) {
@@ -377,7 +399,7 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gem
     }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
-    gemm_bf16_kernel<EPI><<<clusters * 2, kGemmThreads, smem, st>>>(tmA, tmB, g);
+    gemm_bf16_kernel<EPI><<<clusters * 2, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmAux, g);
     KBNER_CHECK_LAUNCH("gemm_bf16");
     return KBNER_OK;
 }
@@ -409,15 +431,24 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     rc = b_mn_major ? make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
                     : make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, BK);
     if (rc) return rc;
+    const bool bf16_out = (epilogue == KBNER_EPI_BIAS || epilogue == KBNER_EPI_BIAS_GELU || epilogue == KBNER_EPI_DGELU_BF16);
+    CUtensorMap tmC, tmAux;
+    rc = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, bf16_out ? 64 : 32, bf16_out ? 2 : 4);
+    if (rc) return rc;
+    tmAux = tmC;
+    if (aux_out) {
+        rc = make_tmap_2d(&tmAux, aux_out, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 64, 2);
+        if (rc) return rc;
+    }
     GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, g, st);
-        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(tmA, tmB, g, st);
-        case KBNER_EPI_BIAS_RESID_F32: return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(tmA, tmB, g, st);
-        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(tmA, tmB, g, st);
-        case KBNER_EPI_DGELU_BF16: return launch_gemm<KBNER_EPI_DGELU_BF16>(tmA, tmB, g, st);
-        case KBNER_EPI_ACCUM_F32: return launch_gemm<KBNER_EPI_ACCUM_F32>(tmA, tmB, g, st);
+        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_BIAS_RESID_F32: return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_DGELU_BF16: return launch_gemm<KBNER_EPI_DGELU_BF16>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_ACCUM_F32: return launch_gemm<KBNER_EPI_ACCUM_F32>(tmA, tmB, tmC, tmAux, g, st);
         default: set_error("gemm: unknown epilogue %d", epilogue); return KBNER_EINVAL;
     }
 }

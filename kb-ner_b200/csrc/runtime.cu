@@ -42,9 +42,9 @@ static PFN_encodeTiled get_encode() {
 struct TmapKey {
     const void *base;
     uint64_t rows, cols, ld;
-    uint32_t br, bc;
+    uint32_t br, bc, eb;
     bool operator==(const TmapKey &o) const {
-        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && br == o.br && bc == o.bc;
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && br == o.br && bc == o.bc && eb == o.eb;
     }
 };
 struct TmapHash {
@@ -53,16 +53,16 @@ struct TmapHash {
         h = h * 1000003u ^ k.rows;
         h = h * 1000003u ^ k.cols;
         h = h * 1000003u ^ k.ld;
-        h = h * 1000003u ^ ((uint64_t)k.br << 32 | k.bc);
+        h = h * 1000003u ^ ((uint64_t)k.br << 32 | k.bc << 4 | k.eb);
         return h;
     }
 };
 
-int make_tmap_bf16_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols, uint32_t elem_bytes) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
-    TmapKey key{base, rows, cols, ld, box_rows, box_cols};
+    TmapKey key{base, rows, cols, ld, box_rows, box_cols, elem_bytes};
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -76,16 +76,17 @@ int make_tmap_bf16_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_
         set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
         return KBNER_ECUDA;
     }
-    if (((uintptr_t)base & 15u) != 0 || (ld * 2) % 16 != 0 || box_cols * 2 != 128 || box_rows > 256) {
-        set_error("tensor map: base must be 16-B aligned, ld*2 a multiple of 16, box 64 x <=256 (got ld=%llu box=%ux%u)",
-                  (unsigned long long)ld, box_rows, box_cols);
+    if (((uintptr_t)base & 15u) != 0 || (ld * elem_bytes) % 16 != 0 || box_cols * elem_bytes != 128 || box_rows > 256 ||
+        (elem_bytes != 2 && elem_bytes != 4)) {
+        set_error("tensor map: base must be 16-B aligned, row pitch a multiple of 16 B, box 128 B x <=256 rows "
+                  "(got ld=%llu box=%ux%u elem=%u)", (unsigned long long)ld, box_rows, box_cols, elem_bytes);
         return KBNER_EINVAL;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
