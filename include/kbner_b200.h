@@ -147,6 +147,14 @@ int kbner_attention_fwd(const uint16_t *qkv /*[R*S,3H]*/, const int32_t *key_len
                         int R, int S, int heads, uint16_t *out /*[R*S,H]*/,
                         float *lse /*[R,heads,S] or NULL*/, void *stream);
 
+/* Backward of kbner_attention_fwd (flash-style: P is recomputed per tile from Q, K and the saved LSE).
+ * out / d_out: attention output and its gradient, [R*S, H] bf16; lse from the forward call ([R,heads,S]);
+ * d_scratch [R,heads,S] fp32 and dq_acc [R*S, H] fp32 are workspaces; dqkv [R*S, 3H] bf16 receives dQ | dK | dV.
+ * What autograd derives from transformers' eager attention (flair/trainers/finetune_trainer.py:956-957). */
+int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out, const float *lse,
+                        const int32_t *key_len, int R, int S, int heads,
+                        float *d_scratch, float *dq_acc, uint16_t *dqkv, void *stream);
+
 /* ---- fine-tuning step: HBM-bound backward kernels, gradient norm, optimizer ----------------------
  * The reference obtains these from autograd + transformers.AdamW
  * (flair/trainers/finetune_trainer.py:939-957 backward, :1007-1023 clip_grad_norm_(5.0) / step / zero_grad). */

@@ -1,0 +1,362 @@
+// Fused multi-head self-attention BACKWARD for one encoder layer (head dim 64), flash-style: the [S,S] probability
+// matrix is recomputed per tile from Q, K and the saved row log-sum-exp; it never reaches HBM.  The reference gets
+// this from autograd through transformers' eager attention (call site /root/reference/flair/embeddings.py:3269 in
+// training mode; flair/trainers/finetune_trainer.py:956-957 `loss.backward()`).
+//
+//   P  = exp(Q.K^T / 8 - LSE)            dV = P^T . dO
+//   dP = dO . V^T                        dS = P * (dP - D),   D = rowsum(dO * O)
+//   dQ = dS . K / 8                      dK = dS^T . Q / 8
+//
+// One CTA = one (window r, head h, block j of 128 keys); it loops over the query blocks i of 128 rows.
+//   warp 4       TMA + MMA issuer (elected lane).  Per (i, j):
+//                  S^T  = K_j . Q_i^T     (M = keys, N = queries; both operands K-major)            -> TMEM
+//                  dP^T = V_j . dO_i^T                                                              -> TMEM
+//                  ... threads turn them into P^T and dS^T (bf16, shared memory) ...
+//                  dV_j += P^T  . dO_i    (A = P^T  K-major from smem,  B = dO_i MN-major in place)  -> TMEM, kept over i
+//                  dK_j += dS^T . Q_i     (A = dS^T K-major,            B = Q_i  MN-major in place)  -> TMEM, kept over i
+//                  dQ_i  = dS   . K_j     (A = the SAME dS^T tile read MN-major, B = K_j MN-major)   -> TMEM
+//   warps 0..3   thread = key row (= TMEM lane) for P^T / dS^T; thread = query row for the dQ_i read-out, which is
+//                added to the fp32 dQ accumulator in global memory with red.global.add (other key blocks add theirs).
+// dK_j / dV_j are written once, as bf16, into the K | V column blocks of the fused dqkv matrix; dQ is converted from
+// the fp32 accumulator by `attn_bwd_dq_kernel`.  D is produced by `attn_bwd_prep_kernel`.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace kbner {
+
+constexpr int kBwdThreads = 160;
+constexpr uint32_t kT128 = 128 * 64 * 2;        // [128 rows][64 bf16] SWIZZLE_128B tile = 16 KB
+
+struct AttnBwdSmem {
+    uint8_t k[kT128];
+    uint8_t v[kT128];
+    uint8_t q[2][kT128];                 // query-block ring
+    uint8_t dO[2][kT128];
+    uint8_t pt[2][kT128];                // P^T  [128 keys][128 queries] as two 64-query sub-tiles
+    uint8_t dst[2][kT128];               // dS^T, same layout (scaled by 1/8)
+    float lse2[2][128];                  // LSE * log2(e) of the query block (+inf beyond the window)
+    float dsum[2][128];                  // D of the query block
+    uint64_t bar_kv;
+    uint64_t qdo_full[2];
+    uint64_t bar_sdp;                    // S^T and dP^T ready in TMEM
+    uint64_t bar_pd;                     // P^T and dS^T written to smem (128 arrivals)
+    uint64_t bar_out;                    // dV/dK/dQ MMAs of this query block retired (also: ring stage free)
+    uint32_t tmem_base;
+};
+
+// D[r][h][s] = sum_d dO[s][h*64+d] * O[s][h*64+d]     (one warp per sub-token row; lane pair = one head)
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const uint16_t *__restrict__ O, const uint16_t *__restrict__ dO, int R, int S, int heads,
+                     float *__restrict__ D) {
+    const int H = heads * 64;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R * S) return;
+    float acc = 0.0f;
+    if (lane * 32 < H) {
+        const uint16_t *o = O + (size_t)row * H + lane * 32, *d = dO + (size_t)row * H + lane * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 a = ld_nc_v4(o + c * 8), b = ld_nc_v4(d + c * 8);
+            float x0, x1, y0, y1;
+            unpack_bf16x2(a.x, x0, x1); unpack_bf16x2(b.x, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+            unpack_bf16x2(a.y, x0, x1); unpack_bf16x2(b.y, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+            unpack_bf16x2(a.z, x0, x1); unpack_bf16x2(b.z, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+            unpack_bf16x2(a.w, x0, x1); unpack_bf16x2(b.w, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    const int head = lane >> 1;
+    if ((lane & 1) == 0 && head < heads) {
+        const int r = row / S, s = row - r * S;
+        D[((size_t)r * heads + head) * S + s] = acc;
+    }
+}
+
+// dqkv[:, 0:H] = bf16(dQ_acc)   (dQ_acc already carries the 1/8 scale)
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_kernel(const float *__restrict__ dq_acc, int M, int H, uint16_t *__restrict__ dqkv) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= (size_t)M * H) return;
+    const size_t row = i / H, col = i - row * H;
+    const float4 a = *reinterpret_cast<const float4 *>(dq_acc + i), b = *reinterpret_cast<const float4 *>(dq_acc + i + 4);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4 *>(dqkv + row * 3 * H + col) = o;
+}
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const int32_t *__restrict__ key_len, const float *__restrict__ lse, const float *__restrict__ Dsum,
+                     int S, int H, int heads, float *__restrict__ dq_acc, uint16_t *__restrict__ dqkv) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    AttnBwdSmem &s = *reinterpret_cast<AttnBwdSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
+    const int klen = min(key_len[r], S);
+    const int row0 = r * S;
+    const int nqb = (S + 127) / 128;
+    const bool active = jb * 128 < klen;          // key block with at least one valid key
+
+    if (threadIdx.x == 0) {
+        if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
+        ptx::prefetch_tensormap(&tmQKV);
+        ptx::prefetch_tensormap(&tmDO);
+        ptx::mbar_init(&s.bar_kv, 1);
+        ptx::mbar_init(&s.qdo_full[0], 1);
+        ptx::mbar_init(&s.qdo_full[1], 1);
+        ptx::mbar_init(&s.bar_sdp, 1);
+        ptx::mbar_init(&s.bar_pd, 128);
+        ptx::mbar_init(&s.bar_out, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) ptx::tmem_alloc<512>(&s.tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const uint32_t t_st = tmem_base, t_dpt = tmem_base + 128, t_dk = tmem_base + 256, t_dv = tmem_base + 320,
+                   t_dq = tmem_base + 384;
+
+    if (!active) {
+        // every key of this block is padding: dK = dV = 0 for its rows (rows inside the window), no dQ contribution
+        if (warp < 4) {
+            const int krow = jb * 128 + warp * 32 + lane;
+            if (krow < S) {
+                uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64;
+#pragma unroll
+                for (int i = 0; i < 64; i += 8) {
+                    *reinterpret_cast<uint4 *>(o + H + i) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(o + 2 * H + i) = make_uint4(0, 0, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== TMA + MMA issuer (warp-uniform; elected lane issues) =====================
+        constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : both K-major
+        constexpr uint32_t idesc_kmn = ptx::make_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major, B MN-major
+        constexpr uint32_t idesc_mnmn = ptx::make_idesc_bf16(128, 64, 1, 1);  // dQ        : both MN-major
+        const uint32_t k_addr = ptx::smem_u32(s.k), v_addr = ptx::smem_u32(s.v);
+        auto load_qdo = [&](int i) {
+            const int st = i & 1;
+            ptx::mbar_expect_tx(&s.qdo_full[st], 2 * kT128);
+            ptx::tma_load_2d(s.q[st], &tmQKV, &s.qdo_full[st], h * 64, row0 + i * 128);
+            ptx::tma_load_2d(s.dO[st], &tmDO, &s.qdo_full[st], h * 64, row0 + i * 128);
+        };
+        auto issue_sdp = [&](int i) {     // S^T and dP^T of query block i
+            const int st = i & 1;
+            const uint32_t q_addr = ptx::smem_u32(s.q[st]), do_addr = ptx::smem_u32(s.dO[st]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                ptx::mma_f16_ss(t_st, ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024),
+                                ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024), idesc_kk, kk != 0);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                ptx::mma_f16_ss(t_dpt, ptx::make_sw128_desc(v_addr + kk * 32, 16, 1024),
+                                ptx::make_sw128_desc(do_addr + kk * 32, 16, 1024), idesc_kk, kk != 0);
+            }
+            ptx::mma_commit(&s.bar_sdp);
+        };
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&s.bar_kv, 2 * kT128);
+            ptx::tma_load_2d(s.k, &tmQKV, &s.bar_kv, H + h * 64, row0 + jb * 128);
+            ptx::tma_load_2d(s.v, &tmQKV, &s.bar_kv, 2 * H + h * 64, row0 + jb * 128);
+            load_qdo(0);
+            if (nqb > 1) load_qdo(1);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&s.bar_kv, 0);
+        ptx::mbar_wait(&s.qdo_full[0], 0);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) issue_sdp(0);
+        __syncwarp();
+        for (int i = 0; i < nqb; ++i) {
+            const int st = i & 1;
+            ptx::mbar_wait(&s.bar_pd, i & 1);              // P^T / dS^T of block i are in smem; S^T / dP^T were drained
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t pt_addr = ptx::smem_u32(s.pt[0]), dst_addr = ptx::smem_u32(s.dst[0]);
+                const uint32_t q_addr = ptx::smem_u32(s.q[st]), do_addr = ptx::smem_u32(s.dO[st]);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {           // K = 128 queries: 8 steps of 16 over the two sub-tiles
+                    const uint32_t a_off = (kk >> 2) * kT128 + (kk & 3) * 32;
+                    const uint32_t b_off = kk * 16 * 128;  // 16 query rows of the [query][d] tile (MN-major B)
+                    ptx::mma_f16_ss(t_dv, ptx::make_sw128_desc(pt_addr + a_off, 16, 1024),
+                                    ptx::make_sw128_desc(do_addr + b_off, 16, 1024), idesc_kmn, (i | kk) != 0);
+                    ptx::mma_f16_ss(t_dk, ptx::make_sw128_desc(dst_addr + a_off, 16, 1024),
+                                    ptx::make_sw128_desc(q_addr + b_off, 16, 1024), idesc_kmn, (i | kk) != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {           // dQ_i = dS . K_j : K = 128 keys
+                    const uint32_t off = kk * 16 * 128;    // 16 key rows of dS^T (MN-major A: 2 query slabs, LBO 16 KB) / K_j
+                    ptx::mma_f16_ss(t_dq, ptx::make_sw128_desc(dst_addr + off, kT128, 1024),
+                                    ptx::make_sw128_desc(k_addr + off, 16, 1024), idesc_mnmn, kk != 0);
+                }
+                ptx::mma_commit(&s.bar_out);
+            }
+            __syncwarp();
+            if (i + 1 < nqb) {
+                ptx::mbar_wait(&s.qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) issue_sdp(i + 1);     // S^T / dP^T TMEM was drained before bar_pd(i)
+                __syncwarp();
+            }
+            if (i + 2 < nqb) {                              // refill this ring stage once block i's MMAs retired
+                ptx::mbar_wait(&s.bar_out, i & 1);
+                if (ptx::elect_one()) load_qdo(i + 2);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== compute warps =====================
+        const int t = warp * 32 + lane;                   // key row of this block (P^T / dS^T) and query row (dQ read-out)
+        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+        const bool key_ok = jb * 128 + t < klen;
+        const float scale_log2 = 0.125f * 1.4426950408889634f;
+        for (int i = 0; i < nqb; ++i) {
+            // stage LSE / D of query block i (one value per thread)
+            {
+                const int qi = i * 128 + t;
+                const size_t off = ((size_t)r * heads + h) * S + qi;
+                s.lse2[i & 1][t] = (qi < S) ? lse[off] * 1.4426950408889634f : CUDART_INF_F;
+                s.dsum[i & 1][t] = (qi < S) ? Dsum[off] : 0.0f;
+            }
+            // P^T / dS^T smem of block i-1 is still being read by its MMAs until bar_out(i-1): handled below (we wait
+            // for bar_out(i-1) before the dQ read-out, i.e. before getting here).  Named barrier: compute warps only.
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ptx::mbar_wait(&s.bar_sdp, i & 1);
+            ptx::tc_fence_after();
+            const float *lse2 = s.lse2[i & 1], *dsum = s.dsum[i & 1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                 // 4 chunks of 32 query columns
+                uint32_t rs[32], rd[32];
+                ptx::tmem_ld_32x32b_x32(t_st + lane_addr + c * 32, rs);
+                ptx::tmem_ld_32x32b_x32(t_dpt + lane_addr + c * 32, rd);
+                ptx::tmem_ld_wait();
+                uint8_t *prow = s.pt[c >> 1] + t * 128, *drow = s.dst[c >> 1] + t * 128;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks of 8 queries
+                    float p[8], d[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = c * 32 + cc * 8 + e;
+                        const float pe = key_ok ? ex2_fast(fmaf(__uint_as_float(rs[cc * 8 + e]), scale_log2, -lse2[col])) : 0.0f;
+                        p[e] = pe;
+                        d[e] = pe * (__uint_as_float(rd[cc * 8 + e]) - dsum[col]) * 0.125f;
+                    }
+                    uint4 pk, dk;
+                    pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
+                    pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
+                    dk.x = pack_bf16x2(d[0], d[1]); dk.y = pack_bf16x2(d[2], d[3]);
+                    dk.z = pack_bf16x2(d[4], d[5]); dk.w = pack_bf16x2(d[6], d[7]);
+                    const int chunk = (c & 1) * 4 + cc;   // 16-byte chunk inside the 128-byte row of the sub-tile
+                    const int phys = (chunk ^ (t & 7)) << 4;
+                    *reinterpret_cast<uint4 *>(prow + phys) = pk;
+                    *reinterpret_cast<uint4 *>(drow + phys) = dk;
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&s.bar_pd);
+            // dQ_i read-out: thread = query row
+            ptx::mbar_wait(&s.bar_out, i & 1);
+            ptx::tc_fence_after();
+            const int qi = i * 128 + t;
+            float *qrow = dq_acc + (size_t)(row0 + qi) * H + h * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rq[32];
+                ptx::tmem_ld_32x32b_x32(t_dq + lane_addr + c * 32, rq);
+                ptx::tmem_ld_wait();
+                if (qi < S) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        red_add_v4(qrow + c * 32 + e, __uint_as_float(rq[e]), __uint_as_float(rq[e + 1]),
+                                   __uint_as_float(rq[e + 2]), __uint_as_float(rq[e + 3]));
+                }
+            }
+            ptx::tc_fence_before();
+        }
+        // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them)
+        const int krow = jb * 128 + t;
+        if (krow < S) {
+            uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t rr[32];
+                    ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + c * 32, rr);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8) {
+                        uint4 ov;
+                        ov.x = pack_bf16x2(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]));
+                        ov.y = pack_bf16x2(__uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+                        ov.z = pack_bf16x2(__uint_as_float(rr[e + 4]), __uint_as_float(rr[e + 5]));
+                        ov.w = pack_bf16x2(__uint_as_float(rr[e + 6]), __uint_as_float(rr[e + 7]));
+                        *reinterpret_cast<uint4 *>(o + (which ? 2 * H : H) + c * 32 + e) = ov;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace kbner
+
+using namespace kbner;
+
+extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
+                                   const float *lse, const int32_t *key_len, int R, int S, int heads,
+                                   float *d_scratch, float *dq_acc, uint16_t *dqkv, void *stream) {
+    KBNER_CHECK_ARG(qkv && out && d_out && lse && key_len && d_scratch && dq_acc && dqkv, "attention_bwd: null pointer");
+    KBNER_CHECK_ARG(R > 0 && S > 0 && heads > 0 && S <= 512, "attention_bwd: bad shape R=%d S=%d heads=%d", R, S, heads);
+    const int H = heads * 64;
+    KBNER_CHECK_ARG(H % 32 == 0 && H / 32 <= 32, "attention_bwd: hidden size %d not supported", H);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = R * S;
+    cudaError_t e = cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)M * H, st);
+    if (e != cudaSuccess) {
+        set_error("attention_bwd: memset: %s", cudaGetErrorString(e));
+        return KBNER_ECUDA;
+    }
+    attn_bwd_prep_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, d_out, R, S, heads, d_scratch);
+    KBNER_CHECK_LAUNCH("attn_bwd_prep");
+    CUtensorMap tmQKV, tmDO;
+    int rc = make_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)M, (uint64_t)3 * H, (uint64_t)3 * H, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmDO, d_out, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
+    if (rc) return rc;
+    const size_t smem = sizeof(AttnBwdSmem);
+    static bool configured = false;
+    if (!configured) {
+        e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return KBNER_ECUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((S + 127) / 128, heads, R);
+    attention_bwd_kernel<<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv);
+    KBNER_CHECK_LAUNCH("attention_bwd");
+    const size_t n8 = (size_t)M * H / 8;
+    attn_bwd_dq_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq_acc, M, H, dqkv);
+    KBNER_CHECK_LAUNCH("attn_bwd_dq");
+    return KBNER_OK;
+}

@@ -192,3 +192,156 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         m = cls(EncoderConfig(**{**cfg, **kw}))
         m.load_hf_state_dict(torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu"))
         return m
+
+
+# =====================================================================================================
+# Fine-tuning path: flat parameter / gradient arenas, forward that keeps what the backward needs, and the
+# hand-written backward (no autograd inside the encoder).  Semantics = what `loss.backward()` does to the
+# transformers module in the reference (flair/trainers/finetune_trainer.py:939-957) with dropout disabled.
+# =====================================================================================================
+class ParamArena:
+    """All parameters of a module as views into ONE flat fp32 buffer (and their .grad into another), in a caller-
+    chosen order.  One buffer = one fused optimizer launch, one gradient-norm launch, contiguous NCCL buckets; the
+    order lets Q|K|V weights (and biases) sit next to each other so the fused [3H,H] projection is a plain view."""
+
+    def __init__(self, params):
+        params = list(params)
+        dev = params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]           # keep every view 16-byte aligned
+        self.numel = sum(sizes)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.offsets = {}
+        off = 0
+        for p, n in zip(params, sizes):
+            self.flat[off:off + p.numel()].copy_(p.detach().reshape(-1).float())
+            p.data = self.flat[off:off + p.numel()].view(p.shape)
+            p.grad = self.grad[off:off + p.numel()].view(p.shape)
+            self.offsets[id(p)] = off
+            off += n
+
+    def view(self, p_first, shape, grad=False):
+        """A [shape] view starting at parameter p_first (used for the fused Q|K|V weight / bias)."""
+        off = self.offsets[id(p_first)]
+        n = 1
+        for s in shape:
+            n *= s
+        return (self.grad if grad else self.flat)[off:off + n].view(shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+def _arena_order(enc):
+    out = []
+    for lyr in enc.encoder.layer:
+        a = lyr.attention
+        out += [a.self.query.weight, a.self.key.weight, a.self.value.weight,
+                a.self.query.bias, a.self.key.bias, a.self.value.bias,
+                a.output.dense.weight, a.output.dense.bias, a.output.LayerNorm.weight, a.output.LayerNorm.bias,
+                lyr.intermediate.dense.weight, lyr.intermediate.dense.bias,
+                lyr.output.dense.weight, lyr.output.dense.bias, lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias]
+    e = enc.embeddings
+    out += [e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight,
+            e.LayerNorm.weight, e.LayerNorm.bias]
+    return out
+
+
+def _ensure_arena(self):
+    if getattr(self, "arena", None) is None:
+        self.arena = ParamArena(_arena_order(self))
+        self._compute = None
+    return self.arena
+
+
+@torch.no_grad()
+def _sync_compute_weights_arena(self):
+    """bf16 compute copies straight from the arena (Q|K|V are one contiguous [3H,H] region: no concatenation)."""
+    ar = self.arena
+    H = self.config.hidden_size
+    layers = []
+    for lyr in self.encoder.layer:
+        a = lyr.attention
+        layers.append(dict(
+            wqkv=ar.view(a.self.query.weight, (3 * H, H)).bfloat16(), bqkv=ar.view(a.self.query.bias, (3 * H,)),
+            wo=a.output.dense.weight.bfloat16(), bo=a.output.dense.bias.data,
+            g1=a.output.LayerNorm.weight.data, b1=a.output.LayerNorm.bias.data,
+            w1=lyr.intermediate.dense.weight.bfloat16(), bi=lyr.intermediate.dense.bias.data,
+            w2=lyr.output.dense.weight.bfloat16(), b2=lyr.output.dense.bias.data,
+            g2=lyr.output.LayerNorm.weight.data, bb2=lyr.output.LayerNorm.bias.data))
+    self._compute = layers
+
+
+@torch.no_grad()
+def _forward_train(self, ids, key_len):
+    """Forward that keeps the activations the backward needs.  Returns (hidden [R*S,H] bf16, saved)."""
+    _ensure_arena(self)
+    if self._compute is None:
+        _sync_compute_weights_arena(self)
+    c = self.config
+    R, S = ids.shape
+    M, H, F = R * S, c.hidden_size, c.intermediate_size
+    dev = ids.device
+    bf, f32 = torch.bfloat16, torch.float32
+    e = self.embeddings
+    x = ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight[0],
+                         e.LayerNorm.weight, e.LayerNorm.bias, c.layer_norm_eps, c.pad_token_id)
+    saved = {"ids": ids, "key_len": key_len, "R": R, "S": S, "layers": []}
+    for w in self._compute:
+        qkv = ops.gemm_bf16(x, w["wqkv"], M, 3 * H, H, ops.EPI_BIAS, bias=w["bqkv"])
+        ctx, lse = ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, want_lse=True)
+        y1 = ops.gemm_bf16(ctx, w["wo"], M, H, H, ops.EPI_BIAS_RESID_F32, bias=w["bo"], aux=x)
+        x1, mean1, rstd1 = ops.layernorm_fwd(y1, w["g1"], w["b1"], c.layer_norm_eps, save_stats=True)
+        hpre = torch.empty((M, F), dtype=bf, device=dev)
+        h = ops.gemm_bf16(x1, w["w1"], M, F, H, ops.EPI_BIAS_GELU, bias=w["bi"], aux_out=hpre)
+        y2 = ops.gemm_bf16(h, w["w2"], M, H, F, ops.EPI_BIAS_RESID_F32, bias=w["b2"], aux=x1)
+        xo, mean2, rstd2 = ops.layernorm_fwd(y2, w["g2"], w["bb2"], c.layer_norm_eps, save_stats=True)
+        saved["layers"].append((x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2))
+        x = xo
+    return x, saved
+
+
+@torch.no_grad()
+def _backward(self, saved, dout):
+    """dout: gradient w.r.t. the last hidden state, fp32 [R*S, H].  Accumulates into the gradient arena."""
+    c = self.config
+    ar = self.arena
+    R, S = saved["R"], saved["S"]
+    M, H, F = R * S, c.hidden_size, c.intermediate_size
+    heads = c.num_attention_heads
+    key_len = saved["key_len"]
+    dev = dout.device
+    ws = (torch.empty((R, heads, S), dtype=torch.float32, device=dev), torch.empty((M, H), dtype=torch.float32, device=dev))
+    for li in range(len(self.encoder.layer) - 1, -1, -1):
+        lyr, w = self.encoder.layer[li], self._compute[li]
+        a = lyr.attention
+        x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2 = saved["layers"][li]
+        # ---- FFN block ------------------------------------------------------------------------------
+        dy2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad)
+        ops.colsum_bf16(dy2, lyr.output.dense.bias.grad)
+        ops.gemm_bf16(dy2, h, H, F, M, ops.EPI_ACCUM_F32, out=lyr.output.dense.weight.grad, a_mn=True, b_mn=True)
+        dhpre = ops.gemm_bf16(dy2, w["w2"], M, F, H, ops.EPI_DGELU_BF16, aux=hpre, b_mn=True)
+        ops.colsum_bf16(dhpre, lyr.intermediate.dense.bias.grad)
+        ops.gemm_bf16(dhpre, x1, F, H, M, ops.EPI_ACCUM_F32, out=lyr.intermediate.dense.weight.grad, a_mn=True, b_mn=True)
+        dx1 = ops.gemm_bf16(dhpre, w["w1"], M, H, F, ops.EPI_BIAS_RESID_F32, aux=dy2, b_mn=True)      # + residual path
+        # ---- attention block ------------------------------------------------------------------------
+        dy1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad)
+        ops.colsum_bf16(dy1, a.output.dense.bias.grad)
+        ops.gemm_bf16(dy1, ctx, H, H, M, ops.EPI_ACCUM_F32, out=a.output.dense.weight.grad, a_mn=True, b_mn=True)
+        dctx = ops.gemm_bf16(dy1, w["wo"], M, H, H, ops.EPI_BIAS, b_mn=True)
+        dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws)
+        ops.colsum_bf16(dqkv, ar.view(a.self.query.bias, (3 * H,), grad=True))
+        ops.gemm_bf16(dqkv, x, 3 * H, H, M, ops.EPI_ACCUM_F32, out=ar.view(a.self.query.weight, (3 * H, H), grad=True),
+                      a_mn=True, b_mn=True)
+        dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_BIAS_RESID_F32, aux=dy1, b_mn=True)
+    e = self.embeddings
+    ops.embed_ln_bwd(saved["ids"], e.word_embeddings.weight.data, e.position_embeddings.weight.data,
+                     e.token_type_embeddings.weight.data[0], e.LayerNorm.weight.data, c.layer_norm_eps, c.pad_token_id,
+                     dout, e.word_embeddings.weight.grad, e.position_embeddings.weight.grad,
+                     e.token_type_embeddings.weight.grad[0], e.LayerNorm.weight.grad, e.LayerNorm.bias.grad)
+
+
+XLMRobertaEncoderB200.ensure_arena = _ensure_arena
+XLMRobertaEncoderB200.forward_train = _forward_train
+XLMRobertaEncoderB200.backward = _backward
+XLMRobertaEncoderB200.sync_compute_weights_arena = _sync_compute_weights_arena

@@ -270,3 +270,22 @@ def gemm_bf16(A, B, M, N, K, epilogue, bias=None, aux=None, aux_out=None, out=No
                                            A.shape[1], B.shape[1], N, int(bool(a_mn)), int(bool(b_mn)), int(epilogue),
                                            _stream()), "gemm_bf16")
     return out
+
+
+def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None):
+    """dQ | dK | dV ([R*S, 3H] bf16) of attention_fwd.  workspace = (d_scratch [R,heads,S] f32, dq_acc [R*S,H] f32)."""
+    _chk(qkv, torch.bfloat16, "qkv", 2)
+    _chk(out, torch.bfloat16, "out", 2)
+    _chk(d_out, torch.bfloat16, "d_out", 2)
+    _chk(lse, torch.float32, "lse", 3)
+    _chk(key_len, torch.int32, "key_len", 1)
+    H = heads * 64
+    if dqkv is None:
+        dqkv = torch.empty((R * S, 3 * H), dtype=torch.bfloat16, device=qkv.device)
+    if workspace is None:
+        workspace = (torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device),
+                     torch.empty((R * S, H), dtype=torch.float32, device=qkv.device))
+    _lib.check(_lib.load().kbner_attention_bwd(_ptr(qkv), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(key_len), R, S, heads,
+                                               _ptr(workspace[0]), _ptr(workspace[1]), _ptr(dqkv), _stream()),
+               "attention_bwd")
+    return dqkv

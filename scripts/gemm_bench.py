@@ -18,7 +18,10 @@ def timeit(fn, reps):
 
 out = {"impl": os.environ.get("KBNER_GEMM", "1"), "rows": []}
 M = int(os.environ.get("M", "16384"))
+only = os.environ.get("SHAPES")
 for name, N, K, epi in (("qkv", 3072, 1024, 0), ("attn_out", 1024, 1024, 2), ("ffn_up", 4096, 1024, 1), ("ffn_down", 1024, 4096, 2), ("plain_f32", 4096, 1024, 3)):
+    if only and name not in only.split(","):
+        continue
     a = torch.randn(M, K, device="cuda").bfloat16()
     b = torch.randn(N, K, device="cuda").bfloat16()
     bias = torch.randn(N, device="cuda")

@@ -182,3 +182,36 @@ def test_adamw_sumsq_clip(ops):
         rp = rp - lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step) * rm / (rv.sqrt() + eps)
         rp = rp - lr * wd * rp
         torch.testing.assert_close(p.double(), rp, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("R,S,heads,lens", [(2, 128, 2, [128, 60]), (2, 512, 16, [512, 300]), (3, 200, 4, [200, 129, 1]),
+                                            (1, 384, 4, [257])])
+def test_attention_bwd(ops, R, S, heads, lens):
+    """dQ, dK, dV against autograd through an fp32 softmax attention on the same bf16 inputs.  Only query rows inside
+    the window carry upstream gradient (padding rows never reach the loss), as in the model."""
+    g = torch.Generator(device="cuda").manual_seed(R * 7 + S + heads)
+    H = heads * 64
+    qkv = _rand(g, R * S, 3 * H, scale=1.0).bfloat16()
+    key_len = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out, lse = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True)
+    d_out = _rand(g, R * S, H, scale=1.0)
+    valid_q = (torch.arange(S, device="cuda")[None, :] < key_len[:, None]).reshape(R * S, 1)
+    d_out = (d_out * valid_q).bfloat16()
+    dqkv = ops.attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.reshape(R, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * 0.125
+    kmask = torch.arange(S, device="cuda")[None, :] < key_len[:, None]
+    sc = sc.masked_fill(~kmask[:, None, None, :], float("-inf"))
+    o = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(R * S, H)
+    o.backward(d_out.float())
+    ref = x.grad
+    # rows beyond the window have no key/value role and no query gradient: compare rows inside the window
+    rows = valid_q.squeeze(1)
+    diff = (dqkv.float() - ref)[rows].abs()
+    scale = ref[rows].abs().max().item()
+    assert diff.max().item() < 3e-2 * max(scale, 1.0), (diff.max().item(), scale)
+    assert (diff.mean() / ref[rows].abs().mean()).item() < 1e-2
+    # key rows outside the window receive exactly zero dK / dV
+    if (~rows).any():
+        assert float(dqkv.float()[~rows][:, H:].abs().max()) == 0.0
