@@ -286,8 +286,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             ptx::tc_fence_before();
         }
         // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them)
+        // (tcgen05.ld is warp-collective: every lane executes it, only the stores are guarded -- a per-lane guard
+        //  around the load deadlocked windows whose length is not a multiple of 128)
         const int krow = jb * 128 + t;
-        if (krow < S) {
+        {
             uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
@@ -296,6 +298,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     uint32_t rr[32];
                     ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + c * 32, rr);
                     ptx::tmem_ld_wait();
+                    if (krow >= S) continue;
 #pragma unroll
                     for (int e = 0; e < 32; e += 8) {
                         uint4 ov;

@@ -25,7 +25,7 @@ namespace kbner {
 
 constexpr int kAttnD = 64;
 constexpr int kBQ = 128, kBKV = 64, kKVStages = 3, kMaxS = 512;
-constexpr int kAttnThreads = 160;
+constexpr int kAttnThreads = 288;      // 8 softmax warps (2 threads per query row) + 1 TMA/MMA warp
 constexpr uint32_t kQBytes = 128 * 64 * 2;     // [128 rows][64 bf16], SWIZZLE_128B
 constexpr uint32_t kKVBytes = 64 * 64 * 2;     // [64 keys][64 bf16]
 constexpr uint32_t kAttnTmemCols = 256;
@@ -41,6 +41,8 @@ struct AttnSmem {
     uint64_t bar_s[2];                 // S_j ready in TMEM buffer j&1
     uint64_t bar_p[2];                 // P_j written to smem buffer j&1 (128 arrivals)
     uint64_t bar_o[2];                 // O_j ready in TMEM buffer j&1
+    float xchg[2][2][128];             // [parity][column half][row]: block row-max exchange between the two halves
+    float xsum[2][128];                // [column half][row]: final row-sum exchange
     uint32_t tmem_base;
 };
 
@@ -76,12 +78,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s.bar_s[i], 1);
-            ptx::mbar_init(&s.bar_p[i], 128);
+            ptx::mbar_init(&s.bar_p[i], 256);
             ptx::mbar_init(&s.bar_o[i], 1);
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc<kAttnTmemCols>(&s.tmem_base);
+    if (warp == 8) ptx::tmem_alloc<kAttnTmemCols>(&s.tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -89,7 +91,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem_s = tmem_base;            // 2 x 64 columns
     const uint32_t tmem_o = tmem_base + 128;      // 2 x 64 columns
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0 && nkb > 0) {
             auto load_kv = [&](int j) {
                 const int st = j % kKVStages;
@@ -144,59 +146,63 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
     } else {
-        // ===================== softmax warps: thread = query row =====================
-        const int row = warp * 32 + lane;                 // TMEM lane == row in the query block
+        // ===================== softmax warps: two threads per query row =====================
+        // warps w and w+4 share TMEM lane quarter w (rows 32w..32w+31); `half` selects which 32 of the block's 64 key
+        // columns -- and which 32 of the 64 output columns -- the thread owns.  Four warps per scheduler (with the two
+        // resident CTAs) instead of two: the round-1 kernel was latency-bound with MUFU and issue both at ~40 %.
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;              // TMEM lane == row in the query block
         const int qrow = qb * kBQ + row;                  // sub-token index inside the window
-        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
         float m_run = -CUDART_INF_F, l_run = 0.0f, alpha_prev = 1.0f;
-        float o_acc[kAttnD];
+        float o_acc[32];
 #pragma unroll
-        for (int i = 0; i < kAttnD; ++i) o_acc[i] = 0.0f;
+        for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
 
         auto accumulate_o = [&](int j, float alpha) {
             ptx::mbar_wait(&s.bar_o[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
             uint32_t ro[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + (j & 1) * 64 + half * 32, ro);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + (j & 1) * 64 + c * 32, ro);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(ro[i]));
-            }
+            for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(ro[i]));
             ptx::tc_fence_before();
         };
 
         for (int j = 0; j < nkb; ++j) {
             ptx::mbar_wait(&s.bar_s[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
-            float sc[kBKV];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            float sc[32];
+            {
                 uint32_t rs[32];
-                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 64 + c * 32, rs);
+                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 64 + half * 32, rs);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sc[c * 32 + i] = __uint_as_float(rs[i]);
+                for (int i = 0; i < 32; ++i) sc[i] = __uint_as_float(rs[i]);
             }
             ptx::tc_fence_before();
-            const int kbase = j * kBKV;
-            if (kbase + kBKV > klen) {       // only the last block of the window is ragged (CTA-uniform)
+            const int kbase = j * kBKV + half * 32;
+            if (kbase + 32 > klen) {         // only the last block of the window is ragged
 #pragma unroll
-                for (int i = 0; i < kBKV; ++i)
+                for (int i = 0; i < 32; ++i)
                     if (kbase + i >= klen) sc[i] = -CUDART_INF_F;
             }
-            float m_blk = sc[0];
+            float m_half = sc[0];
 #pragma unroll
-            for (int i = 1; i < kBKV; ++i) m_blk = fmaxf(m_blk, sc[i]);
+            for (int i = 1; i < 32; ++i) m_half = fmaxf(m_half, sc[i]);
+            // row max over both halves: exchange through shared memory, pair barrier = the two warps of this quarter
+            s.xchg[j & 1][half][row] = m_half;
+            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+            const float m_blk = fmaxf(m_half, s.xchg[j & 1][half ^ 1][row]);
             const float m_new = fmaxf(m_run, m_blk * scale_log2);     // finite: the block has >= 1 valid key
             const float alpha = ex2_approx(m_run - m_new);           // first block: ex2(-inf) = 0
             const float neg_m = -m_new;
             float l_blk = 0.0f;
             uint8_t *prow = s.p[j & 1] + row * 128;
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
+            for (int cc = 0; cc < 4; ++cc) {
                 float pv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -208,9 +214,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 pk.y = pack_bf16x2(pv[2], pv[3]);
                 pk.z = pack_bf16x2(pv[4], pv[5]);
                 pk.w = pack_bf16x2(pv[6], pv[7]);
-                *reinterpret_cast<uint4 *>(prow + ((cc ^ (row & 7)) << 4)) = pk;
+                *reinterpret_cast<uint4 *>(prow + (((half * 4 + cc) ^ (row & 7)) << 4)) = pk;
             }
-            l_run = l_run * alpha + l_blk;
+            l_run = l_run * alpha + l_blk;     // partial row sum over this thread's columns (both halves share m)
             m_run = m_new;
             ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
             ptx::mbar_arrive(&s.bar_p[j & 1]);
@@ -219,12 +225,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             alpha_prev = alpha;
         }
         if (nkb > 0) accumulate_o(nkb - 1, alpha_prev);
-        // epilogue: normalise, bf16, 128 contiguous bytes per row
+        // total row sum = both halves
+        s.xsum[half][row] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+        const float l_tot = l_run + s.xsum[half ^ 1][row];
+        // epilogue: normalise, bf16, 64 contiguous bytes per thread
         if (qrow < S) {
-            const float inv = (l_run > 0.0f) ? 1.0f / l_run : 0.0f;
-            uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD;
+            const float inv = (l_tot > 0.0f) ? 1.0f / l_tot : 0.0f;
+            uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
 #pragma unroll
-            for (int i = 0; i < kAttnD; i += 8) {
+            for (int i = 0; i < 32; i += 8) {
                 uint4 o;
                 o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
                 o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
@@ -232,14 +242,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
                 *reinterpret_cast<uint4 *>(orow + i) = o;
             }
-            if (lse_out)   // natural-log LSE of the scaled scores (for the backward pass)
+            if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
                 lse_out[((size_t)r * heads + h) * S + qrow] =
-                    (l_run > 0.0f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -CUDART_INF_F;
+                    (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<kAttnTmemCols>(tmem_base);
     }

@@ -48,12 +48,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees),
 // never as a hung GPU.  ~2^28 polls of a HW-sleeping try_wait is many seconds.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) {
-            printf("kbner: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+        if ((++spins & 0xFFu) == 0) {                  // SM-clock bound: 8e9 cycles (~4 s) is ~1000x the longest legitimate wait
+            const uint64_t now = (uint64_t)clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ull) {
+                printf("kbner: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+                       blockIdx.z, threadIdx.x, parity);
+                __trap();
+            }
         }
     }
 }

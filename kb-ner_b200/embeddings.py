@@ -78,7 +78,9 @@ def _strip_markup(piece: str) -> str:
 class EncodedBatch:
     """Device-side result of embedding one batch: what the fused pooling kernel consumes."""
 
-    def __init__(self, hidden, S, row_of, first_idx, lengths, key_len, ids):
+    def __init__(self, hidden, S, row_of, first_idx, lengths, key_len, ids, saved=None, encoder=None):
+        self.saved = saved            # activations kept for the backward pass (fine-tuning only)
+        self.encoder = encoder
         self.hidden = hidden          # [R*S, H] bf16
         self.S = S
         self.row_of = row_of          # [B] int32: window row that starts each sentence
@@ -321,6 +323,10 @@ class TransformerWordEmbeddings(torch.nn.Module):
         ids_d = packed[:o0].view(ids.shape)
         key_d, row_d = packed[o0:o1], packed[o1:o2]
         first_d = packed[o2:].view(first_idx.shape)
+        if self.fine_tune and self.training:
+            # gradients are enabled iff (fine_tune and self.training), embeddings.py:3280
+            hidden, saved = self.model.forward_train(ids_d, key_d)
+            return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d, saved=saved, encoder=self.model)
         hidden = self.model.forward_hidden(ids_d, key_d)
         return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d)
 

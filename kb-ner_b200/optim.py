@@ -1,0 +1,81 @@
+"""Fused optimizer step of the fine-tuning path.
+
+Reference semantics (flair/trainers/finetune_trainer.py): two parameter groups keyed on names (:552-571) --
+group 0 = parameters whose name neither contains 'embedding' nor is linear.weight / linear.bias (i.e. the CRF
+`transitions`) at lr * lr_rate, group 1 = the rest (the whole encoder sits under `embeddings.*`, plus the tag
+projection) at lr; transformers-3.0.0 AdamW (betas 0.9/0.999, eps 1e-6, bias correction, decoupled weight decay 0);
+`clip_grad_norm_(model.parameters(), 5.0)` over ALL parameters before the step (:1010); loss / accumulation steps
+(:939-946); linear decay to zero over t_total steps with 0 warm-up (:679-688).
+
+Here every group is a flat fp32 arena: one `sumsq` launch per arena for the global norm, one tiny kernel that turns it
+into the clip coefficient ON THE DEVICE (no host sync), one fused AdamW launch per arena.
+"""
+import math
+
+import torch
+
+from . import ops
+from .encoder import ParamArena
+
+
+class FusedAdamW:
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, max_grad_norm=5.0):
+        """groups: list of dicts {"arena": ParamArena, "lr": float}."""
+        self.groups = []
+        for g in groups:
+            ar = g["arena"]
+            self.groups.append({"arena": ar, "lr": float(g["lr"]), "base_lr": float(g["lr"]),
+                                "m": torch.zeros_like(ar.flat), "v": torch.zeros_like(ar.flat)})
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.steps = 0
+        dev = self.groups[0]["arena"].flat.device
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+
+    def grad_norm(self, grad_scale=1.0):
+        """Global L2 norm of (grad * grad_scale) over all arenas -- a device tensor, no sync."""
+        self._sumsq.zero_()
+        for g in self.groups:
+            ops.sumsq_f32(g["arena"].grad, self._sumsq)
+        return torch.sqrt(self._sumsq) * grad_scale
+
+    def step(self, grad_scale=1.0):
+        """grad_scale multiplies every gradient first (1/accumulation, 1/world after a sum all-reduce)."""
+        self.steps += 1
+        self._sumsq.zero_()
+        for g in self.groups:
+            ops.sumsq_f32(g["arena"].grad, self._sumsq)
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            ops.clip_coef(self._sumsq, grad_scale, self.max_grad_norm, self._coef)
+            coef = self._coef
+        else:
+            coef = None
+        for g in self.groups:
+            ar = g["arena"]
+            ops.adamw_step(ar.flat, ar.grad, g["m"], g["v"], g["lr"], self.betas[0], self.betas[1], self.eps,
+                           self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale)
+
+    def zero_grad(self):
+        for g in self.groups:
+            g["arena"].zero_grad()
+
+    def set_linear_schedule(self, t_total):
+        self.t_total = max(1, int(t_total))
+
+    def scheduler_step(self):
+        """get_linear_schedule_with_warmup(optimizer, 0, t_total): lr = base * max(0, (t_total - t) / t_total)."""
+        f = max(0.0, (self.t_total - self.steps) / self.t_total)
+        for g in self.groups:
+            g["lr"] = g["base_lr"] * f
+
+
+def build_reference_optimizer(tagger, lr=5e-6, lr_rate=10000.0, **kw):
+    """The reference's two groups for a FastSequenceTagger on TransformerWordEmbeddings (finetune_trainer.py:552-571)."""
+    enc = tagger.embeddings.embeddings[0].model
+    enc_arena = enc.ensure_arena()
+    head_arena = ParamArena([tagger.linear.weight, tagger.linear.bias])
+    crf_arena = ParamArena([tagger.transitions])
+    tagger._head_arena, tagger._crf_arena = head_arena, crf_arena
+    return FusedAdamW([{"arena": crf_arena, "lr": lr * lr_rate}, {"arena": enc_arena, "lr": lr},
+                       {"arena": head_arena, "lr": lr}], **kw)

@@ -246,8 +246,7 @@ class SequenceTagger(torch.nn.Module):
         out = []
         for b, s in enumerate(sentences):
             n = len(s.tokens)
-            tb, cb = tags_l[b], conf_l[b]
-            out.append([Label(names[tb[t]], cb[t]) for t in range(n)])
+            out.append([Label(names[a], c) for a, c in zip(tags_l[b][:n], conf_l[b][:n])])
         return out
 
     def _viterbi_decode(self, feats, all_scores: bool = False, current_idx=0):
@@ -390,25 +389,30 @@ class SequenceTagger(torch.nn.Module):
 
 
 class _TagProjGrad(torch.autograd.Function):
-    """Gradient of the fused gather + word-dropout + Linear w.r.t. linear.weight / linear.bias.
-    (The gradient into the encoder hidden state is the round-2 backward path, see DESIGN.md.)"""
+    """Backward of the fused gather + word-dropout + Linear: one kernel for d_hidden / dW / db, then -- when the
+    embeddings are being fine-tuned -- the hand-written encoder backward (encoder.XLMRobertaEncoderB200.backward),
+    which accumulates straight into the encoder's gradient arena."""
 
     @staticmethod
     def forward(ctx, features, weight, bias, enc, drop_keep):
         ctx.enc, ctx.drop_keep = enc, drop_keep
+        ctx.save_for_backward(weight)
         return features.view_as(features)
 
     @staticmethod
     def backward(ctx, g):
         enc, dk = ctx.enc, ctx.drop_keep
-        B, T, L = g.shape
-        idx = enc.row_of.long()[:, None] * enc.S + enc.first_idx.long().clamp(min=0)
-        live = (enc.first_idx >= 0).to(g.dtype)
-        if dk is not None:
-            live = live * dk.to(g.dtype)[None, :]
-        x = enc.hidden[idx.view(-1)].float() * live.view(-1, 1)
-        gw = g.reshape(B * T, L).t() @ x
-        return g, gw, g.sum((0, 1)), None, None
+        (weight,) = ctx.saved_tensors
+        L, H = weight.shape
+        d_hidden = torch.zeros((enc.hidden.shape[0], H), dtype=torch.float32, device=g.device)
+        dW = torch.zeros((L, H), dtype=torch.float32, device=g.device)
+        db = torch.zeros((L,), dtype=torch.float32, device=g.device)
+        ops.gather_tagproj_bwd(enc.hidden, enc.row_of, enc.first_idx, weight.detach().float().contiguous(),
+                               g.contiguous().float(), enc.S, d_hidden, dW, db, drop_keep=dk)
+        if enc.saved is not None:
+            enc.encoder.backward(enc.saved, d_hidden)
+            enc.saved = None
+        return None, dW, db, None, None
 
 
 class FastSequenceTagger(SequenceTagger):

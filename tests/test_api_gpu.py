@@ -185,3 +185,92 @@ def test_long_sentence_windows():
     with torch.no_grad():
         feats = tagger.forward(BatchedData([s]))
     assert feats.shape == (1, 700, 13) and torch.isfinite(feats).all()
+
+
+def test_finetune_gradients_vs_oracle_autograd():
+    """Fine-tuning path: loss.backward() through CRF -> tag projection -> hand-written encoder backward, against
+    torch autograd through the fp32 oracle encoder on the same weights, fed with the same d(loss)/d(logits)."""
+    import encoder_oracle as E
+    from kbner_b200.data import BatchedData
+    tagger, emb, params, ocfg = _models(SMALL, 13, seed=21)
+    emb.fine_tune, emb.static_embeddings = True, False
+    tagger.train()
+    emb.train()
+    tagger.use_word_dropout = 0.0
+    sents = _sentences(4, 5, 40, seed=33)
+    d = tagger.tag_dictionary
+    rng = np.random.RandomState(1)
+    legal = [i for i in range(len(d)) if i not in (0, tagger.x_idx, tagger.start_idx, tagger.stop_idx)]
+    for s in sents:
+        for tok in s.tokens:
+            tok.add_tag("ner", d.get_item_for_index(legal[rng.randint(len(legal))]))
+    batch = BatchedData(sents)
+    enc = emb.model
+    enc.ensure_arena()
+    enc.arena.zero_grad()
+    feats = tagger.forward(batch)
+    feats.retain_grad()
+    loss = tagger._calculate_loss(feats, batch, tagger.mask)
+    loss.backward()
+    d_logits = feats.grad.detach().clone()
+    # ---- oracle: autograd through the fp32 restatement ------------------------------------------------
+    ids, key_len, row_of, first_idx, lengths, S = emb.build_batch(batch)
+    op = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+    hidden = E.encoder_forward(op, ids.long().cuda(), key_len.long().cuda(), ocfg)
+    flat = hidden.reshape(-1, hidden.shape[-1])
+    idx = row_of.long()[:, None] * S + first_idx.long().clamp(min=0)
+    x = flat[idx.cuda()] * (first_idx >= 0).float().cuda()[..., None]
+    W, b = tagger.linear.weight.detach().clone().requires_grad_(True), tagger.linear.bias.detach().clone().requires_grad_(True)
+    (x @ W.t() + b).backward(d_logits)
+    torch.testing.assert_close(tagger.linear.weight.grad, W.grad, rtol=5e-2, atol=5e-3)
+    worst = {}
+    own = dict(enc.named_parameters())
+    for name, ref in op.items():
+        got = own[name].grad
+        if ref.grad is None:
+            continue
+        denom = ref.grad.norm().item()
+        if denom < 1e-8:
+            assert got.norm().item() < 1e-5, name
+            continue
+        worst[name] = ((got - ref.grad).norm() / denom).item()
+    bad = {k: v for k, v in worst.items() if v > 6e-2}
+    print("finetune grad rel-L2: max %.3e over %d tensors" % (max(worst.values()), len(worst)))
+    assert not bad, bad
+
+
+def test_finetune_steps_reduce_loss():
+    """A few optimizer steps (fused AdamW, clip 5.0, accumulation 2) on one batch must lower its CRF loss."""
+    from kbner_b200.data import BatchedData
+    from kbner_b200.optim import build_reference_optimizer
+    tagger, emb, params, ocfg = _models(SMALL, 13, seed=5)
+    emb.fine_tune, emb.static_embeddings = True, False
+    tagger.train()
+    emb.train()
+    tagger.use_word_dropout = 0.0
+    sents = _sentences(6, 5, 30, seed=8)
+    d = tagger.tag_dictionary
+    rng = np.random.RandomState(2)
+    legal = [i for i in range(len(d)) if i not in (0, tagger.x_idx, tagger.start_idx, tagger.stop_idx)]
+    for s in sents:
+        for tok in s.tokens:
+            tok.add_tag("ner", d.get_item_for_index(legal[rng.randint(len(legal))]))
+    opt = build_reference_optimizer(tagger, lr=2e-4, lr_rate=100.0)
+    opt.set_linear_schedule(20)
+    halves = [BatchedData(sents[:3]), BatchedData(sents[3:])]
+    losses = []
+    for step in range(6):
+        opt.zero_grad()
+        tot = 0.0
+        for b in halves:
+            b.features = {}
+            loss = tagger.forward_loss(b) / len(halves)
+            loss.backward()
+            tot += float(loss)
+        opt.step()
+        opt.scheduler_step()
+        emb.model.sync_compute_weights_arena()
+        losses.append(tot)
+    print("finetune losses:", [round(x, 3) for x in losses])
+    assert losses[-1] < losses[0] * 0.9, losses
+    assert all(np.isfinite(losses))
