@@ -43,6 +43,8 @@ const char *kbner_last_error(void);
 int kbner_device_check(int dev);
 /* Number of kernels launched by this library since load (the bench's gpu_launches). */
 uint64_t kbner_launch_count(void);
+/* Account for kernels launched through a replayed CUDA graph (the host captured them once). */
+void kbner_add_launches(uint64_t n);
 
 /* ---- CRF ---------------------------------------------------------------------------- */
 /* remove-X compaction: pos[b][i] = original index of the i-th kept token, klen[b] = #kept,
@@ -127,7 +129,8 @@ int kbner_gather_tagproj_fwd(const uint16_t *hidden /*[R*S,H] bf16*/, const int3
  *   wgrad    dW += dY^T . X       : A = dY [M',N] read MN-major, B = X [M',K'] read MN-major (no transposes)
  * bias [N] may be NULL.  aux (bf16 [M,N], ld = ldc): residual for BIAS_RESID_F32, saved pre-activation for
  * DGELU_BF16.  aux_out (bf16 [M,N], optional): BIAS_GELU additionally stores the pre-activation (training).
- * M, N, K multiples of 8; ragged tile edges are handled by TMA zero-fill and guarded stores. */
+ * N and the leading dimensions are multiples of 8 (16-byte TMA pitches); M and K are arbitrary: ragged tile edges
+ * are zero-filled on load and clipped on store by the TMA unit. */
 int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *aux,
                     uint16_t *aux_out, void *C, int M, int N, int K, int lda, int ldb, int ldc,
                     int a_mn_major, int b_mn_major, int epilogue, void *stream);

@@ -104,6 +104,7 @@ int make_tmap_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t col
 extern "C" int kbner_abi_version(void) { return 1; }
 extern "C" const char *kbner_last_error(void) { return kbner::g_err; }
 extern "C" uint64_t kbner_launch_count(void) { return kbner::g_launches.load(); }
+extern "C" void kbner_add_launches(uint64_t n) { kbner::count_launch((int)n); }
 extern "C" int kbner_device_check(int dev) {
     cudaDeviceProp p;
     cudaError_t e = cudaGetDeviceProperties(&p, dev);

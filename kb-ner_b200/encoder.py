@@ -16,6 +16,11 @@ import torch
 from . import ops
 
 
+def _lib_note_launches(n):
+    from . import _lib
+    _lib.load().kbner_add_launches(int(n))
+
+
 class _Holder(torch.nn.Module):
     """Bare container so parameter names nest like the HF module tree."""
 
@@ -98,6 +103,9 @@ class XLMRobertaEncoderB200(torch.nn.Module):
             self.encoder.layer.append(lyr)
         self._compute = None          # bf16 / fused compute copies, built by sync_compute_weights()
         self._ws = {}
+        self._graphs = {}
+        import os
+        self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
 
     # ---- weights ---------------------------------------------------------------------------------
     def load_hf_state_dict(self, sd):
@@ -139,11 +147,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
 
     # ---- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_hidden(self, ids, key_len):
-        """ids [R,S] int32 (cuda), key_len [R] int32 -> last hidden state [R*S, H] bf16.
-        The returned tensor aliases an internal workspace buffer (valid until the next call)."""
-        if self._compute is None:
-            self.sync_compute_weights()
+    def _forward_hidden_eager(self, ids, key_len):
         c = self.config
         R, S = ids.shape
         M = R * S
@@ -162,6 +166,46 @@ class XLMRobertaEncoderB200(torch.nn.Module):
             ops.gemm_bf16_tn(ws["h"], w["w2"], w["b2"], residual=xn, epilogue=ops.EPI_BIAS_RESID_F32, out=ws["y"])
             ops.layernorm_fwd(ws["y"], w["g2"], w["bb2"], c.layer_norm_eps, out=x)
         return x
+
+    @torch.no_grad()
+    def forward_hidden(self, ids, key_len):
+        """ids [R,S] int32 (cuda), key_len [R] int32 -> last hidden state [R*S, H] bf16.
+        The returned tensor aliases an internal workspace buffer (valid until the next call).
+
+        The 1 + 7*layers launches of one shape are captured into a CUDA graph on the second call with that shape and
+        replayed afterwards (static id / length buffers, static workspace): the forward of a batch is one graph launch,
+        which takes ~170 ctypes round trips per batch off the host's critical path.  KBNER_GRAPHS=0 disables it."""
+        if self._compute is None:
+            self.sync_compute_weights()
+            self._graphs = {}
+        R, S = ids.shape
+        key = (R, S, str(ids.device), id(self._compute))
+        st = self._graphs.get(key) if self._use_graphs else None
+        if st is not None and st["graph"] is not None:
+            st["ids"].copy_(ids, non_blocking=True)
+            st["key_len"].copy_(key_len, non_blocking=True)
+            st["graph"].replay()
+            _lib_note_launches(st["launches"])
+            return st["out"]
+        if not self._use_graphs:
+            return self._forward_hidden_eager(ids, key_len)
+        if st is None:                                   # first call with this shape: eager (also warms every kernel up)
+            self._graphs = {k: v for k, v in self._graphs.items() if k[3] == id(self._compute)}
+            self._graphs[key] = {"graph": None, "calls": 1}
+            return self._forward_hidden_eager(ids, key_len)
+        # second call: capture
+        from . import _lib
+        st["ids"], st["key_len"] = ids.clone(), key_len.clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            st["out"] = self._forward_hidden_eager(st["ids"], st["key_len"])
+        st["launches"] = _lib.launch_count() - l0
+        st["graph"] = g
+        g.replay()
+        _lib_note_launches(st["launches"])
+        return st["out"]
 
     def forward(self, input_ids, attention_mask=None, **_unused):
         """HF-like call: returns (sequence_output [R,S,H] fp32,) -- the contract used at embeddings.py:3269,
