@@ -387,7 +387,7 @@ def run_train(args):
     last = None
     for i in range(K):
         last = step(i)
-    lossv = float(last)                       # device -> host read of the step's result
+    lossv = float(last.detach())              # device -> host read of the step's result
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0

@@ -86,8 +86,10 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
     const int sub = lane / G, j = lane % G;
     const int slot = warp * SPW + sub;
     const int b = blockIdx.x * W * SPW + slot;
-    uint8_t *bp = smem + (size_t)slot * T * G;
-    float *vt = reinterpret_cast<float *>(smem + (size_t)W * SPW * T * G) + slot * G * G;
+    constexpr bool kPackBp = (G == 16);
+    const size_t bp_bytes = kPackBp ? (size_t)((T + 7) / 8) * G * 4 : (size_t)T * G;     // per sentence
+    uint8_t *bp = smem + (size_t)slot * bp_bytes;
+    float *vt = reinterpret_cast<float *>(smem + (size_t)W * SPW * bp_bytes) + slot * G * G;
 
     const bool valid = b < B;
     const int n = valid ? klen[b] : 0;
@@ -108,6 +110,7 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
     for (int k = 0; k < G; ++k) A[k] = (j < L && k < L) ? trans[j * L + k] : -CUDART_INF_F;
 
     float v = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
+    uint32_t bpw = 0;          // G == 16: eight 4-bit back-pointers per word, one word per lane per 8 steps
     __syncwarp();
 
     float e_cur[kVitUnroll], e_nxt[kVitUnroll];
@@ -131,16 +134,32 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
             const int i = i0 + u;
             if (i < nmax) {   // warp-uniform
                 const bool act = i < n;
-                float best = -CUDART_INF_F;
-                int bk = 0;
+                // c[k] = v[k] + A[j][k] for every k, then a 4/5-level tournament instead of a G-long dependent chain.
+                // Combining (lo, hi) takes hi only when hi.val > lo.val, so the FIRST maximal index still wins.
+                float cv[G];
+                int ci[G];
 #pragma unroll
                 for (int k = 0; k < G; ++k) {
-                    const float c = __shfl_sync(0xffffffffu, v, k, G) + A[k];
-                    if (c > best) { best = c; bk = k; }
+                    cv[k] = __shfl_sync(0xffffffffu, v, k, G) + A[k];
+                    ci[k] = k;
                 }
+#pragma unroll
+                for (int stride = 1; stride < G; stride <<= 1) {
+#pragma unroll
+                    for (int k = 0; k < G; k += 2 * stride) {
+                        if (cv[k + stride] > cv[k]) { cv[k] = cv[k + stride]; ci[k] = ci[k + stride]; }
+                    }
+                }
+                const float best = cv[0];
+                const int bk = ci[0];
                 if (act) {
-                    bp[(size_t)i * G + j] = (uint8_t)bk;
+                    if (kPackBp) bpw |= (uint32_t)bk << (4 * (i & 7));
+                    else bp[(size_t)i * G + j] = (uint8_t)bk;
                     v = best + e_cur[u];
+                }
+                if (kPackBp && ((i & 7) == 7 || i == nmax - 1)) {
+                    reinterpret_cast<uint32_t *>(bp)[(size_t)(i >> 3) * G + j] = bpw;
+                    bpw = 0;
                 }
                 vt[(i & (G - 1)) * G + j] = v;
                 if ((i & (G - 1)) == G - 1 || i == nmax - 1) {
@@ -181,7 +200,8 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
         for (int i = n - 1; i >= 0; --i) {
             const int t = pos ? __ldg(pos + rowbase + i) : i;
             tags_out[rowbase + t] = cur;
-            cur = bp[(size_t)i * G + cur];
+            if (kPackBp) cur = (reinterpret_cast<const uint32_t *>(bp)[(size_t)(i >> 3) * G + cur] >> (4 * (i & 7))) & 15u;
+            else cur = bp[(size_t)i * G + cur];
         }
         // cur is START here for every well-formed transition matrix (reference assert :1303)
     }
@@ -442,7 +462,8 @@ static int launch_viterbi(const float *emis, const int32_t *pos, const int32_t *
     int W = 4;
     size_t smem = 0;
     for (; W >= 1; W >>= 1) {
-        smem = (size_t)W * SPW * ((size_t)T * G + (size_t)G * G * sizeof(float));
+        const size_t bp_bytes = (G == 16) ? (size_t)((T + 7) / 8) * G * 4 : (size_t)T * G;
+        smem = (size_t)W * SPW * (bp_bytes + (size_t)G * G * sizeof(float));
         if (smem <= 200 * 1024) break;
     }
     if (W < 1) {

@@ -80,6 +80,41 @@ class Label:
     def __repr__(self):
         return "%s (%.4f)" % (self.value, self.score)
 
+    def __eq__(self, other):
+        return isinstance(other, Label) and self.value == other.value and self.score == other.score
+
+
+class LabelSeq:
+    """Read-only sequence of Labels for one sentence, backed by the decoded tag indices / confidences of the batch.
+    Label objects are created when an element is accessed (a batch of 32 x 510 tokens is 16k Python objects -- 8 ms of
+    pure interpreter time per batch if built eagerly, which was more than half of the GPU time of the whole batch)."""
+    __slots__ = ("_names", "_tags", "_conf")
+
+    def __init__(self, names, tags, conf):
+        self._names, self._tags, self._conf = names, tags, conf
+
+    def __len__(self):
+        return len(self._tags)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [Label(self._names[a], c) for a, c in zip(self._tags[i], self._conf[i])]
+        return Label(self._names[self._tags[i]], self._conf[i])
+
+    def __iter__(self):
+        names = self._names
+        for a, c in zip(self._tags, self._conf):
+            yield Label(names[a], c)
+
+    def tag_indices(self):
+        return self._tags
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return repr(list(self))
+
 
 class Token:
     def __init__(self, text: str, idx: Optional[int] = None):

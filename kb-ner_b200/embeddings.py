@@ -305,7 +305,8 @@ class TransformerWordEmbeddings(torch.nn.Module):
     def encode(self, sentences) -> EncodedBatch:
         ids, key_len, row_of, first_idx, lengths, S = self.build_batch(sentences)
         dev = self.device_
-        parts = (ids, key_len, row_of, first_idx)
+        len_t = torch.tensor(lengths, dtype=torch.int32)
+        parts = (ids, key_len, row_of, first_idx, len_t)
         sizes = [t.numel() for t in parts]
         n = sum(sizes)
         slot = self._staging(n)
@@ -322,13 +323,18 @@ class TransformerWordEmbeddings(torch.nn.Module):
         o0, o1, o2 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
         ids_d = packed[:o0].view(ids.shape)
         key_d, row_d = packed[o0:o1], packed[o1:o2]
-        first_d = packed[o2:].view(first_idx.shape)
+        o3 = o2 + sizes[3]
+        first_d = packed[o2:o3].view(first_idx.shape)
+        len_d = packed[o3:]
         if self.fine_tune and self.training:
             # gradients are enabled iff (fine_tune and self.training), embeddings.py:3280
             hidden, saved = self.model.forward_train(ids_d, key_d)
-            return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d, saved=saved, encoder=self.model)
-        hidden = self.model.forward_hidden(ids_d, key_d)
-        return EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d)
+            eb = EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d, saved=saved, encoder=self.model)
+        else:
+            hidden = self.model.forward_hidden(ids_d, key_d)
+            eb = EncodedBatch(hidden, S, row_d, first_d, lengths, key_d, ids_d)
+        eb.lengths_d = len_d
+        return eb
 
     def embed(self, sentences):
         """Embeddings.embed (:75-101): afterwards ``sentences.features[self.name]`` holds the batch.  Here the

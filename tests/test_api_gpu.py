@@ -222,7 +222,8 @@ def test_finetune_gradients_vs_oracle_autograd():
     x = flat[idx.cuda()] * (first_idx >= 0).float().cuda()[..., None]
     W, b = tagger.linear.weight.detach().clone().requires_grad_(True), tagger.linear.bias.detach().clone().requires_grad_(True)
     (x @ W.t() + b).backward(d_logits)
-    torch.testing.assert_close(tagger.linear.weight.grad, W.grad, rtol=5e-2, atol=5e-3)
+    # (our x is the bf16 hidden state of the bf16 encoder, the oracle's is fp32)
+    assert ((tagger.linear.weight.grad - W.grad).norm() / W.grad.norm()).item() < 3e-2
     worst = {}
     own = dict(enc.named_parameters())
     for name, ref in op.items():
