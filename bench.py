@@ -186,9 +186,9 @@ def run_b200(args):
         (train.py:147-156 -> sequence_tagger_model.py:2611-2612,2698-2700): forward + _obtain_labels per batch."""
         loader = []
         for i in range(k):
-            b = batches[(offset + i) % len(batches)]
-            b.features = {}
-            loader.append(b)
+            # a fresh BatchedData per step: static (non-fine-tuned) embeddings are cached per batch object exactly as in
+            # the reference (embeddings.py:3030-3037), so re-using an object would skip the encoder
+            loader.append(BatchedData(list(batches[(offset + i) % len(batches)])))
         tagger.evaluate(loader, embeddings_storage_mode="none", prediction_mode=True, speed_test=True)
 
     def barrier():

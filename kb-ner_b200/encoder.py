@@ -104,6 +104,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         self._compute = None          # bf16 / fused compute copies, built by sync_compute_weights()
         self._ws = {}
         self._graphs = {}
+        self._tgraphs = {}
         import os
         self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
 
@@ -300,9 +301,19 @@ def _ensure_arena(self):
 
 @torch.no_grad()
 def _sync_compute_weights_arena(self):
-    """bf16 compute copies straight from the arena (Q|K|V are one contiguous [3H,H] region: no concatenation)."""
+    """bf16 compute copies straight from the arena (Q|K|V are one contiguous [3H,H] region: no concatenation).
+    The copies live in STATIC buffers that are refreshed in place after every optimizer step, so CUDA graphs that
+    captured their addresses stay valid."""
     ar = self.arena
     H = self.config.hidden_size
+    if getattr(self, "_compute_static", False) and self._compute is not None:
+        for lyr, w in zip(self.encoder.layer, self._compute):
+            a = lyr.attention
+            w["wqkv"].copy_(ar.view(a.self.query.weight, (3 * H, H)))
+            w["wo"].copy_(a.output.dense.weight)
+            w["w1"].copy_(lyr.intermediate.dense.weight)
+            w["w2"].copy_(lyr.output.dense.weight)
+        return
     layers = []
     for lyr in self.encoder.layer:
         a = lyr.attention
@@ -314,19 +325,18 @@ def _sync_compute_weights_arena(self):
             w2=lyr.output.dense.weight.bfloat16(), b2=lyr.output.dense.bias.data,
             g2=lyr.output.LayerNorm.weight.data, bb2=lyr.output.LayerNorm.bias.data))
     self._compute = layers
+    self._compute_static = True
+    self._graphs = {}
+    self._tgraphs = {}
 
 
 @torch.no_grad()
-def _forward_train(self, ids, key_len):
-    """Forward that keeps the activations the backward needs.  Returns (hidden [R*S,H] bf16, saved)."""
-    _ensure_arena(self)
-    if self._compute is None:
-        _sync_compute_weights_arena(self)
+def _forward_train_eager(self, ids, key_len):
     c = self.config
     R, S = ids.shape
     M, H, F = R * S, c.hidden_size, c.intermediate_size
     dev = ids.device
-    bf, f32 = torch.bfloat16, torch.float32
+    bf = torch.bfloat16
     e = self.embeddings
     x = ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight[0],
                          e.LayerNorm.weight, e.LayerNorm.bias, c.layer_norm_eps, c.pad_token_id)
@@ -346,8 +356,44 @@ def _forward_train(self, ids, key_len):
 
 
 @torch.no_grad()
-def _backward(self, saved, dout):
-    """dout: gradient w.r.t. the last hidden state, fp32 [R*S, H].  Accumulates into the gradient arena."""
+def _forward_train(self, ids, key_len):
+    """Forward that keeps the activations the backward needs.  Returns (hidden [R*S,H] bf16, saved).
+    Like forward_hidden, the launches of one (R, S) shape are captured into a CUDA graph on the second call and
+    replayed afterwards; the saved activations then live in the graph's private pool (valid until the next replay)."""
+    _ensure_arena(self)
+    if self._compute is None or not getattr(self, "_compute_static", False):
+        self._compute = None
+        _sync_compute_weights_arena(self)
+    if not self._use_graphs:
+        return _forward_train_eager(self, ids, key_len)
+    R, S = ids.shape
+    key = (R, S, str(ids.device))
+    st = self._tgraphs.get(key)
+    if st is None:
+        self._tgraphs[key] = {"fwd": None, "bwd": None}
+        return _forward_train_eager(self, ids, key_len)
+    if st["fwd"] is None:
+        from . import _lib
+        st["ids"], st["key_len"] = ids.clone(), key_len.clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            st["out"], st["saved"] = _forward_train_eager(self, st["ids"], st["key_len"])
+        st["fwd_launches"] = _lib.launch_count() - l0
+        st["saved"]["graph_state"] = st
+        st["fwd"] = g
+        st["pool"] = g.pool()
+    else:
+        st["ids"].copy_(ids, non_blocking=True)
+        st["key_len"].copy_(key_len, non_blocking=True)
+    st["fwd"].replay()
+    _lib_note_launches(st["fwd_launches"])
+    return st["out"], st["saved"]
+
+
+@torch.no_grad()
+def _backward_eager(self, saved, dout):
     c = self.config
     ar = self.arena
     R, S = saved["R"], saved["S"]
@@ -383,6 +429,30 @@ def _backward(self, saved, dout):
                      e.token_type_embeddings.weight.data[0], e.LayerNorm.weight.data, c.layer_norm_eps, c.pad_token_id,
                      dout, e.word_embeddings.weight.grad, e.position_embeddings.weight.grad,
                      e.token_type_embeddings.weight.grad[0], e.LayerNorm.weight.grad, e.LayerNorm.bias.grad)
+
+
+@torch.no_grad()
+def _backward(self, saved, dout):
+    """dout: gradient w.r.t. the last hidden state, fp32 [R*S, H].  Accumulates into the gradient arena.
+    When `saved` came from a replayed forward graph, the backward launches are captured / replayed as a graph too
+    (same pool; the activations, the arena and dout's static copy keep their addresses)."""
+    st = saved.get("graph_state")
+    if st is None:
+        return _backward_eager(self, saved, dout)
+    if st["bwd"] is None:
+        from . import _lib
+        st["dout"] = dout.clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g, pool=st["pool"]):
+            _backward_eager(self, saved, st["dout"])
+        st["bwd_launches"] = _lib.launch_count() - l0
+        st["bwd"] = g
+    else:
+        st["dout"].copy_(dout, non_blocking=True)
+    st["bwd"].replay()
+    _lib_note_launches(st["bwd_launches"])
 
 
 XLMRobertaEncoderB200.ensure_arena = _ensure_arena

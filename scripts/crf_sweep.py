@@ -25,7 +25,8 @@ def main():
     trans = torch.from_numpy(trans).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = {"T": T, "L": L, "hbm_peak_gbs": hbm, "rows": []}
-    for B in (64, 128, 256, 512, 1024, 2048, 4096, 16384):
+    sweep = [int(x) for x in os.environ["SWEEP_B"].split(",")] if os.environ.get("SWEEP_B") else (64, 128, 256, 512, 1024, 2048, 4096, 16384)
+    for B in sweep:
         emis = torch.randn(B, T, L, device="cuda") * 3
         lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
         tags = torch.randint(1, L - 2, (B, T), device="cuda", dtype=torch.int32)
