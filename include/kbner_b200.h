@@ -163,10 +163,12 @@ int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t
  * (flair/trainers/finetune_trainer.py:939-957 backward, :1007-1023 clip_grad_norm_(5.0) / step / zero_grad). */
 
 /* LayerNorm backward: x = saved fp32 pre-LN sum, dout = grad w.r.t. the LN output (fp32);
- * dx (bf16) = grad w.r.t. the pre-LN sum; dgamma / dbeta are ACCUMULATED into. */
+ * dx (bf16) = grad w.r.t. the pre-LN sum; dgamma / dbeta are ACCUMULATED into; dxsum (optional, [H]) accumulates the
+ * column sums of dx = the bias gradient of the Linear whose output fed this LayerNorm (saves a pass over dx). */
 int kbner_layernorm_bwd(const float *x /*[M,H]*/, const float *dout /*[M,H]*/, const float *gamma,
                         const float *mean /*[M]*/, const float *rstd /*[M]*/, int M, int H,
-                        uint16_t *dx /*[M,H] bf16*/, float *dgamma /*[H]*/, float *dbeta /*[H]*/, void *stream);
+                        uint16_t *dx /*[M,H] bf16*/, float *dgamma /*[H]*/, float *dbeta /*[H]*/,
+                        float *dxsum /*[H] or NULL*/, void *stream);
 
 /* Bias gradient: db[n] += sum_m dY[m][n]. */
 int kbner_colsum_bf16(const uint16_t *dY /*[M,N] bf16*/, int M, int N, float *db /*[N]*/, void *stream);

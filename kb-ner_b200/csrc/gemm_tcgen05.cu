@@ -128,6 +128,7 @@ struct GemmArgs {
     void *C;
     int M, N, K, ldc;
     int a_mn, b_mn;           // operand layouts (0 = K-major, 1 = MN-major)
+    int kb_per_split;         // k-blocks per work item (split-K, ACCUM epilogue only; otherwise all of K)
 };
 
 template <int EPI>
@@ -144,6 +145,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (g.K + BK - 1) / BK;
+    // split-K (wgrad: few output tiles, long K): work item w = (tile = w % num_tiles, split = w / num_tiles); every split
+    // adds its partial product into C with the TMA reduce-add epilogue
+    const int kb_per = g.kb_per_split;
+    const int num_splits = (num_kb + kb_per - 1) / kb_per;
+    const int num_work = num_tiles * num_splits;
 
     if (warp == 0 && lane == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
@@ -175,10 +181,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t phase = 0;
         const uint32_t a_smem0 = ptx::smem_u32(s.a[0]), b_smem0 = ptx::smem_u32(s.b[0]);
         const uint32_t full0_leader = mapa(ptx::smem_u32(&s.full[0]), 0);
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int w = cluster_id; w < num_work; w += num_clusters) {
+            const int tile = w % num_tiles, split = w / num_tiles;
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int am0 = m_blk * BM + (int)rank * 128, bn0 = n_blk * BN + (int)rank * 128;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, num_kb);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(&s.empty[stage], phase ^ 1);
                 if (ptx::elect_one()) {
                     if (leader) ptx::mbar_expect_tx(&s.full[stage], 2 * (kABytes + kBBytes));
@@ -216,13 +224,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+                const int split = w / num_tiles;
+                const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, num_kb);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&s.full[stage], phase);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
@@ -230,7 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             mma_f16_ss_2sm(d_tmem, pack_desc(a_lo + k * a_kstep, hi), pack_desc(b_lo + k * b_kstep, hi),
-                                           idesc, (kb | k) != 0);
+                                           idesc, (kb != kb0) || (k != 0));
                         mma_commit_mc(empty0 + stage * 8, 0b11);
                     }
                     __syncwarp();
@@ -281,7 +291,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ++nstores;
         };
         int it = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+            const int tile = w % num_tiles;
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -398,7 +409,9 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
         configured = true;
     }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-    const int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+    const int num_kb = (g.K + BK - 1) / BK;
+    const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
+    const int clusters = num_work < kNumSMs / 2 ? num_work : kNumSMs / 2;
     gemm_bf16_kernel<EPI><<<clusters * 2, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmAux, g);
     KBNER_CHECK_LAUNCH("gemm_bf16");
     return KBNER_OK;
@@ -439,7 +452,17 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
         rc = make_tmap_2d(&tmAux, aux_out, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 64, 2);
         if (rc) return rc;
     }
-    GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0};
+    const int num_kb_h = (K + BK - 1) / BK;
+    int kb_per = num_kb_h;
+    if (epilogue == KBNER_EPI_ACCUM_F32) {
+        // fill ~2 work items per cluster, but keep >= 4 k-blocks per item so the pipeline prologue stays amortised
+        const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+        int splits = (2 * (kNumSMs / 2)) / tiles;
+        if (splits > num_kb_h / 4) splits = num_kb_h / 4;
+        if (splits < 1) splits = 1;
+        kb_per = (num_kb_h + splits - 1) / splits;
+    }
+    GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, kb_per};
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
         case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, tmC, tmAux, g, st);

@@ -18,19 +18,20 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout, const float *__restrict__ gamma,
                      const float *__restrict__ mean, const float *__restrict__ rstd, int M,
-                     uint16_t *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+                     uint16_t *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                     float *__restrict__ dxsum) {
     constexpr int H = VPL * 128;
-    __shared__ float s_red[2][H];
+    __shared__ float s_red[3][H];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
     __syncthreads();
     float4 gm[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
-    float4 ag[VPL], ab[VPL];
+    float4 ag[VPL], ab[VPL], ax[VPL];      // per-lane partial column sums: dgamma, dbeta, sum of dx (bias gradient)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+    for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ax[i] = make_float4(0, 0, 0, 0); }
     for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
         const float mu = mean[row], rs = rstd[row];
         const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * H);
@@ -53,9 +54,12 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout
         uint16_t *o = dx + (size_t)row * H;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
+            const float d0 = rs * (g[i].x - m1 - xh[i].x * m2), d1 = rs * (g[i].y - m1 - xh[i].y * m2);
+            const float d2 = rs * (g[i].z - m1 - xh[i].z * m2), d3 = rs * (g[i].w - m1 - xh[i].w * m2);
+            ax[i].x += d0; ax[i].y += d1; ax[i].z += d2; ax[i].w += d3;
             uint2 p;
-            p.x = pack_bf16x2(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2));
-            p.y = pack_bf16x2(rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
+            p.x = pack_bf16x2(d0, d1);
+            p.y = pack_bf16x2(d2, d3);
             *reinterpret_cast<uint2 *>(o + (i * 32 + lane) * 4) = p;
         }
     }
@@ -66,11 +70,16 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout
         atomicAdd(&s_red[0][c + 2], ag[i].z); atomicAdd(&s_red[0][c + 3], ag[i].w);
         atomicAdd(&s_red[1][c + 0], ab[i].x); atomicAdd(&s_red[1][c + 1], ab[i].y);
         atomicAdd(&s_red[1][c + 2], ab[i].z); atomicAdd(&s_red[1][c + 3], ab[i].w);
+        if (dxsum) {
+            atomicAdd(&s_red[2][c + 0], ax[i].x); atomicAdd(&s_red[2][c + 1], ax[i].y);
+            atomicAdd(&s_red[2][c + 2], ax[i].z); atomicAdd(&s_red[2][c + 3], ax[i].w);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
         atomicAdd(&dgamma[i], s_red[0][i]);
         atomicAdd(&dbeta[i], s_red[1][i]);
+        if (dxsum) atomicAdd(&dxsum[i], s_red[2][i]);
     }
 }
 
@@ -334,14 +343,14 @@ using namespace kbner;
 
 extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const float *gamma, const float *mean,
                                    const float *rstd, int M, int H, uint16_t *dx, float *dgamma, float *dbeta,
-                                   void *stream) {
+                                   float *dxsum, void *stream) {
     KBNER_CHECK_ARG(x && dout && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H % 128 == 0, "layernorm_bwd: bad shape");
     if (M == 0) return KBNER_OK;
     int blocks = (M + 7) / 8;
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    if (blocks > kNumSMs) blocks = kNumSMs;       // one block per SM: the per-block column partials end in 3*H global atomics
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL><<<blocks, 256, 0, st>>>(x, dout, gamma, mean, rstd, M, dx, dgamma, dbeta)));
+    DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL><<<blocks, 256, 0, st>>>(x, dout, gamma, mean, rstd, M, dx, dgamma, dbeta, dxsum)));
     KBNER_CHECK_LAUNCH("layernorm_bwd");
     return KBNER_OK;
 }
@@ -349,7 +358,7 @@ extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const floa
 extern "C" int kbner_colsum_bf16(const uint16_t *dY, int M, int N, float *db, void *stream) {
     KBNER_CHECK_ARG(dY && db && M >= 0 && N > 0 && N % 8 == 0, "colsum_bf16: bad arguments");
     if (M == 0) return KBNER_OK;
-    dim3 grid((N + 255) / 256, 32);
+    dim3 grid((N + 255) / 256, 96);            // ~ a few hundred blocks: the pass is latency-bound otherwise
     if ((int)grid.y * 8 > M) grid.y = (M + 7) / 8;
     colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, M, N, db);
     KBNER_CHECK_LAUNCH("colsum_bf16");

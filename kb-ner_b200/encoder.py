@@ -407,16 +407,16 @@ def _backward_eager(self, saved, dout):
         a = lyr.attention
         x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2 = saved["layers"][li]
         # ---- FFN block ------------------------------------------------------------------------------
-        dy2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad)
-        ops.colsum_bf16(dy2, lyr.output.dense.bias.grad)
+        dy2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad,
+                                dxsum=lyr.output.dense.bias.grad)
         ops.gemm_bf16(dy2, h, H, F, M, ops.EPI_ACCUM_F32, out=lyr.output.dense.weight.grad, a_mn=True, b_mn=True)
         dhpre = ops.gemm_bf16(dy2, w["w2"], M, F, H, ops.EPI_DGELU_BF16, aux=hpre, b_mn=True)
         ops.colsum_bf16(dhpre, lyr.intermediate.dense.bias.grad)
         ops.gemm_bf16(dhpre, x1, F, H, M, ops.EPI_ACCUM_F32, out=lyr.intermediate.dense.weight.grad, a_mn=True, b_mn=True)
         dx1 = ops.gemm_bf16(dhpre, w["w1"], M, H, F, ops.EPI_BIAS_RESID_F32, aux=dy2, b_mn=True)      # + residual path
         # ---- attention block ------------------------------------------------------------------------
-        dy1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad)
-        ops.colsum_bf16(dy1, a.output.dense.bias.grad)
+        dy1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad,
+                                dxsum=a.output.dense.bias.grad)
         ops.gemm_bf16(dy1, ctx, H, H, M, ops.EPI_ACCUM_F32, out=a.output.dense.weight.grad, a_mn=True, b_mn=True)
         dctx = ops.gemm_bf16(dy1, w["wo"], M, H, H, ops.EPI_BIAS, b_mn=True)
         dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws)

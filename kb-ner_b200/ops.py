@@ -175,8 +175,8 @@ def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False):
 
 
 # ---- fine-tuning step -----------------------------------------------------------------------------
-def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None):
-    """dx (bf16 [M,H]) of LayerNorm; dgamma / dbeta (fp32 [H]) are accumulated into."""
+def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None, dxsum=None):
+    """dx (bf16 [M,H]) of LayerNorm; dgamma / dbeta (fp32 [H]) are accumulated into; dxsum (optional) += colsum(dx)."""
     _chk(x, torch.float32, "x", 2)
     _chk(dout, torch.float32, "dout", 2)
     for n, t in (("gamma", gamma), ("mean", mean), ("rstd", rstd), ("dgamma", dgamma), ("dbeta", dbeta)):
@@ -184,8 +184,9 @@ def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None):
     M, H = x.shape
     if out is None:
         out = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+    _chk(dxsum, torch.float32, "dxsum", 1)
     _lib.check(_lib.load().kbner_layernorm_bwd(_ptr(x), _ptr(dout), _ptr(gamma), _ptr(mean), _ptr(rstd), M, H, _ptr(out),
-                                               _ptr(dgamma), _ptr(dbeta), _stream()), "layernorm_bwd")
+                                               _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream()), "layernorm_bwd")
     return out
 
 

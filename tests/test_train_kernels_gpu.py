@@ -79,8 +79,10 @@ def test_layernorm_bwd(ops, H):
     torch.nn.functional.layer_norm(x, (H,), gamma, beta, 1e-5).backward(dout)
     dgamma = torch.zeros(H, device="cuda")
     dbeta = torch.zeros(H, device="cuda")
-    dx = ops.layernorm_bwd(x.detach(), dout, gamma.detach(), mean, rstd, dgamma, dbeta)
+    dxsum = torch.zeros(H, device="cuda")
+    dx = ops.layernorm_bwd(x.detach(), dout, gamma.detach(), mean, rstd, dgamma, dbeta, dxsum=dxsum)
     assert bool(((dx.float() - x.grad).abs() <= 2.0 ** -8 * x.grad.abs() + 1e-4).all())
+    torch.testing.assert_close(dxsum, x.grad.sum(0), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(dgamma, gamma.grad, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(dbeta, beta.grad, rtol=1e-4, atol=1e-3)
 
