@@ -8,15 +8,15 @@
 //   dQ = dS . K / 8                      dK = dS^T . Q / 8
 //
 // One CTA = one (window r, head h, block j of 128 keys); it loops over the query blocks i of 128 rows.
-//   warp 4       TMA + MMA issuer (elected lane).  Per (i, j):
+//   warp 8       TMA + MMA issuer (elected lane).  Per (i, j):
 //                  S^T  = K_j . Q_i^T     (M = keys, N = queries; both operands K-major)            -> TMEM
 //                  dP^T = V_j . dO_i^T                                                              -> TMEM
 //                  ... threads turn them into P^T and dS^T (bf16, shared memory) ...
 //                  dV_j += P^T  . dO_i    (A = P^T  K-major from smem,  B = dO_i MN-major in place)  -> TMEM, kept over i
 //                  dK_j += dS^T . Q_i     (A = dS^T K-major,            B = Q_i  MN-major in place)  -> TMEM, kept over i
 //                  dQ_i  = dS   . K_j     (A = the SAME dS^T tile read MN-major, B = K_j MN-major)   -> TMEM
-//   warps 0..3   thread = key row (= TMEM lane) for P^T / dS^T; thread = query row for the dQ_i read-out, which is
-//                added to the fp32 dQ accumulator in global memory with red.global.add (other key blocks add theirs).
+//   warps 0..7   two threads per key row (= TMEM lane) build P^T / dS^T; two threads per query row read dQ_i out, which
+//                is added to the fp32 dQ accumulator in global memory with red.global.add (other key blocks add theirs).
 // dK_j / dV_j are written once, as bf16, into the K | V column blocks of the fused dqkv matrix; dQ is converted from
 // the fp32 accumulator by `attn_bwd_dq_kernel`.  D is produced by `attn_bwd_prep_kernel`.
 #include <math_constants.h>
@@ -27,7 +27,7 @@
 
 namespace kbner {
 
-constexpr int kBwdThreads = 160;
+constexpr int kBwdThreads = 288;        // 8 compute warps (two threads per key / query row) + 1 TMA/MMA warp
 constexpr uint32_t kT128 = 128 * 64 * 2;        // [128 rows][64 bf16] SWIZZLE_128B tile = 16 KB
 
 struct AttnBwdSmem {
@@ -113,11 +113,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         ptx::mbar_init(&s.qdo_full[0], 1);
         ptx::mbar_init(&s.qdo_full[1], 1);
         ptx::mbar_init(&s.bar_sdp, 1);
-        ptx::mbar_init(&s.bar_pd, 128);
+        ptx::mbar_init(&s.bar_pd, 256);
         ptx::mbar_init(&s.bar_out, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 4) ptx::tmem_alloc<512>(&s.tmem_base);
+    if (warp == 8) ptx::tmem_alloc<512>(&s.tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -138,7 +138,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ===================== TMA + MMA issuer (warp-uniform; elected lane issues) =====================
         constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : both K-major
         constexpr uint32_t idesc_kmn = ptx::make_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major, B MN-major
@@ -216,32 +216,34 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
         }
     } else {
-        // ===================== compute warps =====================
-        const int t = warp * 32 + lane;                   // key row of this block (P^T / dS^T) and query row (dQ read-out)
-        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+        // ===================== compute warps: two threads per row =====================
+        // warps w and w+4 share TMEM lane quarter w; `half` picks which 64 of the 128 query columns of the P^T / dS^T
+        // tile (and which 32 of the 64 output columns of dQ / dK / dV) the thread owns.
+        const int quarter = warp & 3, half = warp >> 2;
+        const int t = quarter * 32 + lane;                // key row of this block (P^T / dS^T) and query row (dQ read-out)
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const bool key_ok = jb * 128 + t < klen;
         const float scale_log2 = 0.125f * 1.4426950408889634f;
         for (int i = 0; i < nqb; ++i) {
-            // stage LSE / D of query block i (one value per thread)
+            // stage LSE / D of query block i (one value per row; both threads of a row write the same value)
             {
                 const int qi = i * 128 + t;
                 const size_t off = ((size_t)r * heads + h) * S + qi;
                 s.lse2[i & 1][t] = (qi < S) ? lse[off] * 1.4426950408889634f : CUDART_INF_F;
                 s.dsum[i & 1][t] = (qi < S) ? Dsum[off] : 0.0f;
             }
-            // P^T / dS^T smem of block i-1 is still being read by its MMAs until bar_out(i-1): handled below (we wait
-            // for bar_out(i-1) before the dQ read-out, i.e. before getting here).  Named barrier: compute warps only.
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
             ptx::mbar_wait(&s.bar_sdp, i & 1);
             ptx::tc_fence_after();
             const float *lse2 = s.lse2[i & 1], *dsum = s.dsum[i & 1];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {                 // 4 chunks of 32 query columns
+            for (int cl = 0; cl < 2; ++cl) {              // this thread's 2 chunks of 32 query columns
+                const int c = half * 2 + cl;
                 uint32_t rs[32], rd[32];
                 ptx::tmem_ld_32x32b_x32(t_st + lane_addr + c * 32, rs);
                 ptx::tmem_ld_32x32b_x32(t_dpt + lane_addr + c * 32, rd);
                 ptx::tmem_ld_wait();
-                uint8_t *prow = s.pt[c >> 1] + t * 128, *drow = s.dst[c >> 1] + t * 128;
+                uint8_t *prow = s.pt[half] + t * 128, *drow = s.dst[half] + t * 128;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks of 8 queries
                     float p[8], d[8];
@@ -257,7 +259,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
                     dk.x = pack_bf16x2(d[0], d[1]); dk.y = pack_bf16x2(d[2], d[3]);
                     dk.z = pack_bf16x2(d[4], d[5]); dk.w = pack_bf16x2(d[6], d[7]);
-                    const int chunk = (c & 1) * 4 + cc;   // 16-byte chunk inside the 128-byte row of the sub-tile
+                    const int chunk = cl * 4 + cc;        // 16-byte chunk inside the 128-byte row of sub-tile `half`
                     const int phys = (chunk ^ (t & 7)) << 4;
                     *reinterpret_cast<uint4 *>(prow + phys) = pk;
                     *reinterpret_cast<uint4 *>(drow + phys) = dk;
@@ -266,55 +268,51 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&s.bar_pd);
-            // dQ_i read-out: thread = query row
+            // dQ_i read-out: thread = (query row, 32-column half)
             ptx::mbar_wait(&s.bar_out, i & 1);
             ptx::tc_fence_after();
             const int qi = i * 128 + t;
-            float *qrow = dq_acc + (size_t)(row0 + qi) * H + h * 64;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            float *qrow = dq_acc + (size_t)(row0 + qi) * H + h * 64 + half * 32;
+            {
                 uint32_t rq[32];
-                ptx::tmem_ld_32x32b_x32(t_dq + lane_addr + c * 32, rq);
+                ptx::tmem_ld_32x32b_x32(t_dq + lane_addr + half * 32, rq);
                 ptx::tmem_ld_wait();
                 if (qi < S) {
 #pragma unroll
                     for (int e = 0; e < 32; e += 4)
-                        red_add_v4(qrow + c * 32 + e, __uint_as_float(rq[e]), __uint_as_float(rq[e + 1]),
+                        red_add_v4(qrow + e, __uint_as_float(rq[e]), __uint_as_float(rq[e + 1]),
                                    __uint_as_float(rq[e + 2]), __uint_as_float(rq[e + 3]));
                 }
             }
             ptx::tc_fence_before();
         }
-        // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them)
-        // (tcgen05.ld is warp-collective: every lane executes it, only the stores are guarded -- a per-lane guard
-        //  around the load deadlocked windows whose length is not a multiple of 128)
+        // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them).
+        // tcgen05.ld is warp-collective: every lane executes it, only the stores are guarded (a per-lane guard around
+        // the load deadlocked windows whose length is not a multiple of 128).
         const int krow = jb * 128 + t;
         {
-            uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64;
+            uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64 + half * 32;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
+                uint32_t rr[32];
+                ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + half * 32, rr);
+                ptx::tmem_ld_wait();
+                if (krow >= S) continue;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t rr[32];
-                    ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + c * 32, rr);
-                    ptx::tmem_ld_wait();
-                    if (krow >= S) continue;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 8) {
-                        uint4 ov;
-                        ov.x = pack_bf16x2(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]));
-                        ov.y = pack_bf16x2(__uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
-                        ov.z = pack_bf16x2(__uint_as_float(rr[e + 4]), __uint_as_float(rr[e + 5]));
-                        ov.w = pack_bf16x2(__uint_as_float(rr[e + 6]), __uint_as_float(rr[e + 7]));
-                        *reinterpret_cast<uint4 *>(o + (which ? 2 * H : H) + c * 32 + e) = ov;
-                    }
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 ov;
+                    ov.x = pack_bf16x2(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]));
+                    ov.y = pack_bf16x2(__uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+                    ov.z = pack_bf16x2(__uint_as_float(rr[e + 4]), __uint_as_float(rr[e + 5]));
+                    ov.w = pack_bf16x2(__uint_as_float(rr[e + 6]), __uint_as_float(rr[e + 7]));
+                    *reinterpret_cast<uint4 *>(o + (which ? 2 * H : H) + e) = ov;
                 }
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
     }
