@@ -108,6 +108,22 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         import os
         self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
 
+    # ---- checkpointing: only parameters travel; graphs, workspaces, compute copies and the arena are rebuilt ----
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ("_compute", "arena"):
+            state[k] = None
+        for k in ("_ws", "_graphs", "_tgraphs"):
+            state[k] = {}
+        state["_compute_static"] = False
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        # parameters arrive as views of the saved arena storage: give each its own storage again
+        for p in self.parameters():
+            p.data = p.data.clone()
+
     # ---- weights ---------------------------------------------------------------------------------
     def load_hf_state_dict(self, sd):
         own = self.state_dict()
