@@ -101,6 +101,31 @@ int kbner_layernorm_fwd(const float *x /*[M,H]*/, const float *gamma, const floa
                         int M, int H, uint16_t *y /*[M,H] bf16*/,
                         float *mean /*[M] or NULL*/, float *rstd /*[M] or NULL*/, void *stream);
 
+/* z = dropout(x + bias) + resid;  y = LayerNorm(z) * gamma + beta.
+ * The tail of transformers' BertSelfOutput / BertOutput (dense bias, hidden-state dropout p = 0.1 in training,
+ * residual connection, LayerNorm) as ONE HBM pass; the GEMM before it then has a plain fp32 epilogue (the accumulator
+ * layout of tcgen05.ld is row-per-thread: a residual read there is a 32-sector-per-request load on the critical path).
+ * bias / resid may be NULL.  Dropout is off when drop_seed is NULL or drop_p == 0; otherwise element (row, col) of
+ * dropout site `drop_site` is kept iff the 16-bit half (col & 1) of fmix32(pair * 0x9E3779B1 + key) is >= round(p * 65536),
+ * pair = row * H/2 + col/2, key = fmix32(seed[0] + 0x9E3779B9 * (site + 1)) ^ seed[1]  (csrc/common.cuh); `drop_seed`
+ * is DEVICE memory (2 words) so that a captured CUDA graph picks up a new seed at every replay.
+ * Replaces: torch.nn.Dropout + residual add + torch.nn.LayerNorm as called under flair/embeddings.py:3269. */
+int kbner_add_layernorm_fwd(const float *x /*[M,H]*/, const float *bias /*[H] or NULL*/,
+                            const uint16_t *resid /*[M,H] bf16 or NULL*/, const float *gamma, const float *beta,
+                            float eps, int M, int H, uint16_t *y /*[M,H] bf16*/, float *mean, float *rstd,
+                            const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream);
+
+/* In-place element-wise dropout with the same counter-hash mask (XLMRobertaEmbeddings.dropout: bf16 activations in the
+ * forward, fp32 gradient in the backward). */
+int kbner_dropout_apply(void *x /*[M,H] bf16 or fp32*/, int is_f32, int M, int H, const uint32_t *drop_seed,
+                        uint32_t drop_site, float drop_p, void *stream);
+
+/* attention forward with attention-probability dropout (BertSelfAttention.dropout): the mask multiplies P after the
+ * row sum was taken; counter = ((window * heads + head) * 512 + query) * 256 + key / 2, half = key & 1. */
+int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
+                                float drop_p, void *stream);
+
 /* First-sub-token pooling + word dropout + tag projection in one pass:
  * logits[b,t,:] = keep_t * hidden[row(b), first_idx[b,t], :] . W^T + bias
  * first_idx[b,t] = sub-token index inside the window row (or -1 => zero vector, i.e. bias only).
@@ -169,6 +194,21 @@ int kbner_layernorm_bwd(const float *x /*[M,H]*/, const float *dout /*[M,H]*/, c
                         const float *mean /*[M]*/, const float *rstd /*[M]*/, int M, int H,
                         uint16_t *dx /*[M,H] bf16*/, float *dgamma /*[H]*/, float *dbeta /*[H]*/,
                         float *dxsum /*[H] or NULL*/, void *stream);
+
+/* Backward of kbner_add_layernorm_fwd.  z is recomputed from (x, bias, resid, mask); the incoming gradient is
+ * dout (fp32, the dgrad GEMM's plain output) + dres (bf16, the gradient that arrives over the residual connection, or NULL).
+ * dx = d loss / d z (bf16): what flows on over the residual connection.  With dropout, dx_masked = dx * mask / (1 - p) is
+ * the gradient of the Linear's output (operand of its dgrad / wgrad; its column sums go to dxsum = the bias gradient);
+ * without dropout dx serves both and dx_masked may be NULL. */
+int kbner_add_layernorm_bwd(const float *x, const float *bias, const uint16_t *resid, const float *dout,
+                            const uint16_t *dres, const float *gamma, const float *mean, const float *rstd,
+                            int M, int H, uint16_t *dx, uint16_t *dx_masked, float *dgamma, float *dbeta,
+                            float *dxsum, const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream);
+
+int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out, const float *lse,
+                                const int32_t *key_len, int R, int S, int heads, float *d_scratch, float *dq_acc,
+                                uint16_t *dqkv, const uint32_t *drop_seed, uint32_t drop_site, float drop_p,
+                                void *stream);
 
 /* Bias gradient: db[n] += sum_m dY[m][n]. */
 int kbner_colsum_bf16(const uint16_t *dY /*[M,N] bf16*/, int M, int N, float *db /*[N]*/, void *stream);

@@ -92,10 +92,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// DROP: attention-probability dropout.  The forward multiplied P by mask / (1 - p) before P.V, so
+//   dV = (P * mask / (1-p))^T . dO,   dP = (dO . V^T) * mask / (1-p),   dS = P * (dP - D)   with D = rowsum(dO * O)
+// (D needs no change: O already is the dropped product).  The mask bits are regenerated from (window, head, query, key).
+template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const int32_t *__restrict__ key_len, const float *__restrict__ lse, const float *__restrict__ Dsum,
-                     int S, int H, int heads, float *__restrict__ dq_acc, uint16_t *__restrict__ dqkv) {
+                     int S, int H, int heads, float *__restrict__ dq_acc, uint16_t *__restrict__ dqkv, const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     AttnBwdSmem &s = *reinterpret_cast<AttnBwdSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,6 +228,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const bool key_ok = jb * 128 + t < klen;
         const float scale_log2 = 0.125f * 1.4426950408889634f;
+        const uint32_t dkey = DROP ? drop_key(drop) : 0u;
+        const uint32_t kpair = (uint32_t)(jb * 128 + t) >> 1;          // this thread's key: pair index and half
+        const bool khi = ((jb * 128 + t) & 1) != 0;
+        const uint32_t dwin = (uint32_t)(r * heads + h) * 512u;        // same counter layout as attention_fwd_kernel
         for (int i = 0; i < nqb; ++i) {
             // stage LSE / D of query block i (one value per row; both threads of a row write the same value)
             {
@@ -251,8 +259,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     for (int e = 0; e < 8; ++e) {
                         const int col = c * 32 + cc * 8 + e;
                         const float pe = key_ok ? ex2_fast(fmaf(__uint_as_float(rs[cc * 8 + e]), scale_log2, -lse2[col])) : 0.0f;
+                        float dp = __uint_as_float(rd[cc * 8 + e]);
                         p[e] = pe;
-                        d[e] = pe * (__uint_as_float(rd[cc * 8 + e]) - dsum[col]) * 0.125f;
+                        if (DROP) {
+                            const uint32_t bits = drop_bits(dkey, (dwin + (uint32_t)(i * 128 + col)) * 256u + kpair);
+                            const bool keep = khi ? drop_keep_hi(bits, drop.thresh) : drop_keep_lo(bits, drop.thresh);
+                            p[e] = keep ? pe * drop.scale : 0.0f;      // P after dropout: the A operand of dV
+                            dp = keep ? dp * drop.scale : 0.0f;
+                        }
+                        d[e] = pe * (dp - dsum[col]) * 0.125f;
                     }
                     uint4 pk, dk;
                     pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
@@ -322,9 +337,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 using namespace kbner;
 
-extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
-                                   const float *lse, const int32_t *key_len, int R, int S, int heads,
-                                   float *d_scratch, float *dq_acc, uint16_t *dqkv, void *stream) {
+extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
+                                           const float *lse, const int32_t *key_len, int R, int S, int heads,
+                                           float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
+                                           uint32_t drop_site, float drop_p, void *stream) {
+    KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_bwd: dropout probability %f", (double)drop_p);
+    KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * 512 * 256 < (1ull << 32),
+                    "attention_bwd: R*heads exceeds the 32-bit dropout counter");
+    const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
     KBNER_CHECK_ARG(qkv && out && d_out && lse && key_len && d_scratch && dq_acc && dqkv, "attention_bwd: null pointer");
     KBNER_CHECK_ARG(R > 0 && S > 0 && heads > 0 && S <= 512, "attention_bwd: bad shape R=%d S=%d heads=%d", R, S, heads);
     const int H = heads * 64;
@@ -346,7 +366,9 @@ extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, con
     const size_t smem = sizeof(AttnBwdSmem);
     static bool configured = false;
     if (!configured) {
-        e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return KBNER_ECUDA;
@@ -354,10 +376,20 @@ extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, con
         configured = true;
     }
     dim3 grid((S + 127) / 128, heads, R);
-    attention_bwd_kernel<<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv);
+    if (drop.thresh)
+        attention_bwd_kernel<true><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
+    else
+        attention_bwd_kernel<false><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
     KBNER_CHECK_LAUNCH("attention_bwd");
     const size_t n8 = (size_t)M * H / 8;
     attn_bwd_dq_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq_acc, M, H, dqkv);
     KBNER_CHECK_LAUNCH("attn_bwd_dq");
     return KBNER_OK;
+}
+
+extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
+                                   const float *lse, const int32_t *key_len, int R, int S, int heads,
+                                   float *d_scratch, float *dq_acc, uint16_t *dqkv, void *stream) {
+    return kbner_attention_bwd_dropout(qkv, out, d_out, lse, key_len, R, S, heads, d_scratch, dq_acc, dqkv, nullptr, 0u, 0.0f,
+                                       stream);
 }

@@ -6,12 +6,16 @@
 // One CTA = one (window r, head h, block of 128 query rows); TWO CTAs are resident per SM (96 KB of shared
 // memory, 256 TMEM columns, <= 200 registers each) so the softmax of one overlaps the MMAs of the other --
 // the round-1 version (1 CTA/SM, 1 softmax warp per scheduler) was latency-bound at 162 us per layer.
-//   warp 4        TMA + MMA issuer (one lane): K/V stream through a 3-stage ring of 64-key blocks;
+//   warp 8        TMA + MMA issuer (one lane): K/V stream through a 3-stage ring of 64-key blocks;
 //                 S_j = Q.K_j^T -> TMEM (2 buffers x 64 cols), O_j = P_j.V_j -> TMEM (2 buffers x 64 cols);
 //                 tcgen05.mma kind::f16, V consumed MN-major straight from its row-major [key][d] tile
-//   warps 0..3    softmax: thread = query row = TMEM lane; tcgen05.ld the 64 scores, online max / ex2 / sum
-//                 in fp32 registers, P_j -> bf16 -> shared memory in the SWIZZLE_128B K-major layout the MMA
-//                 reads; running O in registers (O = O*alpha + P_j.V_j): no TMEM read-modify-write pass.
+//   warps 0..7    softmax, two threads per query row (= TMEM lane; warps w and w+4 share a lane quarter and split the
+//                 64 key columns): tcgen05.ld the scores, online max / ex2 / sum in fp32 registers, P_j -> bf16 ->
+//                 shared memory in the SWIZZLE_128B K-major layout the MMA reads; running O in registers
+//                 (O = O*alpha + P_j.V_j): no TMEM read-modify-write pass.
+// Training (DROP): attention-probability dropout (transformers BertSelfAttention.dropout, p = 0.1) is applied to P_j
+// after the row sum has been taken, with the stateless counter-hash mask of common.cuh indexed by
+// (window, head, query, key); the 1/(1-p) scale is folded into the final normalisation.
 // Pipeline inside a CTA: S_{j+1} is issued before softmax(j) finishes; P / O are double-buffered and the
 // accumulation of O_{j-1} is deferred until P_j has been published.
 // Bound: MUFU (one ex2 per score: 16/clk/SM => 512 clk per 128x64 block), not the tensor pipe.
@@ -52,10 +56,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const int32_t *__restrict__ key_len, int S, int H, int heads, uint16_t *__restrict__ out,
-                     float *__restrict__ lse_out) {
+                     float *__restrict__ lse_out, const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     AttnSmem &s = *reinterpret_cast<AttnSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,6 +161,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
         float m_run = -CUDART_INF_F, l_run = 0.0f, alpha_prev = 1.0f;
+        const uint32_t dkey = DROP ? drop_key(drop) : 0u;
+        // dropout counter of (window, head, query): 256 key PAIRS per row (kMaxS / 2), the same in the backward kernel
+        const uint32_t drow = (((uint32_t)(r * heads + h) * (uint32_t)kMaxS) + (uint32_t)qrow) * (uint32_t)(kMaxS / 2);
         float o_acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
@@ -209,6 +217,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     pv[e] = ex2_approx(fmaf(sc[cc * 8 + e], scale_log2, neg_m));
                     l_blk += pv[e];
                 }
+                if (DROP) {                  // the softmax denominator is of the un-dropped row; only P.V sees the mask
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const uint32_t bits = drop_bits(dkey, drow + (uint32_t)((kbase + cc * 8) >> 1) + e2);
+                        if (!drop_keep_lo(bits, drop.thresh)) pv[2 * e2] = 0.0f;
+                        if (!drop_keep_hi(bits, drop.thresh)) pv[2 * e2 + 1] = 0.0f;
+                    }
+                }
                 uint4 pk;
                 pk.x = pack_bf16x2(pv[0], pv[1]);
                 pk.y = pack_bf16x2(pv[2], pv[3]);
@@ -231,7 +247,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float l_tot = l_run + s.xsum[half ^ 1][row];
         // epilogue: normalise, bf16, 64 contiguous bytes per thread
         if (qrow < S) {
-            const float inv = (l_tot > 0.0f) ? 1.0f / l_tot : 0.0f;
+            const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
             uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
@@ -259,9 +275,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 using namespace kbner;
 
-extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
-                                   uint16_t *out, float *lse, void *stream) {
+extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                           uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
+                                           float drop_p, void *stream) {
     KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
+    KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_fwd: dropout probability %f", (double)drop_p);
+    KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * kMaxS * (kMaxS / 2) < (1ull << 32),
+                    "attention_fwd: R*heads exceeds the 32-bit dropout counter");
     KBNER_CHECK_ARG(R > 0 && S > 0 && heads > 0, "attention_fwd: empty problem");
     KBNER_CHECK_ARG(S <= kMaxS, "attention_fwd: S=%d exceeds the %d-sub-token window of XLM-R", S, kMaxS);
     const int H = heads * kAttnD;
@@ -271,9 +291,12 @@ extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, 
     rc = make_tmap_bf16_2d(&tmKV, qkv, (uint64_t)R * S, (uint64_t)3 * H, (uint64_t)3 * H, kBKV, 64);
     if (rc) return rc;
     const size_t smem = sizeof(AttnSmem);
+    const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return KBNER_ECUDA;
@@ -281,7 +304,15 @@ extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, 
         configured = true;
     }
     dim3 grid((S + kBQ - 1) / kBQ, heads, R);
-    attention_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse);
+    if (drop.thresh)
+        attention_fwd_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse, drop);
+    else
+        attention_fwd_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse, drop);
     KBNER_CHECK_LAUNCH("attention_fwd");
     return KBNER_OK;
+}
+
+extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                   uint16_t *out, float *lse, void *stream) {
+    return kbner_attention_fwd_dropout(qkv, key_len, R, S, heads, out, lse, nullptr, 0u, 0.0f, stream);
 }

@@ -81,4 +81,40 @@ __device__ __forceinline__ void st_na_v4(void *p, uint4 v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ---- dropout: stateless keep mask from a counter hash ---------------------------------------------------------------
+// The reference trains with torch.nn.Dropout inside transformers (hidden 0.1, attention probabilities 0.1).  Here a mask
+// is never stored: element e of dropout site `site` is kept iff the 16-bit half (e & 1) of
+//     fmix32((e >> 1) * 0x9E3779B1 + key),   key = f(seed[0], seed[1], site)
+// is >= thresh = round(p * 65536); kept values are scaled by 1 / (1 - thresh / 65536).  The backward kernels regenerate
+// the same bits.  `seed` lives in DEVICE memory so that a captured CUDA graph sees a fresh seed at every replay.
+struct Dropout {
+    const uint32_t *seed;   // device, 2 words; NULL = dropout off
+    uint32_t site;
+    uint32_t thresh;        // 0 = off
+    float scale;
+};
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const Dropout &d) {
+    return fmix32(__ldg(d.seed) + 0x9E3779B9u * (d.site + 1u)) ^ __ldg(d.seed + 1);
+}
+__device__ __forceinline__ uint32_t drop_bits(uint32_t key, uint32_t pair) { return fmix32(pair * 0x9E3779B1u + key); }
+// keep flags of the two elements of a pair
+__device__ __forceinline__ bool drop_keep_lo(uint32_t bits, uint32_t thresh) { return (bits & 0xffffu) >= thresh; }
+__device__ __forceinline__ bool drop_keep_hi(uint32_t bits, uint32_t thresh) { return (bits >> 16) >= thresh; }
+static inline Dropout make_dropout(const uint32_t *seed, uint32_t site, float p) {
+    Dropout d{seed, site, 0u, 1.0f};
+    if (seed && p > 0.0f) {
+        uint32_t t = (uint32_t)(p * 65536.0f + 0.5f);
+        if (t > 65535u) t = 65535u;
+        d.thresh = t;
+        d.scale = 65536.0f / (float)(65536u - t);
+    } else {
+        d.seed = nullptr;
+    }
+    return d;
+}
+
 }  // namespace kbner

@@ -12,11 +12,12 @@ constexpr int kLnWarps = 4;
 // fp32), bf16 out.  HF BertSelfOutput / BertOutput LayerNorm as called from
 // /root/reference/flair/embeddings.py:3269.  VPL = float4 per lane.
 // ------------------------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, bool FUSED>
 __global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
-                     float eps, int M, uint16_t *__restrict__ y, float *__restrict__ mean_out,
-                     float *__restrict__ rstd_out) {
+layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ bias, const uint16_t *__restrict__ resid,
+                     const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int M,
+                     uint16_t *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                     const Dropout drop) {
     constexpr int H = VPL * 128;
     const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -27,6 +28,35 @@ layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamm
     for (int i = 0; i < VPL; ++i) {
         const uint4 u = ld_nc_v4(xr + i * 32 + lane);
         v[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+    }
+    if (FUSED) {
+        // z = dropout(x + bias) + resid : the Linear's bias, the hidden-state dropout and the residual connection of
+        // BertSelfOutput / BertOutput, taken out of the GEMM epilogue (where the row-per-thread accumulator layout made
+        // the residual an uncoalesced 32-sector-per-request load on the critical path; profiles/r01/gemm_attnout_ncu.txt)
+        const uint32_t key = drop.thresh ? drop_key(drop) : 0u;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c4 = i * 32 + lane;           // float4 index inside the row
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+                v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+            }
+            if (drop.thresh) {
+                const uint32_t pair = (uint32_t)row * (H / 2) + (uint32_t)c4 * 2u;
+                const uint32_t b0 = drop_bits(key, pair), b1 = drop_bits(key, pair + 1u);
+                v[i].x = drop_keep_lo(b0, drop.thresh) ? v[i].x * drop.scale : 0.0f;
+                v[i].y = drop_keep_hi(b0, drop.thresh) ? v[i].y * drop.scale : 0.0f;
+                v[i].z = drop_keep_lo(b1, drop.thresh) ? v[i].z * drop.scale : 0.0f;
+                v[i].w = drop_keep_hi(b1, drop.thresh) ? v[i].w * drop.scale : 0.0f;
+            }
+            if (resid) {
+                const uint2 r = __ldg(reinterpret_cast<const uint2 *>(resid + (size_t)row * H) + c4);
+                float r0, r1, r2, r3;
+                unpack_bf16x2(r.x, r0, r1);
+                unpack_bf16x2(r.y, r2, r3);
+                v[i].x += r0; v[i].y += r1; v[i].z += r2; v[i].w += r3;
+            }
+        }
     }
     float sum = 0.0f;
 #pragma unroll
@@ -196,17 +226,32 @@ using namespace kbner;
                  return KBNER_EUNSUPPORTED;                                                     \
     }
 
-extern "C" int kbner_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int M, int H,
-                                   uint16_t *y, float *mean, float *rstd, void *stream) {
+extern "C" int kbner_add_layernorm_fwd(const float *x, const float *bias, const uint16_t *resid, const float *gamma,
+                                       const float *beta, float eps, int M, int H, uint16_t *y, float *mean, float *rstd,
+                                       const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream) {
     KBNER_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 128 == 0, "layernorm_fwd: H=%d must be a multiple of 128", H);
     KBNER_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
+    KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "layernorm_fwd: dropout probability %f", (double)drop_p);
+    KBNER_CHECK_ARG((uint64_t)M * (uint64_t)(H / 2) < (1ull << 32), "layernorm_fwd: M*H/2 exceeds the 32-bit dropout counter");
     if (M == 0) return KBNER_OK;
     const int blocks = (M + kLnWarps - 1) / kLnWarps;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_VPL(H, (layernorm_fwd_kernel<VPL><<<blocks, kLnWarps * 32, 0, st>>>(x, gamma, beta, eps, M, y, mean, rstd)));
+    const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
+    if (bias || resid || drop.thresh) {
+        DISPATCH_VPL(H, (layernorm_fwd_kernel<VPL, true><<<blocks, kLnWarps * 32, 0, st>>>(x, bias, resid, gamma, beta, eps, M,
+                                                                                         y, mean, rstd, drop)));
+    } else {
+        DISPATCH_VPL(H, (layernorm_fwd_kernel<VPL, false><<<blocks, kLnWarps * 32, 0, st>>>(x, bias, resid, gamma, beta, eps,
+                                                                                          M, y, mean, rstd, drop)));
+    }
     KBNER_CHECK_LAUNCH("layernorm_fwd");
     return KBNER_OK;
+}
+
+extern "C" int kbner_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int M, int H,
+                                   uint16_t *y, float *mean, float *rstd, void *stream) {
+    return kbner_add_layernorm_fwd(x, nullptr, nullptr, gamma, beta, eps, M, H, y, mean, rstd, nullptr, 0u, 0.0f, stream);
 }
 
 extern "C" int kbner_embed_ln_fwd(const int32_t *ids, const float *word_emb, const float *pos_emb,

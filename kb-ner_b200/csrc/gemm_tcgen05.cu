@@ -60,8 +60,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t cta) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
     return r;
 }
+// Remote arrive WITHOUT release semantics: what it orders is the drained accumulator, and those tcgen05.ld's have
+// already completed (tcgen05.wait::ld) and are fenced by tcgen05.fence::before_thread_sync.  The default .release form
+// compiles to MEMBAR.ALL.CTA + ERRBAR, which waited for every outstanding global load of the epilogue warp
+// (8 % of the stall samples in profiles/r01/gemm_attnout_ncu.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-SM TMA load: data lands in THIS CTA's smem, transaction bytes complete on the barrier at `bar_cluster_addr`
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr,
@@ -308,6 +312,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int i = 0; i < 16; ++i)
                     raux[i] = (row_ok && colbase + i * 8 < N) ? ld_nc_v4(rrow + i * 8) : make_uint4(0, 0, 0, 0);
             }
+            // this warp's 128 bias values: one coalesced float4 per lane, redistributed with shuffles in the chunk loop
+            // (per-chunk __ldg's exposed an L2 round trip four times per tile)
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_bias && colbase + lane * 4 < N) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + colbase) + lane);
             ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
 #pragma unroll
@@ -319,13 +327,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint32_t r[32];
                     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c * CW + h2 * 32;
                     ptx::tmem_ld_32x32b_x32(taddr, r);
+                    // bias of column (c*CW + h2*32 + i) sits in lane (that offset / 4), component (offset % 4)
                     float bv[32];
-                    if (has_bias) {                    // bias loads overlap the TMEM load
+                    if (has_bias) {                    // warp-uniform
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (col0 + h2 * 32 + i < N) t = __ldg(reinterpret_cast<const float4 *>(g.bias + col0 + h2 * 32 + i));
-                            bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+                        for (int i = 0; i < 32; ++i) {
+                            const int off = c * CW + h2 * 32 + i;
+                            const float comp = (off & 3) == 0 ? bias4.x : (off & 3) == 1 ? bias4.y : (off & 3) == 2 ? bias4.z : bias4.w;
+                            bv[i] = __shfl_sync(0xffffffffu, comp, off >> 2);
                         }
                     } else {
 #pragma unroll

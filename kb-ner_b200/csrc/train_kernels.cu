@@ -14,12 +14,13 @@ namespace kbner {
 // One warp per row, rows strided over a persistent grid; per-lane partial dgamma/dbeta in registers, reduced
 // through shared memory, one atomic per column per block.
 // ------------------------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, bool FUSED>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout, const float *__restrict__ gamma,
+layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias, const uint16_t *__restrict__ resid,
+                     const float *__restrict__ dout, const uint16_t *__restrict__ dres, const float *__restrict__ gamma,
                      const float *__restrict__ mean, const float *__restrict__ rstd, int M,
-                     uint16_t *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta,
-                     float *__restrict__ dxsum) {
+                     uint16_t *__restrict__ dx, uint16_t *__restrict__ dxm, float *__restrict__ dgamma,
+                     float *__restrict__ dbeta, float *__restrict__ dxsum, const Dropout drop) {
     constexpr int H = VPL * 128;
     __shared__ float s_red[3][H];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -32,17 +33,52 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout
     float4 ag[VPL], ab[VPL], ax[VPL];      // per-lane partial column sums: dgamma, dbeta, sum of dx (bias gradient)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ax[i] = make_float4(0, 0, 0, 0); }
+    const uint32_t key = (FUSED && drop.thresh) ? drop_key(drop) : 0u;
     for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
         const float mu = mean[row], rs = rstd[row];
         const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * H);
         const float4 *dr = reinterpret_cast<const float4 *>(dout + (size_t)row * H);
         float4 xh[VPL], g[VPL];
+        uint32_t keep[VPL];                 // 4 keep bits per float4 (FUSED + dropout only)
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            const uint4 ux = ld_nc_v4(xr + i * 32 + lane), ud = ld_nc_v4(dr + i * 32 + lane);
-            const float4 xv = make_float4(__uint_as_float(ux.x), __uint_as_float(ux.y), __uint_as_float(ux.z), __uint_as_float(ux.w));
-            const float4 dv = make_float4(__uint_as_float(ud.x), __uint_as_float(ud.y), __uint_as_float(ud.z), __uint_as_float(ud.w));
+            const int c4 = i * 32 + lane;
+            const uint4 ux = ld_nc_v4(xr + c4), ud = ld_nc_v4(dr + c4);
+            float4 xv = make_float4(__uint_as_float(ux.x), __uint_as_float(ux.y), __uint_as_float(ux.z), __uint_as_float(ux.w));
+            float4 dv = make_float4(__uint_as_float(ud.x), __uint_as_float(ud.y), __uint_as_float(ud.z), __uint_as_float(ud.w));
+            keep[i] = 0xfu;
+            if (FUSED) {
+                // the LayerNorm input is recomputed exactly as the forward built it: z = dropout(x + bias) + resid
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+                    xv.x += b.x; xv.y += b.y; xv.z += b.z; xv.w += b.w;
+                }
+                if (drop.thresh) {
+                    const uint32_t pair = (uint32_t)row * (H / 2) + (uint32_t)c4 * 2u;
+                    const uint32_t b0 = drop_bits(key, pair), b1 = drop_bits(key, pair + 1u);
+                    keep[i] = (drop_keep_lo(b0, drop.thresh) ? 1u : 0u) | (drop_keep_hi(b0, drop.thresh) ? 2u : 0u) |
+                              (drop_keep_lo(b1, drop.thresh) ? 4u : 0u) | (drop_keep_hi(b1, drop.thresh) ? 8u : 0u);
+                    xv.x = (keep[i] & 1u) ? xv.x * drop.scale : 0.0f;
+                    xv.y = (keep[i] & 2u) ? xv.y * drop.scale : 0.0f;
+                    xv.z = (keep[i] & 4u) ? xv.z * drop.scale : 0.0f;
+                    xv.w = (keep[i] & 8u) ? xv.w * drop.scale : 0.0f;
+                }
+                if (resid) {
+                    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(resid + (size_t)row * H) + c4);
+                    float r0, r1, r2, r3;
+                    unpack_bf16x2(r.x, r0, r1);
+                    unpack_bf16x2(r.y, r2, r3);
+                    xv.x += r0; xv.y += r1; xv.z += r2; xv.w += r3;
+                }
+                if (dres) {                 // gradient arriving over the residual connection (bf16) joins the GEMM's fp32 dgrad
+                    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(dres + (size_t)row * H) + c4);
+                    float r0, r1, r2, r3;
+                    unpack_bf16x2(r.x, r0, r1);
+                    unpack_bf16x2(r.y, r2, r3);
+                    dv.x += r0; dv.y += r1; dv.z += r2; dv.w += r3;
+                }
+            }
             xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
             g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
             s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -54,13 +90,23 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dout
         uint16_t *o = dx + (size_t)row * H;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            const float d0 = rs * (g[i].x - m1 - xh[i].x * m2), d1 = rs * (g[i].y - m1 - xh[i].y * m2);
-            const float d2 = rs * (g[i].z - m1 - xh[i].z * m2), d3 = rs * (g[i].w - m1 - xh[i].w * m2);
-            ax[i].x += d0; ax[i].y += d1; ax[i].z += d2; ax[i].w += d3;
+            float d0 = rs * (g[i].x - m1 - xh[i].x * m2), d1 = rs * (g[i].y - m1 - xh[i].y * m2);
+            float d2 = rs * (g[i].z - m1 - xh[i].z * m2), d3 = rs * (g[i].w - m1 - xh[i].w * m2);
             uint2 p;
             p.x = pack_bf16x2(d0, d1);
             p.y = pack_bf16x2(d2, d3);
-            *reinterpret_cast<uint2 *>(o + (i * 32 + lane) * 4) = p;
+            *reinterpret_cast<uint2 *>(o + (i * 32 + lane) * 4) = p;           // grad w.r.t. z: the residual path
+            if (FUSED && drop.thresh) {
+                // grad w.r.t. the Linear's output: through the dropout mask (what dgrad / wgrad / the bias gradient consume)
+                d0 = (keep[i] & 1u) ? d0 * drop.scale : 0.0f;
+                d1 = (keep[i] & 2u) ? d1 * drop.scale : 0.0f;
+                d2 = (keep[i] & 4u) ? d2 * drop.scale : 0.0f;
+                d3 = (keep[i] & 8u) ? d3 * drop.scale : 0.0f;
+                p.x = pack_bf16x2(d0, d1);
+                p.y = pack_bf16x2(d2, d3);
+                *reinterpret_cast<uint2 *>(dxm + (size_t)row * H + (i * 32 + lane) * 4) = p;
+            }
+            ax[i].x += d0; ax[i].y += d1; ax[i].z += d2; ax[i].w += d3;
         }
     }
 #pragma unroll
@@ -327,6 +373,49 @@ __global__ void clip_coef_kernel(const float *__restrict__ sumsq, float pre, flo
     *coef = fminf(1.0f, max_norm / (nrm + 1e-6f));
 }
 
+// ------------------------------------------------------------------------------------------
+// Element-wise dropout (in place) with the counter-hash mask of common.cuh: the embedding dropout of
+// XLMRobertaEmbeddings (applied to the bf16 LayerNorm output in the forward, to the fp32 gradient in the backward).
+// The per-layer dropouts are fused into the LayerNorm and attention kernels instead.
+// ------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void __launch_bounds__(256)
+dropout_apply_kernel(void *__restrict__ x, size_t n_pairs, const Dropout drop) {
+    const uint32_t key = drop_key(drop);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n_pairs; q += stride) {   // 4 pairs = 8 elements
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t b = drop_bits(key, (uint32_t)(q * 4 + j));
+            keep |= (drop_keep_lo(b, drop.thresh) ? 1u : 0u) << (2 * j);
+            keep |= (drop_keep_hi(b, drop.thresh) ? 1u : 0u) << (2 * j + 1);
+        }
+        if (F32) {
+            float4 *p = reinterpret_cast<float4 *>(x) + q * 2;
+            float4 a = p[0], b = p[1];
+            a.x = (keep & 1u) ? a.x * drop.scale : 0.0f;   a.y = (keep & 2u) ? a.y * drop.scale : 0.0f;
+            a.z = (keep & 4u) ? a.z * drop.scale : 0.0f;   a.w = (keep & 8u) ? a.w * drop.scale : 0.0f;
+            b.x = (keep & 16u) ? b.x * drop.scale : 0.0f;  b.y = (keep & 32u) ? b.y * drop.scale : 0.0f;
+            b.z = (keep & 64u) ? b.z * drop.scale : 0.0f;  b.w = (keep & 128u) ? b.w * drop.scale : 0.0f;
+            p[0] = a; p[1] = b;
+        } else {
+            uint4 *p = reinterpret_cast<uint4 *>(x) + q;
+            uint4 u = *p;
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a, b;
+                unpack_bf16x2(w[j], a, b);
+                a = ((keep >> (2 * j)) & 1u) ? a * drop.scale : 0.0f;
+                b = ((keep >> (2 * j + 1)) & 1u) ? b * drop.scale : 0.0f;
+                w[j] = pack_bf16x2(a, b);
+            }
+            *p = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 }  // namespace kbner
 
 using namespace kbner;
@@ -341,18 +430,37 @@ using namespace kbner;
                  return KBNER_EUNSUPPORTED;                                                       \
     }
 
-extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const float *gamma, const float *mean,
-                                   const float *rstd, int M, int H, uint16_t *dx, float *dgamma, float *dbeta,
-                                   float *dxsum, void *stream) {
+extern "C" int kbner_add_layernorm_bwd(const float *x, const float *bias, const uint16_t *resid, const float *dout,
+                                       const uint16_t *dres, const float *gamma, const float *mean, const float *rstd,
+                                       int M, int H, uint16_t *dx, uint16_t *dx_masked, float *dgamma, float *dbeta,
+                                       float *dxsum, const uint32_t *drop_seed, uint32_t drop_site, float drop_p,
+                                       void *stream) {
     KBNER_CHECK_ARG(x && dout && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H % 128 == 0, "layernorm_bwd: bad shape");
+    KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "layernorm_bwd: dropout probability %f", (double)drop_p);
+    const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
+    KBNER_CHECK_ARG(!drop.thresh || dx_masked, "layernorm_bwd: dropout needs the dx_masked output");
+    KBNER_CHECK_ARG((uint64_t)M * (uint64_t)(H / 2) < (1ull << 32), "layernorm_bwd: M*H/2 exceeds the 32-bit dropout counter");
     if (M == 0) return KBNER_OK;
     int blocks = (M + 7) / 8;
     if (blocks > kNumSMs) blocks = kNumSMs;       // one block per SM: the per-block column partials end in 3*H global atomics
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL><<<blocks, 256, 0, st>>>(x, dout, gamma, mean, rstd, M, dx, dgamma, dbeta, dxsum)));
+    if (bias || resid || dres || drop.thresh) {
+        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL, true><<<blocks, 256, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
+                                                                                  dx, dx_masked, dgamma, dbeta, dxsum, drop)));
+    } else {
+        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL, false><<<blocks, 256, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
+                                                                                   dx, dx_masked, dgamma, dbeta, dxsum, drop)));
+    }
     KBNER_CHECK_LAUNCH("layernorm_bwd");
     return KBNER_OK;
+}
+
+extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const float *gamma, const float *mean,
+                                   const float *rstd, int M, int H, uint16_t *dx, float *dgamma, float *dbeta,
+                                   float *dxsum, void *stream) {
+    return kbner_add_layernorm_bwd(x, nullptr, nullptr, dout, nullptr, gamma, mean, rstd, M, H, dx, nullptr, dgamma, dbeta,
+                                   dxsum, nullptr, 0u, 0.0f, stream);
 }
 
 extern "C" int kbner_colsum_bf16(const uint16_t *dY, int M, int N, float *db, void *stream) {
@@ -450,5 +558,23 @@ extern "C" int kbner_adamw_step(float *p, const float *g, float *m, float *v, si
     adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_size,
                                                                 gscale_dev, gscale_host);
     KBNER_CHECK_LAUNCH("adamw_step");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_dropout_apply(void *x, int is_f32, int M, int H, const uint32_t *drop_seed, uint32_t drop_site,
+                                   float drop_p, void *stream) {
+    KBNER_CHECK_ARG(x && drop_seed, "dropout_apply: null pointer");
+    KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 8 == 0, "dropout_apply: H=%d must be a multiple of 8", H);
+    KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "dropout_apply: dropout probability %f", (double)drop_p);
+    KBNER_CHECK_ARG((uint64_t)M * (uint64_t)(H / 2) < (1ull << 32), "dropout_apply: M*H/2 exceeds the 32-bit dropout counter");
+    const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
+    if (M == 0 || !drop.thresh) return KBNER_OK;
+    const size_t n_pairs = (size_t)M * H / 2;
+    size_t blocks = (n_pairs / 4 + 255) / 256;
+    if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_f32) dropout_apply_kernel<true><<<(int)blocks, 256, 0, st>>>(x, n_pairs, drop);
+    else dropout_apply_kernel<false><<<(int)blocks, 256, 0, st>>>(x, n_pairs, drop);
+    KBNER_CHECK_LAUNCH("dropout_apply");
     return KBNER_OK;
 }

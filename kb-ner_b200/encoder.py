@@ -42,7 +42,8 @@ def _ln(h):
 class EncoderConfig:
     def __init__(self, vocab_size=250002, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
                  intermediate_size=4096, max_position_embeddings=514, layer_norm_eps=1e-5, pad_token_id=1,
-                 type_vocab_size=1, name="xlm-roberta-large", **_unused):
+                 type_vocab_size=1, name="xlm-roberta-large", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                 **_unused):
         self.vocab_size = vocab_size
         self.hidden_size = hidden_size
         self.num_hidden_layers = num_hidden_layers
@@ -54,6 +55,9 @@ class EncoderConfig:
         self.type_vocab_size = type_vocab_size
         self.output_hidden_states = True
         self.name = name
+        # transformers XLMRobertaConfig defaults; active only in the fine-tuning forward of a module in train() mode
+        self.hidden_dropout_prob = hidden_dropout_prob
+        self.attention_probs_dropout_prob = attention_probs_dropout_prob
 
     @classmethod
     def xlmr_large(cls, **kw):
@@ -111,7 +115,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
     # ---- checkpointing: only parameters travel; graphs, workspaces, compute copies and the arena are rebuilt ----
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ("_compute", "arena"):
+        for k in ("_compute", "arena", "_drop_seed", "_drop_seed_buf"):
             state[k] = None
         for k in ("_ws", "_graphs", "_tgraphs"):
             state[k] = {}
@@ -177,11 +181,12 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         for w in self._compute:
             ops.gemm_bf16_tn(x, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BIAS, out=ws["qkv"])
             ops.attention_fwd(ws["qkv"], key_len, R, S, c.num_attention_heads, out=ws["ctx"])
-            ops.gemm_bf16_tn(ws["ctx"], w["wo"], w["bo"], residual=x, epilogue=ops.EPI_BIAS_RESID_F32, out=ws["y"])
-            ops.layernorm_fwd(ws["y"], w["g1"], w["b1"], c.layer_norm_eps, out=xn)
+            # dense bias + residual are added by the LayerNorm pass (coalesced), not by the GEMM epilogue
+            ops.gemm_bf16_tn(ws["ctx"], w["wo"], None, epilogue=ops.EPI_NONE_F32, out=ws["y"])
+            ops.layernorm_fwd(ws["y"], w["g1"], w["b1"], c.layer_norm_eps, out=xn, bias=w["bo"], resid=x)
             ops.gemm_bf16_tn(xn, w["w1"], w["bi"], epilogue=ops.EPI_BIAS_GELU, out=ws["h"])
-            ops.gemm_bf16_tn(ws["h"], w["w2"], w["b2"], residual=xn, epilogue=ops.EPI_BIAS_RESID_F32, out=ws["y"])
-            ops.layernorm_fwd(ws["y"], w["g2"], w["bb2"], c.layer_norm_eps, out=x)
+            ops.gemm_bf16_tn(ws["h"], w["w2"], None, epilogue=ops.EPI_NONE_F32, out=ws["y"])
+            ops.layernorm_fwd(ws["y"], w["g2"], w["bb2"], c.layer_norm_eps, out=x, bias=w["b2"], resid=xn)
         return x
 
     @torch.no_grad()
@@ -346,6 +351,17 @@ def _sync_compute_weights_arena(self):
     self._tgraphs = {}
 
 
+def _dropout_sites(self, li):
+    """(attention-probability, attention-output, FFN-output) dropout descriptors of layer li, or Nones when off."""
+    seed = getattr(self, "_drop_seed", None)
+    if seed is None:
+        return None, None, None
+    c = self.config
+    pa, ph = c.attention_probs_dropout_prob, c.hidden_dropout_prob
+    return ((seed, 4 * li + 0, pa) if pa > 0 else None, (seed, 4 * li + 1, ph) if ph > 0 else None,
+            (seed, 4 * li + 2, ph) if ph > 0 else None)
+
+
 @torch.no_grad()
 def _forward_train_eager(self, ids, key_len):
     c = self.config
@@ -356,16 +372,22 @@ def _forward_train_eager(self, ids, key_len):
     e = self.embeddings
     x = ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight[0],
                          e.LayerNorm.weight, e.LayerNorm.bias, c.layer_norm_eps, c.pad_token_id)
-    saved = {"ids": ids, "key_len": key_len, "R": R, "S": S, "layers": []}
-    for w in self._compute:
+    drop_on = getattr(self, "_drop_seed", None) is not None
+    if drop_on and c.hidden_dropout_prob > 0:
+        ops.dropout_apply(x, (self._drop_seed, 4 * len(self._compute), c.hidden_dropout_prob))
+    saved = {"ids": ids, "key_len": key_len, "R": R, "S": S, "layers": [], "dropout": drop_on}
+    for li, w in enumerate(self._compute):
+        d_attn, d_h1, d_h2 = _dropout_sites(self, li)
         qkv = ops.gemm_bf16(x, w["wqkv"], M, 3 * H, H, ops.EPI_BIAS, bias=w["bqkv"])
-        ctx, lse = ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, want_lse=True)
-        y1 = ops.gemm_bf16(ctx, w["wo"], M, H, H, ops.EPI_BIAS_RESID_F32, bias=w["bo"], aux=x)
-        x1, mean1, rstd1 = ops.layernorm_fwd(y1, w["g1"], w["b1"], c.layer_norm_eps, save_stats=True)
+        ctx, lse = ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, want_lse=True, drop=d_attn)
+        y1 = ops.gemm_bf16(ctx, w["wo"], M, H, H, ops.EPI_NONE_F32)
+        x1, mean1, rstd1 = ops.layernorm_fwd(y1, w["g1"], w["b1"], c.layer_norm_eps, save_stats=True, bias=w["bo"], resid=x,
+                                             drop=d_h1)
         hpre = torch.empty((M, F), dtype=bf, device=dev)
         h = ops.gemm_bf16(x1, w["w1"], M, F, H, ops.EPI_BIAS_GELU, bias=w["bi"], aux_out=hpre)
-        y2 = ops.gemm_bf16(h, w["w2"], M, H, F, ops.EPI_BIAS_RESID_F32, bias=w["b2"], aux=x1)
-        xo, mean2, rstd2 = ops.layernorm_fwd(y2, w["g2"], w["bb2"], c.layer_norm_eps, save_stats=True)
+        y2 = ops.gemm_bf16(h, w["w2"], M, H, F, ops.EPI_NONE_F32)
+        xo, mean2, rstd2 = ops.layernorm_fwd(y2, w["g2"], w["bb2"], c.layer_norm_eps, save_stats=True, bias=w["b2"], resid=x1,
+                                             drop=d_h2)
         saved["layers"].append((x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2))
         x = xo
     return x, saved
@@ -380,10 +402,22 @@ def _forward_train(self, ids, key_len):
     if self._compute is None or not getattr(self, "_compute_static", False):
         self._compute = None
         _sync_compute_weights_arena(self)
+    # dropout (transformers: hidden 0.1, attention probabilities 0.1) is active in train() mode, like torch.nn.Dropout.
+    # The two seed words live in a static device buffer (the captured graphs read it) and are refreshed from torch's CUDA
+    # generator before every forward, so torch.manual_seed() makes a run reproducible; the backward reuses them.
+    c = self.config
+    drop_on = bool(self.training and (c.hidden_dropout_prob > 0 or c.attention_probs_dropout_prob > 0))
+    if drop_on:
+        if getattr(self, "_drop_seed_buf", None) is None or self._drop_seed_buf.device != ids.device:
+            self._drop_seed_buf = torch.zeros(2, dtype=torch.int32, device=ids.device)
+        self._drop_seed_buf.copy_(torch.randint(0, 2 ** 31 - 1, (2,), dtype=torch.int32, device=ids.device))
+        self._drop_seed = self._drop_seed_buf
+    else:
+        self._drop_seed = None
     if not self._use_graphs:
         return _forward_train_eager(self, ids, key_len)
     R, S = ids.shape
-    key = (R, S, str(ids.device))
+    key = (R, S, str(ids.device), drop_on)
     st = self._tgraphs.get(key)
     if st is None:
         self._tgraphs[key] = {"fwd": None, "bwd": None}
@@ -418,28 +452,40 @@ def _backward_eager(self, saved, dout):
     key_len = saved["key_len"]
     dev = dout.device
     ws = (torch.empty((R, heads, S), dtype=torch.float32, device=dev), torch.empty((M, H), dtype=torch.float32, device=dev))
+    # `dout` (fp32) + `dres` (bf16, or None) is the gradient w.r.t. the current layer's output: the dgrad GEMMs keep a plain
+    # fp32 epilogue and the gradient that arrives over the residual connection is added by the LayerNorm backward pass
+    dres = None
     for li in range(len(self.encoder.layer) - 1, -1, -1):
         lyr, w = self.encoder.layer[li], self._compute[li]
         a = lyr.attention
+        d_attn, d_h1, d_h2 = _dropout_sites(self, li) if saved.get("dropout") else (None, None, None)
         x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2 = saved["layers"][li]
         # ---- FFN block ------------------------------------------------------------------------------
-        dy2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad,
-                                dxsum=lyr.output.dense.bias.grad)
+        dz2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad,
+                                dxsum=lyr.output.dense.bias.grad, bias=w["b2"], resid=x1, dres=dres, drop=d_h2)
+        dz2, dy2 = dz2 if isinstance(dz2, tuple) else (dz2, dz2)      # (residual path, through the dropout mask)
         ops.gemm_bf16(dy2, h, H, F, M, ops.EPI_ACCUM_F32, out=lyr.output.dense.weight.grad, a_mn=True, b_mn=True)
         dhpre = ops.gemm_bf16(dy2, w["w2"], M, F, H, ops.EPI_DGELU_BF16, aux=hpre, b_mn=True)
         ops.colsum_bf16(dhpre, lyr.intermediate.dense.bias.grad)
         ops.gemm_bf16(dhpre, x1, F, H, M, ops.EPI_ACCUM_F32, out=lyr.intermediate.dense.weight.grad, a_mn=True, b_mn=True)
-        dx1 = ops.gemm_bf16(dhpre, w["w1"], M, H, F, ops.EPI_BIAS_RESID_F32, aux=dy2, b_mn=True)      # + residual path
+        dx1 = ops.gemm_bf16(dhpre, w["w1"], M, H, F, ops.EPI_NONE_F32, b_mn=True)
         # ---- attention block ------------------------------------------------------------------------
-        dy1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad,
-                                dxsum=a.output.dense.bias.grad)
+        dz1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad,
+                                dxsum=a.output.dense.bias.grad, bias=w["bo"], resid=x, dres=dz2, drop=d_h1)
+        dz1, dy1 = dz1 if isinstance(dz1, tuple) else (dz1, dz1)
         ops.gemm_bf16(dy1, ctx, H, H, M, ops.EPI_ACCUM_F32, out=a.output.dense.weight.grad, a_mn=True, b_mn=True)
         dctx = ops.gemm_bf16(dy1, w["wo"], M, H, H, ops.EPI_BIAS, b_mn=True)
-        dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws)
+        dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws, drop=d_attn)
         ops.colsum_bf16(dqkv, ar.view(a.self.query.bias, (3 * H,), grad=True))
         ops.gemm_bf16(dqkv, x, 3 * H, H, M, ops.EPI_ACCUM_F32, out=ar.view(a.self.query.weight, (3 * H, H), grad=True),
                       a_mn=True, b_mn=True)
-        dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_BIAS_RESID_F32, aux=dy1, b_mn=True)
+        if li > 0:
+            dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_NONE_F32, b_mn=True)
+            dres = dz1
+        else:      # the embedding backward takes one fp32 tensor: let this last dgrad add the residual gradient itself
+            dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_BIAS_RESID_F32, aux=dz1, b_mn=True)
+    if saved.get("dropout") and c.hidden_dropout_prob > 0:
+        ops.dropout_apply(dout, (self._drop_seed, 4 * len(self._compute), c.hidden_dropout_prob))
     e = self.embeddings
     ops.embed_ln_bwd(saved["ids"], e.word_embeddings.weight.data, e.position_embeddings.weight.data,
                      e.token_type_embeddings.weight.data[0], e.LayerNorm.weight.data, c.layer_norm_eps, c.pad_token_id,

@@ -108,10 +108,24 @@ def embed_ln_fwd(ids, word_emb, pos_emb, type_emb, gamma, beta, eps, pad_id, out
     return out
 
 
-def layernorm_fwd(x, gamma, beta, eps, out=None, save_stats=False):
+def _drop_args(drop):
+    """drop = None | (seed int32[2] cuda tensor, site int, p float) -> (seed ptr, site, p) of the C ABI."""
+    if drop is None:
+        return None, 0, 0.0
+    seed, site, p = drop
+    _chk(seed, torch.int32, "drop_seed", 1)
+    if seed.numel() != 2:
+        raise _lib.KbnerError("drop_seed must hold 2 words")
+    return _ptr(seed), int(site), float(p)
+
+
+def layernorm_fwd(x, gamma, beta, eps, out=None, save_stats=False, bias=None, resid=None, drop=None):
+    """y = LayerNorm(dropout(x + bias) + resid) * gamma + beta (bias / resid / drop optional)."""
     _chk(x, torch.float32, "x", 2)
     _chk(gamma, torch.float32, "gamma", 1)
     _chk(beta, torch.float32, "beta", 1)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(resid, torch.bfloat16, "resid", 2)
     M, H = x.shape
     if out is None:
         out = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
@@ -119,9 +133,22 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, save_stats=False):
     if save_stats:
         mean = torch.empty((M,), dtype=torch.float32, device=x.device)
         rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().kbner_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), M, H, _ptr(out),
-                                               _ptr(mean), _ptr(rstd), _stream()), "layernorm_fwd")
+    sp, site, p = _drop_args(drop)
+    _lib.check(_lib.load().kbner_add_layernorm_fwd(_ptr(x), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta), float(eps), M, H,
+                                                   _ptr(out), _ptr(mean), _ptr(rstd), sp, site, p, _stream()),
+               "layernorm_fwd")
     return (out, mean, rstd) if save_stats else out
+
+
+def dropout_apply(x, drop):
+    """In-place dropout of a [M,H] bf16 / fp32 tensor with the counter-hash mask of site drop[1]."""
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.KbnerError("dropout_apply: bf16 or fp32 expected")
+    _chk(x, x.dtype, "x", 2)
+    sp, site, p = _drop_args(drop)
+    _lib.check(_lib.load().kbner_dropout_apply(_ptr(x), 1 if x.dtype == torch.float32 else 0, x.shape[0], x.shape[1], sp, site, p,
+                                               _stream()), "dropout_apply")
+    return x
 
 
 def gather_tagproj_fwd(hidden, row_of, first_idx, W, bias, S, drop_keep=None):
@@ -160,7 +187,7 @@ def gemm_bf16_tn(A, B, bias=None, residual=None, epilogue=EPI_BIAS, out=None):
     return out
 
 
-def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False):
+def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None):
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(key_len, torch.int32, "key_len", 1)
     H = heads * 64
@@ -169,25 +196,36 @@ def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False):
     if out is None:
         out = torch.empty((R * S, H), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device) if want_lse else None
-    _lib.check(_lib.load().kbner_attention_fwd(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), _ptr(lse),
-                                               _stream()), "attention_fwd")
+    sp, site, p = _drop_args(drop)
+    _lib.check(_lib.load().kbner_attention_fwd_dropout(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), _ptr(lse), sp, site, p,
+                                                       _stream()), "attention_fwd")
     return (out, lse) if want_lse else out
 
 
 # ---- fine-tuning step -----------------------------------------------------------------------------
-def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None, dxsum=None):
-    """dx (bf16 [M,H]) of LayerNorm; dgamma / dbeta (fp32 [H]) are accumulated into; dxsum (optional) += colsum(dx)."""
+def layernorm_bwd(x, dout, gamma, mean, rstd, dgamma, dbeta, out=None, dxsum=None, bias=None, resid=None, dres=None,
+                  drop=None, out_masked=None):
+    """Backward of layernorm_fwd.  Returns dx (bf16 [M,H], grad w.r.t. the LayerNorm input z = dropout(x+bias)+resid); with
+    dropout returns (dx, dx_masked) where dx_masked is the gradient of x (through the mask).  dgamma / dbeta (fp32 [H]) are
+    accumulated into; dxsum (optional) += colsum(dx_masked or dx) = the bias gradient; dres (bf16) is added to dout."""
     _chk(x, torch.float32, "x", 2)
     _chk(dout, torch.float32, "dout", 2)
     for n, t in (("gamma", gamma), ("mean", mean), ("rstd", rstd), ("dgamma", dgamma), ("dbeta", dbeta)):
         _chk(t, torch.float32, n, 1)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(resid, torch.bfloat16, "resid", 2)
+    _chk(dres, torch.bfloat16, "dres", 2)
     M, H = x.shape
     if out is None:
         out = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
     _chk(dxsum, torch.float32, "dxsum", 1)
-    _lib.check(_lib.load().kbner_layernorm_bwd(_ptr(x), _ptr(dout), _ptr(gamma), _ptr(mean), _ptr(rstd), M, H, _ptr(out),
-                                               _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _stream()), "layernorm_bwd")
-    return out
+    sp, site, p = _drop_args(drop)
+    if sp is not None and p > 0.0 and out_masked is None:
+        out_masked = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().kbner_add_layernorm_bwd(_ptr(x), _ptr(bias), _ptr(resid), _ptr(dout), _ptr(dres), _ptr(gamma),
+                                                   _ptr(mean), _ptr(rstd), M, H, _ptr(out), _ptr(out_masked), _ptr(dgamma),
+                                                   _ptr(dbeta), _ptr(dxsum), sp, site, p, _stream()), "layernorm_bwd")
+    return (out, out_masked) if out_masked is not None else out
 
 
 def colsum_bf16(dY, db):
@@ -273,7 +311,7 @@ def gemm_bf16(A, B, M, N, K, epilogue, bias=None, aux=None, aux_out=None, out=No
     return out
 
 
-def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None):
+def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None, drop=None):
     """dQ | dK | dV ([R*S, 3H] bf16) of attention_fwd.  workspace = (d_scratch [R,heads,S] f32, dq_acc [R*S,H] f32)."""
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(out, torch.bfloat16, "out", 2)
@@ -286,7 +324,8 @@ def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspa
     if workspace is None:
         workspace = (torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device),
                      torch.empty((R * S, H), dtype=torch.float32, device=qkv.device))
-    _lib.check(_lib.load().kbner_attention_bwd(_ptr(qkv), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(key_len), R, S, heads,
-                                               _ptr(workspace[0]), _ptr(workspace[1]), _ptr(dqkv), _stream()),
-               "attention_bwd")
+    sp, site, p = _drop_args(drop)
+    _lib.check(_lib.load().kbner_attention_bwd_dropout(_ptr(qkv), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(key_len), R, S, heads,
+                                                       _ptr(workspace[0]), _ptr(workspace[1]), _ptr(dqkv), sp, site, p,
+                                                       _stream()), "attention_bwd")
     return dqkv

@@ -55,8 +55,14 @@ def position_ids(ids, pad_id=1):
     return torch.cumsum(mask, dim=1) * mask + pad_id
 
 
-def encoder_forward(params, ids, key_len, cfg, all_layers=False):
-    """ids [R,S] int64, key_len [R] -> last hidden state [R,S,H] fp32 (or list of all 1+NL states)."""
+def encoder_forward(params, ids, key_len, cfg, all_layers=False, masks=None):
+    """ids [R,S] int64, key_len [R] -> last hidden state [R,S,H] fp32 (or list of all 1+NL states).
+    masks (training-mode dropout, transformers modeling_bert.py: BertEmbeddings.dropout, BertSelfAttention.dropout,
+    BertSelfOutput.dropout, BertOutput.dropout): optional dict of multiplicative masks (0 or 1/(1-p)) with keys
+    "emb" [R,S,H], ("attn", i) [R,heads,S,S], ("attn_out", i) [R,S,H], ("ffn_out", i) [R,S,H]; torch.nn.Dropout draws
+    them from torch's generator, the tests feed the masks the CUDA path generated."""
+    masks = masks or {}
+    mk = lambda t, key: t * masks[key] if key in masks else t
     H, heads, NL, eps = cfg["hidden"], cfg["heads"], cfg["layers"], cfg.get("eps", 1e-5)
     pad = cfg.get("pad_id", 1)
     R, S = ids.shape
@@ -64,7 +70,7 @@ def encoder_forward(params, ids, key_len, cfg, all_layers=False):
     x = (params["embeddings.word_embeddings.weight"][ids]
          + params["embeddings.token_type_embeddings.weight"][0][None, None, :]
          + params["embeddings.position_embeddings.weight"][position_ids(ids, pad)])
-    x = F.layer_norm(x, (H,), params["embeddings.LayerNorm.weight"], params["embeddings.LayerNorm.bias"], eps)
+    x = mk(F.layer_norm(x, (H,), params["embeddings.LayerNorm.weight"], params["embeddings.LayerNorm.bias"], eps), "emb")
     kmask = torch.arange(S, device=ids.device)[None, :] < key_len[:, None].to(ids.device)
     states = [x]
     for i in range(NL):
@@ -75,12 +81,12 @@ def encoder_forward(params, ids, key_len, cfg, all_layers=False):
         v = lin(x, "attention.self.value").view(R, S, heads, d).transpose(1, 2)
         sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
         sc = sc.masked_fill(~kmask[:, None, None, :], torch.finfo(sc.dtype).min)
-        ctx = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(R, S, H)
-        x = F.layer_norm(lin(ctx, "attention.output.dense") + x, (H,),
+        ctx = (mk(torch.softmax(sc, -1), ("attn", i)) @ v).transpose(1, 2).reshape(R, S, H)
+        x = F.layer_norm(mk(lin(ctx, "attention.output.dense"), ("attn_out", i)) + x, (H,),
                          params[pre + "attention.output.LayerNorm.weight"],
                          params[pre + "attention.output.LayerNorm.bias"], eps)
         h = F.gelu(lin(x, "intermediate.dense"))                   # erf GELU ("gelu")
-        x = F.layer_norm(lin(h, "output.dense") + x, (H,), params[pre + "output.LayerNorm.weight"],
+        x = F.layer_norm(mk(lin(h, "output.dense"), ("ffn_out", i)) + x, (H,), params[pre + "output.LayerNorm.weight"],
                          params[pre + "output.LayerNorm.bias"], eps)
         states.append(x)
     return states if all_layers else x

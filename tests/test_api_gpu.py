@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _models(cfg_kw, L_tags, seed=0, remove_x=False):
+def _models(cfg_kw, L_tags, seed=0, remove_x=False, dropout=0.0):
     from kbner_b200.data import Dictionary
     from kbner_b200.embeddings import StackedEmbeddings, SyntheticTokenizer, TransformerWordEmbeddings
     from kbner_b200.encoder import EncoderConfig
@@ -24,7 +24,7 @@ def _models(cfg_kw, L_tags, seed=0, remove_x=False):
                 layers=cfg_kw["num_hidden_layers"], vocab=cfg_kw["vocab_size"], max_pos=cfg_kw["max_position_embeddings"],
                 eps=1e-5, pad_id=1)
     params = E.init_params(ocfg, seed=seed)
-    cfg = EncoderConfig(name="synthetic-xlmr", **cfg_kw)
+    cfg = EncoderConfig(name="synthetic-xlmr", hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout, **cfg_kw)
     emb = TransformerWordEmbeddings(model="synthetic-xlmr", layers="-1", pooling_operation="first", fine_tune=False,
                                     tokenizer=SyntheticTokenizer(cfg.vocab_size), config=cfg, device="cuda")
     emb.model.load_hf_state_dict(params)
@@ -239,6 +239,106 @@ def test_finetune_gradients_vs_oracle_autograd():
     bad = {k: v for k, v in worst.items() if v > 6e-2}
     print("finetune grad rel-L2: max %.3e over %d tensors" % (max(worst.values()), len(worst)))
     assert not bad, bad
+
+
+def _fmix32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13); x *= np.uint32(0xC2B2AE35); x ^= x >> np.uint32(16)
+    return x
+
+
+def host_dropout_mask(seed, site, p, n_elems=None, attn=None):
+    """Host restatement of the counter-hash keep mask of csrc/common.cuh (multiplicative: 0 or 1/(1-p)).
+    Dense sites: element e of the flattened [M,H] tensor.  attn=(R, heads, S): element (r, h, q, k)."""
+    with np.errstate(over="ignore"):
+        s0, s1 = np.uint32(seed[0]), np.uint32(seed[1])
+        key = _fmix32(np.array([s0 + np.uint32(0x9E3779B9) * np.uint32(site + 1)], np.uint32))[0] ^ s1
+        thresh = min(int(p * 65536.0 + 0.5), 65535)
+        if attn is None:
+            e = np.arange(n_elems, dtype=np.uint64)
+            pair, half = (e >> np.uint64(1)).astype(np.uint32), (e & np.uint64(1)).astype(np.uint32)
+        else:
+            R, heads, S = attn
+            r, h, q, k = np.meshgrid(np.arange(R), np.arange(heads), np.arange(S), np.arange(S), indexing="ij")
+            pair = ((((r * heads + h) * 512 + q) * 256) + (k >> 1)).astype(np.uint32)
+            half = (k & 1).astype(np.uint32)
+        bits = _fmix32(pair * np.uint32(0x9E3779B1) + key)
+        val = np.where(half == 1, bits >> np.uint32(16), bits & np.uint32(0xFFFF))
+        keep = val >= thresh
+    return keep.astype(np.float32) * np.float32(65536.0 / (65536 - thresh))
+
+
+def test_finetune_dropout_matches_oracle_with_same_masks():
+    """Training-mode dropout (hidden 0.1 + attention-probability 0.1 + embeddings): the masks the kernels regenerate from
+    (seed, site, element) are rebuilt on the host and handed to the fp32 oracle; forward hidden state and every parameter
+    gradient must then agree as closely as without dropout -- this pins forward/backward mask consistency at all four
+    dropout sites -- and the keep rate must be 1 - p."""
+    import encoder_oracle as E
+    from kbner_b200.data import BatchedData
+    p_drop = 0.1
+    tagger, emb, params, ocfg = _models(SMALL, 13, seed=23, dropout=p_drop)
+    emb.fine_tune, emb.static_embeddings = True, False
+    tagger.train()
+    emb.train()
+    tagger.use_word_dropout = 0.0
+    sents = _sentences(3, 5, 40, seed=35)
+    d = tagger.tag_dictionary
+    rng = np.random.RandomState(3)
+    legal = [i for i in range(len(d)) if i not in (0, tagger.x_idx, tagger.start_idx, tagger.stop_idx)]
+    for s in sents:
+        for tok in s.tokens:
+            tok.add_tag("ner", d.get_item_for_index(legal[rng.randint(len(legal))]))
+    batch = BatchedData(sents)
+    enc = emb.model
+    assert enc.training
+    enc.ensure_arena()
+    enc.arena.zero_grad()
+    torch.manual_seed(77)
+    feats = tagger.forward(batch)
+    feats.retain_grad()
+    loss = tagger._calculate_loss(feats, batch, tagger.mask)
+    loss.backward()
+    d_logits = feats.grad.detach().clone()
+    seed = enc._drop_seed.cpu().numpy().astype(np.uint32)
+    ids, key_len, row_of, first_idx, lengths, S = emb.build_batch(batch)
+    R, H, heads, NL = ids.shape[0], ocfg["hidden"], ocfg["heads"], ocfg["layers"]
+    masks = {"emb": torch.from_numpy(host_dropout_mask(seed, 4 * NL, p_drop, n_elems=R * S * H)).view(R, S, H).cuda()}
+    rates = []
+    for li in range(NL):
+        masks[("attn", li)] = torch.from_numpy(host_dropout_mask(seed, 4 * li, p_drop, attn=(R, heads, S))).cuda()
+        masks[("attn_out", li)] = torch.from_numpy(host_dropout_mask(seed, 4 * li + 1, p_drop, n_elems=R * S * H)).view(R, S, H).cuda()
+        masks[("ffn_out", li)] = torch.from_numpy(host_dropout_mask(seed, 4 * li + 2, p_drop, n_elems=R * S * H)).view(R, S, H).cuda()
+        rates += [float((masks[k] > 0).float().mean()) for k in (("attn", li), ("attn_out", li), ("ffn_out", li))]
+    print("dropout keep rates:", [round(r, 4) for r in rates])
+    assert all(abs(r - (1 - p_drop)) < 5e-3 for r in rates), rates
+    assert len({float(masks[("attn_out", 0)].sum()), float(masks[("ffn_out", 0)].sum()), float(masks[("attn_out", 1)].sum())}) == 3
+    op = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+    hidden = E.encoder_forward(op, ids.long().cuda(), key_len.long().cuda(), ocfg, masks=masks)
+    got_h = batch.features[emb.name].hidden.float().view(R, S, H)
+    rel = []
+    for r in range(R):
+        n = int(key_len[r])
+        rel.append(((got_h[r, :n] - hidden[r, :n].detach()).norm() / hidden[r, :n].norm()).item())
+    print("dropout forward hidden rel-L2 per window:", [round(x, 5) for x in rel])
+    assert max(rel) < 2e-2, rel              # without identical masks this is O(1)
+    flat = hidden.reshape(-1, H)
+    idx = row_of.long()[:, None] * S + first_idx.long().clamp(min=0)
+    x = flat[idx.cuda()] * (first_idx >= 0).float().cuda()[..., None]
+    W, b = tagger.linear.weight.detach().clone().requires_grad_(True), tagger.linear.bias.detach().clone().requires_grad_(True)
+    (x @ W.t() + b).backward(d_logits)
+    worst = {}
+    own = dict(enc.named_parameters())
+    for name, ref in op.items():
+        if ref.grad is None or ref.grad.norm().item() < 1e-8:
+            continue
+        worst[name] = ((own[name].grad - ref.grad).norm() / ref.grad.norm()).item()
+    print("dropout finetune grad rel-L2: max %.3e over %d tensors" % (max(worst.values()), len(worst)))
+    bad = {k: v for k, v in worst.items() if v > 6e-2}
+    assert not bad, bad
+    # a second forward draws a new seed -> different masks
+    batch2 = BatchedData(sents)
+    tagger.forward(batch2)
+    assert not np.array_equal(enc._drop_seed.cpu().numpy().astype(np.uint32), seed)
 
 
 def test_finetune_steps_reduce_loss():

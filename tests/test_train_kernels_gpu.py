@@ -3,6 +3,7 @@ operand-layout variants of the tensor-core GEMM (dgrad / wgrad read W, dY, X in 
 accumulate epilogues, LayerNorm / embedding / tag-projection backward, bias gradients, gradient norm, AdamW."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -217,3 +218,95 @@ def test_attention_bwd(ops, R, S, heads, lens):
     # key rows outside the window receive exactly zero dK / dV
     if (~rows).any():
         assert float(dqkv.float()[~rows][:, H:].abs().max()) == 0.0
+
+
+def _seed_tensor(a, b):
+    return torch.tensor([a, b], dtype=torch.int32, device="cuda")
+
+
+@pytest.mark.parametrize("H,p", [(256, 0.0), (1024, 0.1), (1024, 0.3)])
+def test_add_layernorm_fwd_bwd_with_dropout(ops, H, p):
+    """y = LN(dropout(x + bias) + resid): forward and every gradient against torch autograd with the host-rebuilt mask."""
+    from test_api_gpu import host_dropout_mask
+    g = torch.Generator(device="cuda").manual_seed(H + int(p * 100))
+    M, site = 555, 7
+    x = _rand(g, M, H, scale=1.5).requires_grad_(True)
+    bias = _rand(g, H, scale=0.3).requires_grad_(True)
+    resid = _rand(g, M, H, scale=1.0).bfloat16()
+    rf = resid.float().requires_grad_(True)
+    gamma = (torch.rand(H, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = _rand(g, H, scale=0.1).requires_grad_(True)
+    dout = _rand(g, M, H, scale=1.0)
+    dres = _rand(g, M, H, scale=0.5).bfloat16()
+    seed = _seed_tensor(1234567, 89)
+    drop = (seed, site, p) if p > 0 else None
+    mask = (torch.from_numpy(host_dropout_mask(np.array([1234567, 89], np.uint32), site, p, n_elems=M * H)).view(M, H).cuda()
+            if p > 0 else torch.ones(M, H, device="cuda"))
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), gamma.detach(), beta.detach(), 1e-5, save_stats=True, bias=bias.detach(),
+                                      resid=resid, drop=drop)
+    z = (x + bias) * mask + rf
+    ref = torch.nn.functional.layer_norm(z, (H,), gamma, beta, 1e-5)
+    assert bool(((y.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5).all())
+    ref.backward(dout + dres.float())
+    dgamma, dbeta, dxsum = (torch.zeros(H, device="cuda") for _ in range(3))
+    res = ops.layernorm_bwd(x.detach(), dout, gamma.detach(), mean, rstd, dgamma, dbeta, dxsum=dxsum, bias=bias.detach(),
+                            resid=resid, dres=dres, drop=drop)
+    dz, dxm = res if isinstance(res, tuple) else (res, res)
+    assert (p > 0) == isinstance(res, tuple)
+    assert bool(((dz.float() - rf.grad).abs() <= 2.0 ** -8 * rf.grad.abs() + 1e-4).all())        # residual path: unmasked
+    assert bool(((dxm.float() - x.grad).abs() <= 2.0 ** -8 * x.grad.abs() + 1e-4).all())         # through the mask
+    torch.testing.assert_close(dxsum, bias.grad, rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(dgamma, gamma.grad, rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(dbeta, beta.grad, rtol=1e-4, atol=2e-3)
+
+
+def test_dropout_apply_bf16_and_f32(ops):
+    from test_api_gpu import host_dropout_mask
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, H, site, p = 333, 1024, 96, 0.1
+    mask = torch.from_numpy(host_dropout_mask(np.array([42, 4242], np.uint32), site, p, n_elems=M * H)).view(M, H).cuda()
+    seed = _seed_tensor(42, 4242)
+    xf = _rand(g, M, H, scale=1.0)
+    xb = xf.bfloat16()
+    want_f, want_b = xf * mask, (xb.float() * mask).bfloat16()
+    ops.dropout_apply(xf, (seed, site, p))
+    ops.dropout_apply(xb, (seed, site, p))
+    torch.testing.assert_close(xf, want_f, rtol=1e-6, atol=0)
+    assert torch.equal(xb, want_b)
+
+
+@pytest.mark.parametrize("R,S,heads,lens", [(2, 512, 16, [512, 300]), (3, 200, 4, [200, 129, 1])])
+def test_attention_fwd_bwd_with_dropout(ops, R, S, heads, lens):
+    """Attention-probability dropout: O and dQ / dK / dV against autograd through softmax -> mask -> P.V with the
+    host-rebuilt mask (same tolerances as the dropout-free test)."""
+    from test_api_gpu import host_dropout_mask
+    g = torch.Generator(device="cuda").manual_seed(R * 11 + S + heads)
+    H, p, site = heads * 64, 0.1, 40
+    qkv = _rand(g, R * S, 3 * H, scale=1.0).bfloat16()
+    key_len = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    seed = _seed_tensor(2024, 925)
+    drop = (seed, site, p)
+    out, lse = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True, drop=drop)
+    out0, lse0 = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True)
+    torch.testing.assert_close(lse, lse0, rtol=0, atol=0)            # the softmax statistics ignore the mask
+    mask = torch.from_numpy(host_dropout_mask(np.array([2024, 925], np.uint32), site, p, attn=(R, heads, S))).cuda()
+    d_out = _rand(g, R * S, H, scale=1.0)
+    valid_q = (torch.arange(S, device="cuda")[None, :] < key_len[:, None]).reshape(R * S, 1)
+    d_out = (d_out * valid_q).bfloat16()
+    dqkv = ops.attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, drop=drop)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.reshape(R, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * 0.125
+    kmask = torch.arange(S, device="cuda")[None, :] < key_len[:, None]
+    sc = sc.masked_fill(~kmask[:, None, None, :], float("-inf"))
+    o = ((torch.softmax(sc, -1) * mask) @ v).permute(0, 2, 1, 3).reshape(R * S, H)
+    rows = valid_q.squeeze(1)
+    do = (out.float() - o.detach())[rows].abs()
+    assert do.max().item() < 3e-2 and do.mean().item() < 3e-3, (do.max().item(), do.mean().item())
+    assert (out.float() - out0.float())[rows].abs().max().item() > 0.05          # the mask really was applied
+    o.backward(d_out.float())
+    ref = x.grad
+    diff = (dqkv.float() - ref)[rows].abs()
+    scale = ref[rows].abs().max().item()
+    assert diff.max().item() < 3e-2 * max(scale, 1.0), (diff.max().item(), scale)
+    assert (diff.mean() / ref[rows].abs().mean()).item() < 1e-2
