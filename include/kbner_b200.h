@@ -115,6 +115,16 @@ int kbner_add_layernorm_fwd(const float *x /*[M,H]*/, const float *bias /*[H] or
                             float eps, int M, int H, uint16_t *y /*[M,H] bf16*/, float *mean, float *rstd,
                             const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream);
 
+/* Y = LayerNorm(A . W^T + bias + resid) * gamma + beta in ONE kernel (inference forward): the attention-output and
+ * FFN-down projections with the BertSelfOutput / BertOutput tail.  A [M,K] bf16 (K-major), W [N,K] bf16 (torch Linear
+ * layout), N in {256, 512, 768, 1024}; a thread-block cluster of 2 * N/256 CTAs owns a full 256-row panel and exchanges the
+ * per-row LayerNorm statistics through distributed shared memory (csrc/gemm_ln_tcgen05.cu).  bias / resid may be NULL.
+ * Replaces: torch.nn.Linear + residual add + torch.nn.LayerNorm under flair/embeddings.py:3269 (eval mode). */
+int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t *W, const float *bias, const uint16_t *resid,
+                                    const float *gamma, const float *beta, float eps, uint16_t *Y /*[M,N] bf16*/,
+                                    int M, int N, int K, int lda, int ldw, void *stream);
+int kbner_gemm_ln_resident_clusters(int N);
+
 /* In-place element-wise dropout with the same counter-hash mask (XLMRobertaEmbeddings.dropout: bf16 activations in the
  * forward, fp32 gradient in the backward). */
 int kbner_dropout_apply(void *x /*[M,H] bf16 or fp32*/, int is_f32, int M, int H, const uint32_t *drop_seed,

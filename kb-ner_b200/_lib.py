@@ -37,6 +37,8 @@ SIGNATURES = {
     "kbner_attention_fwd_dropout": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p] * 3 + [ctypes.c_uint32, _c_float, _c_void_p], _c_int),
     "kbner_attention_bwd_dropout": ([_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p] * 4 + [ctypes.c_uint32, _c_float, _c_void_p],
                                     _c_int),
+    "kbner_gemm_bias_resid_layernorm": ([_c_void_p] * 6 + [_c_float, _c_void_p] + [_c_int] * 5 + [_c_void_p], _c_int),
+    "kbner_gemm_ln_resident_clusters": ([_c_int], _c_int),
     "kbner_colsum_bf16": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
     "kbner_embed_ln_bwd": ([_c_void_p] * 5 + [_c_float] + [_c_int] * 4 + [_c_void_p] * 7, _c_int),
     "kbner_gather_tagproj_bwd": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 4, _c_int),

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace kbner {
 namespace ptx {

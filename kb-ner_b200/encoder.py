@@ -111,6 +111,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         self._tgraphs = {}
         import os
         self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
+        self._fuse_ln = os.environ.get("KBNER_FUSE_LN", "1") != "0"
 
     # ---- checkpointing: only parameters travel; graphs, workspaces, compute copies and the arena are rebuilt ----
     def __getstate__(self):
@@ -178,15 +179,25 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight,
                          e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias,
                          c.layer_norm_eps, c.pad_token_id, out=x)
+        # attention-output and FFN-down projections: bias + residual + LayerNorm fused into the GEMM epilogue over a
+        # thread-block cluster that owns full rows (csrc/gemm_ln_tcgen05.cu); hidden sizes it is not built for, or
+        # KBNER_FUSE_LN=0, take the GEMM (fp32 out) + LayerNorm-with-bias-and-residual pair instead
+        fuse = self._fuse_ln and c.hidden_size in (256, 512, 768, 1024)
+        y, h, ctx = ws["y"], ws["h"], ws["ctx"]
         for w in self._compute:
             ops.gemm_bf16_tn(x, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BIAS, out=ws["qkv"])
-            ops.attention_fwd(ws["qkv"], key_len, R, S, c.num_attention_heads, out=ws["ctx"])
-            # dense bias + residual are added by the LayerNorm pass (coalesced), not by the GEMM epilogue
-            ops.gemm_bf16_tn(ws["ctx"], w["wo"], None, epilogue=ops.EPI_NONE_F32, out=ws["y"])
-            ops.layernorm_fwd(ws["y"], w["g1"], w["b1"], c.layer_norm_eps, out=xn, bias=w["bo"], resid=x)
-            ops.gemm_bf16_tn(xn, w["w1"], w["bi"], epilogue=ops.EPI_BIAS_GELU, out=ws["h"])
-            ops.gemm_bf16_tn(ws["h"], w["w2"], None, epilogue=ops.EPI_NONE_F32, out=ws["y"])
-            ops.layernorm_fwd(ws["y"], w["g2"], w["bb2"], c.layer_norm_eps, out=x, bias=w["b2"], resid=xn)
+            ops.attention_fwd(ws["qkv"], key_len, R, S, c.num_attention_heads, out=ctx)
+            if fuse:
+                ops.gemm_ln(ctx, w["wo"], w["bo"], x, w["g1"], w["b1"], c.layer_norm_eps, out=xn)
+            else:
+                ops.gemm_bf16_tn(ctx, w["wo"], None, epilogue=ops.EPI_NONE_F32, out=y)
+                ops.layernorm_fwd(y, w["g1"], w["b1"], c.layer_norm_eps, out=xn, bias=w["bo"], resid=x)
+            ops.gemm_bf16_tn(xn, w["w1"], w["bi"], epilogue=ops.EPI_BIAS_GELU, out=h)
+            if fuse:
+                ops.gemm_ln(h, w["w2"], w["b2"], xn, w["g2"], w["bb2"], c.layer_norm_eps, out=x)
+            else:
+                ops.gemm_bf16_tn(h, w["w2"], None, epilogue=ops.EPI_NONE_F32, out=y)
+                ops.layernorm_fwd(y, w["g2"], w["bb2"], c.layer_norm_eps, out=x, bias=w["b2"], resid=xn)
         return x
 
     @torch.no_grad()

@@ -187,6 +187,29 @@ def gemm_bf16_tn(A, B, bias=None, residual=None, epilogue=EPI_BIAS, out=None):
     return out
 
 
+def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None):
+    """out[M,N] (bf16) = LayerNorm(A[M,K] @ W[N,K]^T + bias + resid) * gamma + beta, one kernel (N in 256..1024 step 256)."""
+    _chk(A, torch.bfloat16, "A", 2)
+    _chk(W, torch.bfloat16, "W", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(resid, torch.bfloat16, "resid", 2)
+    _chk(gamma, torch.float32, "gamma", 1)
+    _chk(beta, torch.float32, "beta", 1)
+    M, K = A.shape
+    N, K2 = W.shape
+    if K != K2:
+        raise _lib.KbnerError("gemm_ln: K mismatch %d vs %d" % (K, K2))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=A.device)
+    else:
+        _chk(out, torch.bfloat16, "out", 2)
+    if resid is not None and resid.data_ptr() == out.data_ptr():
+        raise _lib.KbnerError("gemm_ln: out must not alias resid (other CTAs still read the residual rows)")
+    _lib.check(_lib.load().kbner_gemm_bias_resid_layernorm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta),
+                                                           float(eps), _ptr(out), M, N, K, K, K, _stream()), "gemm_ln")
+    return out
+
+
 def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None):
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(key_len, torch.int32, "key_len", 1)

@@ -192,6 +192,35 @@ def test_gemm_tcgen05(ops, M, N, K, epi):
     assert bool((diff <= tol).all()), "max diff %g at %s" % (diff.max().item(), (M, N, K, epi))
 
 
+@pytest.mark.parametrize("M,N,K,with_resid", [(300, 256, 192, True), (1000, 512, 256, True), (2125, 768, 320, True),
+                                              (4096, 1024, 1024, True), (16384, 1024, 1024, True), (16384, 1024, 4096, True),
+                                              (777, 1024, 512, False)])
+def test_gemm_bias_resid_layernorm_fused(ops, M, N, K, with_resid):
+    """One-kernel LayerNorm(A.W^T + bias + resid): cluster of 2*N/256 CTAs, statistics exchanged through DSMEM.  Checked
+    against the fp32 restatement on the same bf16 inputs, and against the unfused pair of kernels (which must agree to one
+    bf16 rounding of nearly identical fp32 values)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.2
+    resid = (torch.randn(M, N, device="cuda", generator=g) + 0.3).bfloat16() if with_resid else None
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    beta = torch.randn(N, device="cuda", generator=g) * 0.1
+    y = ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5)
+    assert y.dtype == torch.bfloat16 and y.shape == (M, N)
+    z = a.float() @ w.float().t() + bias[None, :]
+    if with_resid:
+        z = z + resid.float()
+    ref = torch.nn.functional.layer_norm(z, (N,), gamma, beta, 1e-5)
+    diff = (y.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2e-3
+    assert bool((diff <= tol).all()), "max diff %g (ref %g)" % (diff.max().item(), ref.abs().max().item())
+    y0 = ops.gemm_bf16_tn(a, w, None, epilogue=3)
+    y1 = ops.layernorm_fwd(y0, gamma, beta, 1e-5, bias=bias, resid=resid)
+    mism = (y.float() - y1.float()).abs() > 2.0 ** -7 * y1.float().abs() + 1e-3
+    assert int(mism.sum()) == 0, int(mism.sum())
+
+
 def test_gemm_linearity_full_size(ops):
     """Config-2 shape (M=16384, N=3072, K=1024): checked by sampling rows against fp32 and by linearity
     C(a1+a2) = C(a1) + C(a2) for exactly representable inputs."""
