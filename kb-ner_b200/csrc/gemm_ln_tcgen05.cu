@@ -38,7 +38,7 @@ struct GemmLnSmem {
     uint8_t cstage[kLEpiWarps][2][4096];    // per warp, per 64-column half: residual tile in, bf16 output tile out (32 rows x 128 B,
                                             // SWIZZLE_128B; a lane only ever touches its own row, so the output overwrites in place)
     float2 stats[2][2 * kMaxPairs][128];    // [tile parity][source = pair * 2 + column half][row]: (mean, M2) of 128 columns
-    alignas(16) float par[3][256];          // bias, gamma, beta of this pair's 256 columns
+    alignas(16) float par[3][512];          // bias, gamma, beta of this pair's (up to 512) columns
     uint64_t full[kLStages];
     uint64_t empty[kLStages];
     uint64_t tmem_full[2];
@@ -53,6 +53,7 @@ struct GemmLnArgs {
     const float *gamma, *beta;
     int M, N, K;
     float eps;
+    int tiles_per_pair;       // 256-column tiles each CTA pair computes per row panel (1 or 2)
 };
 
 __device__ __forceinline__ uint32_t cluster_nctarank() {
@@ -62,10 +63,6 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 }
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
-}
-// release at cluster scope: the partial statistics stored just before must be visible to the CTA that owns the barrier
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -102,6 +99,29 @@ __device__ __forceinline__ void chan_merge(float &n_a, float &mean_a, float &m2_
     n_a = n;
 }
 
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns (inverse of tmem_ld_32x32b_x32)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Cluster = `npairs` CTA pairs; pair p owns T = tiles_per_pair consecutive 256-column tiles (columns p*T*256 ...), one TMEM
+// accumulator buffer per tile.  Per 256-row panel:
+//   MMA      tile 0 -> TMEM buffer 0, tile 1 -> buffer 1                        (T = 1: buffers alternate between panels)
+//   epilogue pass 1 of tile j as soon as it is complete: z = acc + bias + resid is written BACK to TMEM (tcgen05.st) and the
+//            thread's running (mean, M2) is updated -- pass 1 of tile 0 overlaps the main loop of tile 1;
+//            one DSMEM exchange of the partials among the same-parity CTAs of all pairs;
+//            pass 2 reads z from TMEM, normalises, stores; buffer j is handed back to the MMA warp after its last read.
+// N = 1024 runs as clusters of 4 CTAs (2 pairs x 2 tiles): clusters of 8 (4 pairs x 1 tile) fit only 15 times on the
+// 148 SMs (GPC granularity) and needed 5 rounds for 64 panels; clusters of 4 fit ~36 times (2 rounds).
 __global__ void __launch_bounds__(kLThreads, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const GemmLnArgs g) {
@@ -112,10 +132,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t pair = rank >> 1, sub = rank & 1u, leader_rank = rank & ~1u;
     const bool leader = sub == 0;
     const int npairs = (int)(csize >> 1);
+    const int T = g.tiles_per_pair;
     const int cluster_id = blockIdx.x / (int)csize, num_clusters = gridDim.x / (int)csize;
     const int M = g.M, N = g.N;
     const int num_panels = (M + LBM - 1) / LBM;
     const int num_kb = (g.K + LBK - 1) / LBK;
+    const int col_pair0 = (int)pair * T * LBN;        // first column of this pair
 
     if (warp == 0 && lane == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
@@ -136,11 +158,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ptx::fence_barrier_init();
     }
-    // this pair's 256 columns of bias / gamma / beta: loaded once, read as shared-memory broadcasts in the epilogue
-    for (int i = threadIdx.x; i < 3 * 256; i += kLThreads) {
-        const int which = i >> 8, c = i & 255;
+    // this pair's columns of bias / gamma / beta: loaded once, read as shared-memory broadcasts in the epilogue
+    for (int i = threadIdx.x; i < 3 * 512; i += kLThreads) {
+        const int which = i >> 9, c = i & 511;
         const float *src = which == 0 ? g.bias : which == 1 ? g.gamma : g.beta;
-        s.par[which][c] = src ? src[pair * 256 + c] : 0.0f;
+        s.par[which][c] = (src && c < T * LBN) ? src[col_pair0 + c] : 0.0f;
     }
     if (warp == 1) tmem_alloc_2sm<kLTmemCols>(&s.tmem_base);
     ptx::tc_fence_before();
@@ -154,19 +176,21 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t phase = 0;
         const uint32_t a_smem0 = ptx::smem_u32(s.a[0]), b_smem0 = ptx::smem_u32(s.b[0]);
         const uint32_t full0_leader = mapa(ptx::smem_u32(&s.full[0]), leader_rank);
-        const int bn0 = (int)pair * LBN + (int)sub * 128;
         for (int panel = cluster_id; panel < num_panels; panel += num_clusters) {
             const int am0 = panel * LBM + (int)sub * 128;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                ptx::mbar_wait(&s.empty[stage], phase ^ 1);
-                if (ptx::elect_one()) {
-                    if (leader) ptx::mbar_expect_tx(&s.full[stage], 2 * (kLABytes + kLBBytes));
-                    const uint32_t bar = full0_leader + stage * 8;
-                    tma_load_2d_2sm(a_smem0 + stage * kLABytes, &tmA, bar, kb * LBK, am0);
-                    tma_load_2d_2sm(b_smem0 + stage * kLBBytes, &tmB, bar, kb * LBK, bn0);
+            for (int j = 0; j < T; ++j) {
+                const int bn0 = col_pair0 + j * LBN + (int)sub * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&s.empty[stage], phase ^ 1);
+                    if (ptx::elect_one()) {
+                        if (leader) ptx::mbar_expect_tx(&s.full[stage], 2 * (kLABytes + kLBBytes));
+                        const uint32_t bar = full0_leader + stage * 8;
+                        tma_load_2d_2sm(a_smem0 + stage * kLABytes, &tmA, bar, kb * LBK, am0);
+                        tma_load_2d_2sm(b_smem0 + stage * kLBBytes, &tmB, bar, kb * LBK, bn0);
+                    }
+                    __syncwarp();
+                    if (++stage == kLStages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == kLStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -180,166 +204,186 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint16_t mask = (uint16_t)(0x3u << (pair * 2));     // both CTAs of THIS pair
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int panel = cluster_id; panel < num_panels; panel += num_clusters, ++it) {
-                const int acc = it & 1;
-                ptx::mbar_wait(&s.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * LBN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(&s.full[stage], phase);
+            int tc = 0;                               // tile counter: buffer = tc & 1
+            for (int panel = cluster_id; panel < num_panels; panel += num_clusters) {
+                for (int j = 0; j < T; ++j, ++tc) {
+                    const int acc = tc & 1;
+                    ptx::mbar_wait(&s.tmem_empty[acc], ((tc >> 1) & 1) ^ 1);
                     ptx::tc_fence_after();
-                    if (ptx::elect_one()) {
-                        const uint32_t a_lo = a_lo0 + stage * (kLABytes >> 4), b_lo = b_lo0 + stage * (kLBBytes >> 4);
+                    const uint32_t d_tmem = tmem_base + acc * LBN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(&s.full[stage], phase);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint32_t a_lo = a_lo0 + stage * (kLABytes >> 4), b_lo = b_lo0 + stage * (kLBBytes >> 4);
 #pragma unroll
-                        for (int k = 0; k < LBK / 16; ++k)
-                            mma_f16_ss_2sm(d_tmem, pack_desc(a_lo + k * 2u, hi), pack_desc(b_lo + k * 2u, hi), idesc,
-                                           (kb != 0) || (k != 0));
-                        mma_commit_mc(empty0 + stage * 8, mask);
+                            for (int k = 0; k < LBK / 16; ++k)
+                                mma_f16_ss_2sm(d_tmem, pack_desc(a_lo + k * 2u, hi), pack_desc(b_lo + k * 2u, hi), idesc,
+                                               (kb != 0) || (k != 0));
+                            mma_commit_mc(empty0 + stage * 8, mask);
+                        }
+                        __syncwarp();
+                        if (++stage == kLStages) { stage = 0; phase ^= 1; }
                     }
+                    if (ptx::elect_one()) mma_commit_mc(tfull0 + acc * 8, mask);
                     __syncwarp();
-                    if (++stage == kLStages) { stage = 0; phase ^= 1; }
                 }
-                if (ptx::elect_one()) mma_commit_mc(tfull0 + acc * 8, mask);
-                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue: bias + residual + LayerNorm over the cluster =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                     // which 128 of the pair's 256 columns
+        const int half = ew >> 2;                     // which 128 of a tile's 256 columns
         const int row_l = quarter * 32 + lane;        // row inside this CTA's 128 rows
-        const int colw = (int)pair * LBN + half * 128;   // first global column of this warp
         const uint32_t tempty_leader = mapa(ptx::smem_u32(&s.tmem_empty[0]), leader_rank);
         uint8_t *stage_buf = s.cstage[ew][0];
         const uint32_t stage_u32 = ptx::smem_u32(stage_buf);
-        const float *bias_s = s.par[0] + half * 128, *gamma_s = s.par[1] + half * 128, *beta_s = s.par[2] + half * 128;
         const bool has_resid = g.resid != nullptr;
         const float inv_n = 1.0f / (float)N;
-        int it = 0;
+        const float n_part = (float)(T * 128);        // columns behind one published partial
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        int it = 0, tc = 0;
+        uint32_t nstores = 0;                         // TMA stores issued by this warp (lane 0 tracks the bulk groups)
         for (int panel = cluster_id; panel < num_panels; panel += num_clusters, ++it) {
-            const int acc = it & 1;
             const int row_w0 = panel * LBM + (int)sub * 128 + quarter * 32;     // first global row of this warp
-            // ---- residual tile [32 rows x 128 bf16] -> shared memory with cp.async: the global side is coalesced (4 rows x 128 B
-            // per request), the shared side lands transposed-ready (row r at r * 128 B, 16-byte chunks XOR-swizzled), no
-            // registers are held while the main loop of this tile still runs
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's stores have read the buffers
-            __syncwarp();
-            if (has_resid) {
+            const int tc0 = tc;
+            // ---- pass 1 per tile: z = acc + bias + resid back to TMEM, running (mean, M2) of this thread's columns
+            float n_a = 0.0f, mean_a = 0.0f, m2_a = 0.0f;
+            for (int j = 0; j < T; ++j, ++tc) {
+                const int acc = tc & 1;
+                const int colw = col_pair0 + j * LBN + half * 128;               // first global column of this warp in tile j
+                // residual tile [32 rows x 128 bf16] -> shared memory with cp.async: the global side is coalesced (4 rows x
+                // 128 B per request), the shared side lands row-per-lane ready (row r at r * 128 B, 16-byte chunks XOR-swizzled)
+                if (j == 0) {                          // the previous panel's stores must have read the buffers
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();                          // (j > 0: every lane finished reading tile j-1's residual)
+                if (has_resid) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
+                    for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + (lane >> 3);
-                        const int grow = row_w0 + r;
-                        const uint32_t dst = stage_u32 + hh * 4096 + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
-                        if (grow < M) {
-                            const uint16_t *src = g.resid + (size_t)grow * N + colw + hh * 64 + (lane & 7) * 8;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                        } else {
-                            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 4 * i + (lane >> 3);
+                            const int grow = row_w0 + r;
+                            const uint32_t dst = stage_u32 + hh * 4096 + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
+                            if (grow < M) {
+                                const uint16_t *src = g.resid + (size_t)grow * N + colw + hh * 64 + (lane & 7) * 8;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                            } else {
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+                            }
                         }
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-            ptx::mbar_wait(&s.tmem_full[acc], (it >> 1) & 1);
-            ptx::tc_fence_after();
-            if (has_resid) asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();                              // every lane's part of the residual tile is in shared memory
-            const uint32_t taddr0 = tmem_base + (uint32_t(quarter * 32) << 16) + acc * LBN + half * 128;
-            // z of 32 columns starting at column c32 * 32 of this warp's range
-            auto load_z = [&](int c32, float (&z)[32]) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr0 + c32 * 32, r);
-                ptx::tmem_ld_wait();
+                ptx::mbar_wait(&s.tmem_full[acc], (tc >> 1) & 1);
+                ptx::tc_fence_after();
+                if (has_resid) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();                          // every lane's part of the residual tile is in shared memory
+                const uint32_t taddr0 = tmem_base + lane_addr + acc * LBN + half * 128;
+                const float *bias_s = s.par[0] + j * LBN + half * 128;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    const int chunk = (c32 & 1) * 4 + (i >> 3);             // 16-byte chunk inside the 128-byte row of half c32 >> 1
-                    uint4 rv = make_uint4(0, 0, 0, 0);
-                    if (has_resid)
-                        rv = *reinterpret_cast<const uint4 *>(stage_buf + (c32 >> 1) * 4096 + lane * 128 + ((chunk ^ (lane & 7)) << 4));
-                    float a[8];
-                    unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
-                    unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(taddr0 + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    float sm = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        z[i + e] = (__uint_as_float(r[i + e]) + bias_s[c32 * 32 + i + e]) + a[e];   // same order as the unfused path
+                    for (int i = 0; i < 32; i += 8) {
+                        const int chunk = (c & 1) * 4 + (i >> 3);             // 16-byte chunk inside the 128-byte row of half c >> 1
+                        uint4 rv = make_uint4(0, 0, 0, 0);
+                        if (has_resid)
+                            rv = *reinterpret_cast<const uint4 *>(stage_buf + (c >> 1) * 4096 + lane * 128 + ((chunk ^ (lane & 7)) << 4));
+                        float a[8];
+                        unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
+                        unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float z = (__uint_as_float(r[i + e]) + bias_s[c * 32 + i + e]) + a[e];   // order of the unfused path
+                            r[i + e] = __float_as_uint(z);
+                            sm += z;
+                        }
+                    }
+                    tmem_st_32x32b_x32(taddr0 + c * 32, r);
+                    const float cm = sm * (1.0f / 32.0f);
+                    float sq = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - cm; sq = fmaf(d, d, sq); }
+                    if (j == 0 && c == 0) { n_a = 32.0f; mean_a = cm; m2_a = sq; }
+                    else chan_merge(n_a, mean_a, m2_a, 32.0f, cm, sq);
                 }
-            };
-            // ---- pass 1: (mean, M2) of this thread's 128 columns, chunk-wise two-pass + Chan merge
-            float n_a = 0.0f, mean_a = 0.0f, m2_a = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float z[32];
-                load_z(c, z);
-                float sm = 0.0f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sm += z[i];
-                const float cm = sm * (1.0f / 32.0f);
-                float sq = 0.0f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { const float d = z[i] - cm; sq = fmaf(d, d, sq); }
-                if (c == 0) { n_a = 32.0f; mean_a = cm; m2_a = sq; }
-                else chan_merge(n_a, mean_a, m2_a, 32.0f, cm, sq);
+                tmem_st_wait();
             }
             // ---- publish the partial to the CTAs that hold the same rows (same parity in every pair), then collect
             const int sbuf = it & 1;
             {
                 const uint32_t slot_addr = ptx::smem_u32(&s.stats[sbuf][pair * 2 + half][row_l]);
                 const uint32_t bar_addr = ptx::smem_u32(&s.stats_bar[sbuf]);
-                for (int qp = 0; qp < npairs; ++qp) {
-                    const uint32_t dst = (uint32_t)(2 * qp) + sub;
-                    st_cluster_f32x2(mapa(slot_addr, dst), mean_a, m2_a);
-                    mbar_arrive_release_cluster(mapa(bar_addr, dst));
-                }
+                // all remote stores first, ONE cluster-scope fence, then relaxed arrives: a release-arrive per destination
+                // compiled to MEMBAR + ERRBAR per destination, thread and panel (22 % of the stall samples of the first version)
+                for (int qp = 0; qp < npairs; ++qp) st_cluster_f32x2(mapa(slot_addr, (uint32_t)(2 * qp) + sub), mean_a, m2_a);
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                for (int qp = 0; qp < npairs; ++qp) mbar_arrive_cluster(mapa(bar_addr, (uint32_t)(2 * qp) + sub));
             }
             mbar_wait_acq_cluster(&s.stats_bar[sbuf], (it >> 1) & 1);
             float n_t = 0.0f, mean = 0.0f, m2 = 0.0f;
             for (int sl = 0; sl < 2 * npairs; ++sl) {
                 const float2 p = s.stats[sbuf][sl][row_l];
-                if (sl == 0) { n_t = 128.0f; mean = p.x; m2 = p.y; }
-                else chan_merge(n_t, mean, m2, 128.0f, p.x, p.y);
+                if (sl == 0) { n_t = n_part; mean = p.x; m2 = p.y; }
+                else chan_merge(n_t, mean, m2, n_part, p.x, p.y);
             }
             const float rstd = rsqrtf(m2 * inv_n + g.eps);
-            // ---- pass 2: normalise, bf16, SWIZZLE_128B staging, TMA store (two chunks of 64 columns)
+            // ---- pass 2 per tile: normalise z from TMEM, bf16, SWIZZLE_128B staging, TMA store (chunks of 64 columns)
+            for (int j = 0; j < T; ++j) {
+                const int acc = (tc0 + j) & 1;
+                const int colw = col_pair0 + j * LBN + half * 128;
+                const uint32_t taddr0 = tmem_base + lane_addr + acc * LBN + half * 128;
+                const float *gamma_s = s.par[1] + j * LBN + half * 128, *beta_s = s.par[2] + j * LBN + half * 128;
 #pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                uint4 ov[8];
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    uint4 ov[8];
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    float z[32];
-                    load_z(c2 * 2 + h2, z);
-                    const int cb = c2 * 64 + h2 * 32;
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32b_x32(taddr0 + (c2 * 2 + h2) * 32, r);
+                        ptx::tmem_ld_wait();
+                        const int cb = c2 * 64 + h2 * 32;
+                        float y[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) z[i] = fmaf((z[i] - mean) * rstd, gamma_s[cb + i], beta_s[cb + i]);
+                        for (int i = 0; i < 32; ++i) y[i] = fmaf((__uint_as_float(r[i]) - mean) * rstd, gamma_s[cb + i], beta_s[cb + i]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        ov[h2 * 4 + j].x = pack_bf16x2(z[j * 8 + 0], z[j * 8 + 1]);
-                        ov[h2 * 4 + j].y = pack_bf16x2(z[j * 8 + 2], z[j * 8 + 3]);
-                        ov[h2 * 4 + j].z = pack_bf16x2(z[j * 8 + 4], z[j * 8 + 5]);
-                        ov[h2 * 4 + j].w = pack_bf16x2(z[j * 8 + 6], z[j * 8 + 7]);
+                        for (int q = 0; q < 4; ++q) {
+                            ov[h2 * 4 + q].x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+                            ov[h2 * 4 + q].y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+                            ov[h2 * 4 + q].z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+                            ov[h2 * 4 + q].w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+                        }
                     }
-                }
-                if (c2 == 1) {                         // accumulator drained for good: the MMA warp may reuse it
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
-                }
-                // the output row replaces the residual row it was computed from (this lane's own 128 bytes of half c2)
-                uint8_t *dst = stage_buf + c2 * 4096 + lane * 128;
+                    if (c2 == 1) {                     // buffer `acc` drained for good: the MMA warp may reuse it
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                    }
+                    if (nstores >= 2) {                // the store that last read this half (two stores ago) must be done with it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                    }
+                    uint8_t *dst = stage_buf + c2 * 4096 + lane * 128;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4 *>(dst + ((j ^ (lane & 7)) << 4)) = ov[j];
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(stage_u32 + c2 * 4096), "r"(colw + c2 * 64), "r"(row_w0)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4 *>(dst + ((q ^ (lane & 7)) << 4)) = ov[q];
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(stage_u32 + c2 * 4096), "r"(colw + c2 * 64), "r"(row_w0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++nstores;
                 }
             }
+            nstores = 0;                               // the next panel starts with wait_group.read 0
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -376,7 +420,10 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
     rc = make_tmap_2d(&tmY, Y, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 64, 2);
     if (rc) return rc;
     const size_t smem = sizeof(GemmLnSmem);
-    const int csize = 2 * (N / 256);
+    // N/256 tiles = npairs x tiles_per_pair: 256 -> 1x1, 512 -> 1x2, 768 -> 3x1, 1024 -> 2x2
+    const int ntiles = N / 256;
+    const int tpp = (ntiles % 2 == 0) ? 2 : 1;
+    const int csize = 2 * (ntiles / tpp);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -407,7 +454,7 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
     const int panels = (M + LBM - 1) / LBM;
     const int clusters = panels < g_max_clusters[csize] ? panels : g_max_clusters[csize];
     cfg.gridDim = dim3((unsigned)(clusters * csize));
-    GemmLnArgs g{bias, resid, gamma, beta, M, N, K, eps};
+    GemmLnArgs g{bias, resid, gamma, beta, M, N, K, eps, tpp};
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_kernel, tmA, tmB, tmY, g);
     if (e != cudaSuccess) {
         set_error("gemm_ln: launch failed: %s", cudaGetErrorString(e));
@@ -420,5 +467,6 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
 // Resident clusters the fused kernel gets for hidden size N (0 before its first launch): reported by bench.py.
 extern "C" int kbner_gemm_ln_resident_clusters(int N) {
     if (N % 256 != 0 || N < 256 || N > 256 * kMaxPairs) return 0;
-    return g_max_clusters[2 * (N / 256)];
+    const int ntiles = N / 256;
+    return g_max_clusters[2 * (ntiles / ((ntiles % 2 == 0) ? 2 : 1))];
 }
