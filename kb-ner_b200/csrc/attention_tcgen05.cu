@@ -69,6 +69,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int nkb = (klen + kBKV - 1) / kBKV;        // key blocks that hold at least one valid key
     const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
             printf("kbner attention: dynamic shared memory is not 1024-byte aligned\n");
@@ -95,6 +96,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem_base = s.tmem_base;
     const uint32_t tmem_s = tmem_base;            // 2 x 64 columns
     const uint32_t tmem_o = tmem_base + 128;      // 2 x 64 columns
+    pdl_wait();                // Q / K / V come from the preceding GEMM (key_len above is a step input, not a kernel output)
 
     if (warp == 8) {
         if (lane == 0 && nkb > 0) {
@@ -304,10 +306,17 @@ extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *k
         configured = true;
     }
     dim3 grid((S + kBQ - 1) / kBQ, heads, R);
+    cudaError_t le;
     if (drop.thresh)
-        attention_fwd_kernel<true><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse, drop);
+        le = launch_kernel(attention_fwd_kernel<true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
+                           key_len, S, H, heads, out, lse, drop);
     else
-        attention_fwd_kernel<false><<<grid, kAttnThreads, smem, (cudaStream_t)stream>>>(tmQ, tmKV, key_len, S, H, heads, out, lse, drop);
+        le = launch_kernel(attention_fwd_kernel<false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
+                           key_len, S, H, heads, out, lse, drop);
+    if (le != cudaSuccess) {
+        set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
+        return KBNER_ECUDA;
+    }
     KBNER_CHECK_LAUNCH("attention_fwd");
     return KBNER_OK;
 }

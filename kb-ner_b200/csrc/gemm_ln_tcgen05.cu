@@ -139,6 +139,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_kb = (g.K + LBK - 1) / LBK;
     const int col_pair0 = (int)pair * T * LBN;        // first column of this pair
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
             printf("kbner gemm_ln: dynamic shared memory is not 1024-byte aligned\n");
@@ -169,6 +170,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
+    pdl_wait();                // (the prologue only read parameters: bias / gamma / beta are not written inside a step)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -425,11 +427,13 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
     const int tpp = (ntiles % 2 == 0) ? 2 : 1;
     const int csize = 2 * (ntiles / tpp);
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(kLThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
@@ -454,6 +458,7 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
     const int panels = (M + LBM - 1) / LBM;
     const int clusters = panels < g_max_clusters[csize] ? panels : g_max_clusters[csize];
     cfg.gridDim = dim3((unsigned)(clusters * csize));
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     GemmLnArgs g{bias, resid, gamma, beta, M, N, K, eps, tpp};
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_kernel, tmA, tmB, tmY, g);
     if (e != cudaSuccess) {

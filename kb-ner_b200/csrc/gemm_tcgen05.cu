@@ -97,6 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_splits = (num_kb + kb_per - 1) / kb_per;
     const int num_work = num_tiles * num_splits;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
             printf("kbner gemm: dynamic shared memory is not 1024-byte aligned\n");
@@ -120,6 +121,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync();            // barriers of the peer are initialised, TMEM allocated in both CTAs
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
+    pdl_wait();                // prologue done; from here on memory written by the preceding kernel is touched
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs; warp-uniform, elected lane issues) =====================
@@ -363,7 +365,12 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     const int num_kb = (g.K + BK - 1) / BK;
     const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
     const int clusters = num_work < kNumSMs / 2 ? num_work : kNumSMs / 2;
-    gemm_bf16_kernel<EPI><<<clusters * 2, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmAux, g);
+    cudaError_t le = launch_kernel(gemm_bf16_kernel<EPI>, dim3(clusters * 2), dim3(kGemmThreads), smem, st, 0, true, tmA, tmB, tmC,
+                                   tmAux, g);
+    if (le != cudaSuccess) {
+        set_error("gemm_bf16: launch failed: %s", cudaGetErrorString(le));
+        return KBNER_ECUDA;
+    }
     KBNER_CHECK_LAUNCH("gemm_bf16");
     return KBNER_OK;
 }

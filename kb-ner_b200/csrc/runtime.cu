@@ -1,4 +1,5 @@
 // Library-level plumbing of the C ABI: error text, launch counter, device check, TMA maps.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -21,6 +22,13 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("KBNER_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
