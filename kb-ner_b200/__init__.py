@@ -6,11 +6,11 @@ exposed through mirrors of the reference's flair classes.  See DESIGN.md.
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
 
-from . import data, encoder, embeddings, sequence_tagger  # noqa: F401,E402
+from . import data, datasets, encoder, embeddings, sequence_tagger  # noqa: F401,E402
 from .data import BatchedData, Dictionary, Label, Sentence, Token  # noqa: F401,E402
 from .embeddings import StackedEmbeddings, SyntheticTokenizer, TransformerWordEmbeddings  # noqa: F401,E402
 from .sequence_tagger import FastSequenceTagger, SequenceTagger  # noqa: F401,E402
 
-__all__ = ["_lib", "ops", "data", "encoder", "embeddings", "sequence_tagger", "TransformerWordEmbeddings",
+__all__ = ["_lib", "ops", "data", "datasets", "encoder", "embeddings", "sequence_tagger", "TransformerWordEmbeddings",
            "StackedEmbeddings", "SyntheticTokenizer", "SequenceTagger", "FastSequenceTagger", "Sentence", "Token",
            "Label", "Dictionary", "BatchedData"]

@@ -41,9 +41,8 @@ log = logging.getLogger("kbner_b200")
 def make_batches(sentences, mini_batch_size: int, sort: bool = True) -> List[BatchedData]:
     """Sentence-level batching of ColumnDataLoader (custom_data_loader.py:84-149): sort by WORD count (use_bert is
     False for TransformerWordEmbeddings, Appendix B.3), then chunk."""
-    order = sorted(range(len(sentences)), key=lambda i: len(sentences[i])) if sort else list(range(len(sentences)))
-    return [BatchedData([sentences[i] for i in order[k:k + mini_batch_size]])
-            for k in range(0, len(order), mini_batch_size)]
+    from .datasets import ColumnDataLoader
+    return list(ColumnDataLoader(list(sentences), mini_batch_size, sentence_level_batch=True, sort_data=sort).data)
 
 
 class ModelFinetuner:
