@@ -298,7 +298,7 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels (gemm_bf16_kernel + gemm_ln_kernel, %d launches/step; the fused "
                                "LayerNorm epilogues are charged to the GEMM time, their FLOPs are not counted)" % len(gemm_events),
                      "achieved": round(achieved, 1), "peak": sust, "unit": "TFLOP/s", "frac": round(achieved / sust, 4),
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % how, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % how, "traffic": _gemm_traffic(),
                      "gemm_ms_per_step": round(gemm_ms, 3),
                      "model_tflops_whole_step": round(flops_sent * BATCH / (ms_dev / K / 1e3) / 1e12, 1)},
     }
@@ -536,6 +536,15 @@ def run_reference(args):
             "e2e": {"value": v, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _gemm_traffic():
+    """DRAM bytes per GEMM launch (mean over the four shapes of a layer) from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "gemm_dram_traffic.json")) as f:
+            return int(json.load(f)["mean_per_launch"])
+    except Exception:
+        return None
 
 
 def main():

@@ -50,6 +50,19 @@ struct AttnSmem {
     uint32_t tmem_base;
 };
 
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -141,7 +154,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     const uint64_t da = ptx::make_sw128_desc(p_addr + kk * 32, 16, 1024);
                     // V tile [key][d]: 16 keys per MMA = two 8-row swizzle atoms, 1024 B apart (SBO)
                     const uint64_t db = ptx::make_sw128_desc(v_addr + kk * 16 * 128, 16, 1024);
-                    ptx::mma_f16_ss(tmem_o + (j & 1) * 64, da, db, idesc_o, kk != 0);
+                    ptx::mma_f16_ss(tmem_o, da, db, idesc_o, (j != 0) || (kk != 0));   // O accumulates in TMEM over the key blocks
                 }
                 ptx::mma_commit(&s.bar_o[j & 1]);
                 ptx::mma_commit(&s.kv_free[st]);
@@ -162,24 +175,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int qrow = qb * kBQ + row;                  // sub-token index inside the window
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
-        float m_run = -CUDART_INF_F, l_run = 0.0f, alpha_prev = 1.0f;
+        float m_run = -CUDART_INF_F, l_run = 0.0f;
         const uint32_t dkey = DROP ? drop_key(drop) : 0u;
         // dropout counter of (window, head, query): 256 key PAIRS per row (kMaxS / 2), the same in the backward kernel
         const uint32_t drow = (((uint32_t)(r * heads + h) * (uint32_t)kMaxS) + (uint32_t)qrow) * (uint32_t)(kMaxS / 2);
-        float o_acc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
-
-        auto accumulate_o = [&](int j, float alpha) {
-            ptx::mbar_wait(&s.bar_o[j & 1], (j >> 1) & 1);
-            ptx::tc_fence_after();
-            uint32_t ro[32];
-            ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + (j & 1) * 64 + half * 32, ro);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(ro[i]));
-            ptx::tc_fence_before();
-        };
+        const uint32_t o_addr = tmem_o + lane_addr + half * 32;     // this thread's 32 of the 64 output columns
 
         for (int j = 0; j < nkb; ++j) {
             ptx::mbar_wait(&s.bar_s[j & 1], (j >> 1) & 1);
@@ -205,10 +205,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             // row max over both halves: exchange through shared memory, pair barrier = the two warps of this quarter
             s.xchg[j & 1][half][row] = m_half;
             asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-            const float m_blk = fmaxf(m_half, s.xchg[j & 1][half ^ 1][row]);
-            const float m_new = fmaxf(m_run, m_blk * scale_log2);     // finite: the block has >= 1 valid key
-            const float alpha = ex2_approx(m_run - m_new);           // first block: ex2(-inf) = 0
-            const float neg_m = -m_new;
+            const float m_blk = fmaxf(m_half, s.xchg[j & 1][half ^ 1][row]) * scale_log2;   // finite: the block has >= 1 valid key
+            // LAZY rescaling: the running O lives in TMEM and is only touched when the row maximum grows by more than 2^8;
+            // otherwise the stale maximum stays the reference (probabilities up to 256 are exact enough in bf16 / fp32 and the
+            // final division by the row sum cancels the common factor).  Both threads of a row take the same decision (same
+            // m_blk, same m_run).  Removes a TMEM load + 32 FMAs + a barrier wait per block from the round-1 kernel.
+            // tcgen05.ld / .st are warp-collective: the decision is taken per WARP (any row of the warp over the threshold ->
+            // all 32 rows do the exact online-softmax update); warps w and w+4 see identical per-row values, so both halves
+            // of a row agree.
+            if (j == 0) {
+                m_run = m_blk;
+            } else if (__any_sync(0xffffffffu, m_blk > m_run + 8.0f)) {
+                const float m_new = fmaxf(m_run, m_blk);
+                const float alpha = ex2_approx(m_run - m_new);
+                m_run = m_new;
+                l_run *= alpha;
+                ptx::mbar_wait(&s.bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);    // P_{j-1}.V_{j-1} has retired
+                ptx::tc_fence_after();
+                uint32_t ro[32];
+                ptx::tmem_ld_32x32b_x32(o_addr, ro);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                tmem_st_32x32b_x32(o_addr, ro);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                ptx::tc_fence_before();
+            }
+            const float neg_m = -m_run;
             float l_blk = 0.0f;
             uint8_t *prow = s.p[j & 1] + row * 128;
 #pragma unroll
@@ -234,15 +257,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 pk.w = pack_bf16x2(pv[6], pv[7]);
                 *reinterpret_cast<uint4 *>(prow + (((half * 4 + cc) ^ (row & 7)) << 4)) = pk;
             }
-            l_run = l_run * alpha + l_blk;     // partial row sum over this thread's columns (both halves share m)
-            m_run = m_new;
+            l_run += l_blk;                     // partial row sum over this thread's columns (both halves share m_run)
             ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
             ptx::mbar_arrive(&s.bar_p[j & 1]);
-            // deferred accumulation of the previous block's P.V (overlaps this block's MMA)
-            if (j > 0) accumulate_o(j - 1, alpha_prev);
-            alpha_prev = alpha;
         }
-        if (nkb > 0) accumulate_o(nkb - 1, alpha_prev);
+        float o_acc[32];
+        if (nkb > 0) {
+            ptx::mbar_wait(&s.bar_o[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t ro[32];
+            ptx::tmem_ld_32x32b_x32(o_addr, ro);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(ro[i]);
+            ptx::tc_fence_before();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
+        }
         // total row sum = both halves
         s.xsum[half][row] = l_run;
         asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
