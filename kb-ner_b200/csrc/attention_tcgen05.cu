@@ -201,7 +201,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             float m_half = sc[0];
 #pragma unroll
-            for (int i = 1; i < 32; ++i) m_half = fmaxf(m_half, sc[i]);
+            for (int i = 1; i < 31; i += 2) m_half = fmax3(m_half, sc[i], sc[i + 1]);      // FMNMX3: 16 instead of 31 issue slots
+            m_half = fmaxf(m_half, sc[31]);
             // row max over both halves: exchange through shared memory, pair barrier = the two warps of this quarter
             s.xchg[j & 1][half][row] = m_half;
             asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
@@ -232,15 +233,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::tc_fence_before();
             }
             const float neg_m = -m_run;
-            float l_blk = 0.0f;
+            float l_blk = 0.0f, l_blk1 = 0.0f;
             uint8_t *prow = s.p[j & 1] + row * 128;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 float pv[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    pv[e] = ex2_approx(fmaf(sc[cc * 8 + e], scale_log2, neg_m));
-                    l_blk += pv[e];
+                for (int e = 0; e < 8; e += 2) {          // packed fp32: one FFMA2 + one FADD2 per two scores
+                    float x0, x1;
+                    ffma2(x0, x1, sc[cc * 8 + e], sc[cc * 8 + e + 1], scale_log2, neg_m);
+                    pv[e] = ex2_approx(x0);
+                    pv[e + 1] = ex2_approx(x1);
+                    fadd2(l_blk, l_blk1, pv[e], pv[e + 1]);
                 }
                 if (DROP) {                  // the softmax denominator is of the un-dropped row; only P.V sees the mask
 #pragma unroll
@@ -257,7 +261,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 pk.w = pack_bf16x2(pv[6], pv[7]);
                 *reinterpret_cast<uint4 *>(prow + (((half * 4 + cc) ^ (row & 7)) << 4)) = pk;
             }
-            l_run += l_blk;                     // partial row sum over this thread's columns (both halves share m_run)
+            l_run += l_blk + l_blk1;            // partial row sum over this thread's columns (both halves share m_run)
             ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
             ptx::mbar_arrive(&s.bar_p[j & 1]);
         }

@@ -82,6 +82,23 @@ __device__ __forceinline__ void st_na_v4(void *p, uint4 v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ---- Blackwell packed-fp32 and 3-input ALU ops (SASS FFMA2 / FADD2 / FMNMX3): half the issue slots of the scalar forms ----
+__device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, float b, float c) {   // d = a * b + c on a pair
+    asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float &s0, float &s1, float a0, float a1) {                    // s += a on a pair
+    asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "+f"(s0), "+f"(s1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---- dropout: stateless keep mask from a counter hash ---------------------------------------------------------------
 // The reference trains with torch.nn.Dropout inside transformers (hidden 0.1, attention probabilities 0.1).  Here a mask
 // is never stored: element e of dropout site `site` is kept iff the 16-bit half (e & 1) of
