@@ -1,5 +1,5 @@
-// Linear-chain CRF on sm_100a: remove-X compaction, Viterbi (+confidence), log-partition /
-// gold score, and their gradient.  Replaces the per-token Python loops of
+// Linear-chain CRF on sm_100a: remove-X compaction, log-partition / gold score, and their
+// gradient (Viterbi: crf_viterbi.cu).  Replaces the per-token Python loops of
 // /root/reference/flair/models/sequence_tagger_model.py (_viterbi_decode :1248-1304,
 // _forward_alg :1329-1394, _score_sentence :2544-2591, _calculate_loss :2448-2506,
 // _obtain_labels :1193-1210).
@@ -61,150 +61,6 @@ __device__ __forceinline__ int warp_max_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
-}
-
-// ------------------------------------------------------------------------------------------
-// Viterbi.  Bit-exact with the reference: fp32, c = v[k] + A[j][k] (one add), first maximal k,
-// then + e[j] (second add); terminal v + A[STOP], entries STOP/START forced to -1e12, first max.
-// Back-pointers: one byte per (step, tag) in shared memory; back-trace by lane 0 of the group.
-// Confidence = 1 / sum_k exp(v_t[k] - max_k v_t[k]) is computed G steps at a time from a
-// G x G staging tile (lane r finishes step r), so it costs ~L/G exps per step instead of a
-// cross-lane reduction per step.
-// ------------------------------------------------------------------------------------------
-constexpr int kVitUnroll = 8;
-
-template <int G>
-__global__ void __launch_bounds__(128)
-crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ pos,
-                   const int32_t *__restrict__ klen, const int32_t *__restrict__ slen,
-                   const float *__restrict__ trans, int B, int T, int L, int start, int stop,
-                   int x_idx, int32_t *__restrict__ tags_out, float *__restrict__ conf_out) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int SPW = 32 / G;
-    const int W = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / G, j = lane % G;
-    const int slot = warp * SPW + sub;
-    const int b = blockIdx.x * W * SPW + slot;
-    constexpr bool kPackBp = (G == 16);
-    const size_t bp_bytes = kPackBp ? (size_t)((T + 7) / 8) * G * 4 : (size_t)T * G;     // per sentence
-    uint8_t *bp = smem + (size_t)slot * bp_bytes;
-    float *vt = reinterpret_cast<float *>(smem + (size_t)W * SPW * bp_bytes) + slot * G * G;
-
-    const bool valid = b < B;
-    const int n = valid ? klen[b] : 0;
-    const int ns = valid ? slen[b] : 0;
-    const int nmax = warp_max_int(n);
-    const size_t rowbase = (size_t)(valid ? b : 0) * T;
-
-    // default fill (S-X padding of _obtain_labels :1202-1208, -1 beyond the sentence)
-    if (valid) {
-        for (int t = j; t < T; t += G) {
-            tags_out[rowbase + t] = (t < ns) ? x_idx : -1;
-            conf_out[rowbase + t] = (t < ns) ? 1.0f : 0.0f;
-        }
-    }
-    // transition row of this lane; padding lanes / columns are -inf so they never win
-    float A[G];
-#pragma unroll
-    for (int k = 0; k < G; ++k) A[k] = (j < L && k < L) ? trans[j * L + k] : -CUDART_INF_F;
-
-    float v = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
-    uint32_t bpw = 0;          // G == 16: eight 4-bit back-pointers per word, one word per lane per 8 steps
-    __syncwarp();
-
-    float e_cur[kVitUnroll], e_nxt[kVitUnroll];
-    auto load_block = [&](int i0, float (&dst)[kVitUnroll]) {
-#pragma unroll
-        for (int u = 0; u < kVitUnroll; ++u) {
-            const int i = i0 + u;
-            float ev = 0.0f;
-            if (i < n && j < L) {
-                const int t = pos ? __ldg(pos + rowbase + i) : i;
-                ev = __ldg(emis + (rowbase + t) * L + j);
-            }
-            dst[u] = ev;
-        }
-    };
-    load_block(0, e_cur);
-    for (int i0 = 0; i0 < nmax; i0 += kVitUnroll) {
-        load_block(i0 + kVitUnroll, e_nxt);
-#pragma unroll
-        for (int u = 0; u < kVitUnroll; ++u) {
-            const int i = i0 + u;
-            if (i < nmax) {   // warp-uniform
-                const bool act = i < n;
-                // c[k] = v[k] + A[j][k] for every k, then a 4/5-level tournament instead of a G-long dependent chain.
-                // Combining (lo, hi) takes hi only when hi.val > lo.val, so the FIRST maximal index still wins.
-                float cv[G];
-                int ci[G];
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    cv[k] = __shfl_sync(0xffffffffu, v, k, G) + A[k];
-                    ci[k] = k;
-                }
-#pragma unroll
-                for (int stride = 1; stride < G; stride <<= 1) {
-#pragma unroll
-                    for (int k = 0; k < G; k += 2 * stride) {
-                        if (cv[k + stride] > cv[k]) { cv[k] = cv[k + stride]; ci[k] = ci[k + stride]; }
-                    }
-                }
-                const float best = cv[0];
-                const int bk = ci[0];
-                if (act) {
-                    if (kPackBp) bpw |= (uint32_t)bk << (4 * (i & 7));
-                    else bp[(size_t)i * G + j] = (uint8_t)bk;
-                    v = best + e_cur[u];
-                }
-                if (kPackBp && ((i & 7) == 7 || i == nmax - 1)) {
-                    reinterpret_cast<uint32_t *>(bp)[(size_t)(i >> 3) * G + j] = bpw;
-                    bpw = 0;
-                }
-                vt[(i & (G - 1)) * G + j] = v;
-                if ((i & (G - 1)) == G - 1 || i == nmax - 1) {
-                    __syncwarp();
-                    const int s = (i & ~(G - 1)) + j;   // lane j finishes step s
-                    if (s <= i && s < n) {
-                        const float *r = vt + (s & (G - 1)) * G;
-                        float m = r[0];
-                        for (int k = 1; k < L; ++k) m = fmaxf(m, r[k]);
-                        float sum = 0.0f;
-                        for (int k = 0; k < L; ++k) sum += expf(r[k] - m);
-                        const int t = pos ? __ldg(pos + rowbase + s) : s;
-                        conf_out[rowbase + t] = 1.0f / sum;
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kVitUnroll; ++u) e_cur[u] = e_nxt[u];
-    }
-    // terminal (:1279-1287): first max of v + A[STOP], with STOP / START forced to -1e12
-    float term = -CUDART_INF_F;
-    if (j < L) {
-        term = v + trans[stop * L + j];
-        if (j == stop || j == start) term = kNeg;
-    }
-    int idx = j;
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, term, o, G);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o, G);
-        if (ov > term || (ov == term && oi < idx)) { term = ov; idx = oi; }
-    }
-    __syncwarp();
-    if (j == 0 && n > 0) {
-        int cur = idx;
-        for (int i = n - 1; i >= 0; --i) {
-            const int t = pos ? __ldg(pos + rowbase + i) : i;
-            tags_out[rowbase + t] = cur;
-            if (kPackBp) cur = (reinterpret_cast<const uint32_t *>(bp)[(size_t)(i >> 3) * G + cur] >> (4 * (i & 7))) & 15u;
-            else cur = bp[(size_t)i * G + cur];
-        }
-        // cur is START here for every well-formed transition matrix (reference assert :1303)
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -452,56 +308,6 @@ extern "C" int kbner_crf_compact(const uint8_t *keep, int B, int T, int32_t *pos
     crf_compact_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(keep, B, T, pos, klen);
     KBNER_CHECK_LAUNCH("crf_compact");
     return KBNER_OK;
-}
-
-template <int G>
-static int launch_viterbi(const float *emis, const int32_t *pos, const int32_t *klen,
-                          const int32_t *slen, const float *trans, int B, int T, int L, int start,
-                          int stop, int x_idx, int32_t *tags_out, float *conf_out, cudaStream_t st) {
-    constexpr int SPW = 32 / G;
-    int W = 4;
-    size_t smem = 0;
-    for (; W >= 1; W >>= 1) {
-        const size_t bp_bytes = (G == 16) ? (size_t)((T + 7) / 8) * G * 4 : (size_t)T * G;
-        smem = (size_t)W * SPW * (bp_bytes + (size_t)G * G * sizeof(float));
-        if (smem <= 200 * 1024) break;
-    }
-    if (W < 1) {
-        set_error("crf_viterbi: T=%d too long for the shared-memory back-pointer table", T);
-        return KBNER_EUNSUPPORTED;
-    }
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(crf_viterbi_kernel<G>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-        if (e != cudaSuccess) {
-            set_error("crf_viterbi: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return KBNER_ECUDA;
-        }
-        configured = 200 * 1024;
-    }
-    const int per_block = W * SPW;
-    const int blocks = (B + per_block - 1) / per_block;
-    crf_viterbi_kernel<G><<<blocks, W * 32, smem, st>>>(emis, pos, klen, slen, trans, B, T, L, start,
-                                                         stop, x_idx, tags_out, conf_out);
-    KBNER_CHECK_LAUNCH("crf_viterbi");
-    return KBNER_OK;
-}
-
-extern "C" int kbner_crf_viterbi(const float *emis, const int32_t *pos, const int32_t *klen,
-                                 const int32_t *slen, const float *trans, int B, int T, int L,
-                                 int start_idx, int stop_idx, int x_idx, int32_t *tags_out,
-                                 float *conf_out, void *stream) {
-    KBNER_CHECK_ARG(emis && klen && slen && trans && tags_out && conf_out, "crf_viterbi: null pointer");
-    KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_viterbi: need L in [2,32], got L=%d T=%d", L, T);
-    KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,
-                    "crf_viterbi: start/stop index out of range");
-    if (B == 0) return KBNER_OK;
-    if (L <= 16)
-        return launch_viterbi<16>(emis, pos, klen, slen, trans, B, T, L, start_idx, stop_idx, x_idx,
-                                  tags_out, conf_out, (cudaStream_t)stream);
-    return launch_viterbi<32>(emis, pos, klen, slen, trans, B, T, L, start_idx, stop_idx, x_idx,
-                              tags_out, conf_out, (cudaStream_t)stream);
 }
 
 extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const int32_t *pos,
