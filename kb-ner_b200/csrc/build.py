@@ -14,7 +14,7 @@ OUT = os.path.join(PKG, "libkbner_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 SOURCES = ["runtime.cu", "crf.cu", "crf_viterbi.cu", "elementwise.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "attention_tcgen05.cu", "attention_bwd_tcgen05.cu",
            "train_kernels.cu"]
-HEADERS = ["common.cuh", "tc_ptx.cuh", "cluster_ptx.cuh", "tma_host.cuh", os.path.join("..", "..", "include", "kbner_b200.h")]
+HEADERS = ["common.cuh", "crf_common.cuh", "tc_ptx.cuh", "cluster_ptx.cuh", "tma_host.cuh", os.path.join("..", "..", "include", "kbner_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -11,7 +11,7 @@
 // is the emissions read once ("CRF kernels").
 #include <math_constants.h>
 
-#include "common.cuh"
+#include "crf_common.cuh"
 
 namespace kbner {
 
@@ -65,86 +65,163 @@ __device__ __forceinline__ int warp_max_int(int v) {
 
 // ------------------------------------------------------------------------------------------
 // log Z and gold score.  The reference evaluates alpha'[j] = max_k x + log sum_k exp(x - max),
-// x = (e[j] + A[j][k]) + alpha[k]  (L^2 exps per step).  Here the same quantity is carried in a
-// normalised form  alpha_t[j] = S_t + ahat_t[j],  max_j ahat_t[j] = 0,  S_t accumulated in fp64:
-//   r[j]        = e[j] + rmax_j + log sum_k E[j][k] * exp(ahat[k]),   E[j][k] = exp(A[j][k] - rmax_j)
-//   ahat'[j]    = r[j] - max_j r[j],      S' = S + max_j r[j]
-// one exp per lane per step and an FMA per pair.  Keeping the O(T) magnitude in a separate fp64
-// scalar is what keeps the marginals of the backward pass accurate at T = 512 (alpha ~ 2000 would
-// otherwise carry ~1e-4 absolute error per step into exp(alpha + beta - logZ)).
+// x = (e[j] + A[j][k]) + alpha[k]  (L^2 exps per step).  Here the same quantity is carried as
+//   alpha_t[j] = S_t + a_t[j],   S_t accumulated in fp64,
+//   m = max_k a_t[k],  p[k] = exp(a_t[k]),  E[j][k] = exp(A[j][k] - rmax_j)
+//   a_{t+1}[j] = (e[j] + rmax_j) + log sum_k E[j][k] * p[k] - m,      S_{t+1} = S_t + m
+// (a_{t+1} <= e + rmax + log L: bounded by ONE step's growth, so p stays finite for |e + rmax| < 80).
+// Keeping the O(T) magnitude in a separate fp64 scalar is what keeps the marginals of the backward pass accurate at
+// T = 512 (alpha ~ 2000 would otherwise carry ~1e-4 absolute error per step into exp(alpha + beta - logZ)).
+//
+// Mapping (second design, same as the Viterbi kernel): one warp per block, Q lanes per sentence, lane j owns tag j; the
+// lane publishes the pair (a[j], exp(a[j])) in a two-row shared-memory tile (one STS.64, K/2 broadcast LDS.128 per
+// step) and EVERY lane takes the max of the gathered a itself, so a step needs one exchange, one exp, one log and no
+// cross-lane reduction; emissions stream through a cp.async ring.  The first design (16 shuffles + a 4-level shuffle max per step,
+// register-prefetched emissions) took 1075 cycles per step for one warp.
+// The normalised pair the backward pass consumes (alpha = a - max a, scale = S + max a) falls out one step later, when
+// the max of the stored vector has been computed anyway.
 // ------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(128)
+constexpr int kNllChunk = 16;     // steps per ring stage
+constexpr int kNllStages = 3;
+
+template <int Q, int K>
+struct NllCfg {
+    static constexpr int SPW = 32 / Q;
+    static constexpr int KP = (K + 3) / 4 * 4;
+    static constexpr int PADB = (SPW > 1) ? 128 / SPW : 0;     // see VitCfg: the sentences of a warp tile the banks
+    static __host__ __device__ int padded(int bytes) { return bytes + (PADB - bytes % 128 + 128) % 128; }
+    static __host__ __device__ int chunk_stride(int L) { return padded(kNllChunk * L * 4); }
+    static __host__ __device__ int tile_stride() { return padded(2 * 2 * KP * 4); }   // 2 rows of KP (a, p) pairs
+    static __host__ __device__ size_t ring_bytes(int L) { return (size_t)kNllStages * SPW * chunk_stride(L); }
+    static __host__ __device__ size_t smem_bytes(int L) { return ring_bytes(L) + (size_t)SPW * tile_stride() + 64; }
+};
+
+template <int Q, int K>
+__global__ void __launch_bounds__(32)
 crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
                    const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
-                   const float *__restrict__ trans, int B, int T, int L, int start, int stop,
+                   const float *__restrict__ trans, int B, int T, int L, int start, int stop, int vec16,
                    float *__restrict__ logz, float *__restrict__ gold, float *__restrict__ alpha_out,
                    double *__restrict__ ascale_out) {
-    constexpr int SPW = 32 / G;
-    const int W = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / G, j = lane % G;
-    const int b = (blockIdx.x * W + warp) * SPW + sub;
+    using C = NllCfg<Q, K>;
+    constexpr int SPW = C::SPW, KP = C::KP, CH = kNllChunk, NST = kNllStages, UN = 8;
+    extern __shared__ __align__(16) uint8_t smem[];
+    int *s_ctl = reinterpret_cast<int *>(smem + C::ring_bytes(L) + (size_t)SPW * C::tile_stride());
+    const int lane = threadIdx.x;
+    const int sub = lane / Q, j = lane % Q;
+    const int b = blockIdx.x * SPW + sub;
     const bool valid = b < B;
     const int n = valid ? klen[b] : 0;
-    const int nmax = warp_max_int(n);
     const size_t rowbase = (size_t)(valid ? b : 0) * T;
+    {
+        const int nm = warp_max_int(n);
+        if (lane == 0) s_ctl[0] = nm;
+    }
+    __syncwarp();
+    const int nmax = s_ctl[0];                     // block-uniform trip count: the warp stays converged
+    const int nchunks = (nmax + CH - 1) / CH;
+
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t chunk_b = C::chunk_stride(L), stage_b = SPW * chunk_b;
+    const uint32_t my_chunk_s = ring_s + sub * chunk_b;
+    const uint32_t tile_s = ring_s + (uint32_t)C::ring_bytes(L) + sub * C::tile_stride();
+    const float *my_row = emis + rowbase * L;
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            const uint32_t dst = my_chunk_s + (c % NST) * stage_b;
+            const int i0 = c * CH;
+            if (vec16) {
+                const int lim = n * L - i0 * L;
+                for (int r = j * 4; r < CH * L && r < lim; r += Q * 4) cp_async16(dst + r * 4, my_row + i0 * L + r);
+            } else {
+                for (int u = 0; u < CH && i0 + u < n; ++u) {
+                    const int t = pos ? __ldg(pos + rowbase + i0 + u) : i0 + u;
+                    for (int jj = j; jj < L; jj += Q) cp_async4(dst + (u * L + jj) * 4, my_row + (size_t)t * L + jj);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) issue(c);
 
     float rmax = -CUDART_INF_F;
     if (j < L)
         for (int k = 0; k < L; ++k) rmax = fmaxf(rmax, trans[j * L + k]);
-    float E[G];
+    float E[K];
 #pragma unroll
-    for (int k = 0; k < G; ++k) E[k] = (j < L && k < L) ? expf(trans[j * L + k] - rmax) : 0.0f;
+    for (int k = 0; k < K; ++k) E[k] = (j < L && k < L) ? expf(trans[j * L + k] - rmax) : 0.0f;
     if (j >= L) rmax = 0.0f;
 
-    float a = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;   // ahat_0 (max = 0)
+    float a = (j < L) ? ((j == start) ? 0.0f : kNeg) : -CUDART_INF_F;
     double S = 0.0;
-    constexpr int U = 4;
-    float e_cur[U], e_nxt[U];
-    auto load_block = [&](int i0, float (&dst)[U]) {
+    // tile: two rows of KP (a, exp(a)) pairs, (-inf, 0) in the padding columns; step i writes row i & 1, reads the other
+    constexpr uint32_t kRow = 2 * KP * 4;
+    for (int x = j; x < 2 * KP; x += Q) sts_v2(tile_s + x * 8, -CUDART_INF_F, 0.0f);
+    __syncwarp();
+    if (j < KP) sts_v2(tile_s + kRow + j * 8, a, (j < L) ? expf(a) : 0.0f);
+    __syncwarp();
+    const uint32_t eoff = sub * chunk_b + min(j, L - 1) * 4;
+    const uint32_t L4 = L * 4;
+
+    // top of step i: gather (alpha_i, exp alpha_i), the max, and -- one step late -- the normalised record of step i - 1
+    auto gather = [&](int row, int i, float (&pk)[K]) -> float {
+        float ak[K];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u;
-            float ev = 0.0f;
-            if (i < n && j < L) {
-                const int t = pos ? __ldg(pos + rowbase + i) : i;
-                ev = __ldg(emis + (rowbase + t) * L + j);
-            }
-            dst[u] = ev;
+        for (int k2 = 0; k2 < (K + 1) / 2; ++k2) {
+            const float4 x = lds_v4(tile_s + row * kRow + k2 * 16);
+            ak[2 * k2] = x.x; pk[2 * k2] = x.y;
+            if (2 * k2 + 1 < K) { ak[2 * k2 + 1] = x.z; pk[2 * k2 + 1] = x.w; }
         }
+        const float m = max_tree<K>(ak);
+        if (alpha_out && i >= 1 && i - 1 < n) {
+            if (j < L) alpha_out[(rowbase + i - 1) * L + j] = a - m;
+            if (j == 0) ascale_out[rowbase + i - 1] = S + (double)m;
+        }
+        return m;
     };
-    load_block(0, e_cur);
-    for (int i0 = 0; i0 < nmax; i0 += U) {
-        load_block(i0 + U, e_nxt);
+
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        issue(c + NST - 1);
+        cp_async_wait<NST - 1>();
+        __syncwarp();
+        const uint32_t st_s = ring_s + (c % NST) * stage_b;
+#pragma unroll 1
+        for (int h = 0; h < CH / UN; ++h) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u;
-            if (i < nmax) {
-                const float p = expf(a);
-                float s = 0.0f;
+            for (int u = 0; u < UN; ++u) {
+                const int i = c * CH + h * UN + u;
+                const float e = lds_f32(st_s + eoff + (h * UN + u) * L4);
+                float pk[K];
+                const float m = gather((u & 1) ^ 1, i, pk);
+                float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int k = 0; k < G; ++k) s = fmaf(E[k], __shfl_sync(0xffffffffu, p, k, G), s);
-                const float r = (j < L) ? (e_cur[u] + rmax) + logf(s) : -CUDART_INF_F;
-                const float m = group_max<G>(r);
+                for (int k = 0; k < K; ++k) s4[k & 3] = fmaf(E[k], pk[k], s4[k & 3]);
+                const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                const float r = (j < L) ? ((e + rmax) + __logf(s)) - m : -CUDART_INF_F;   // lg2.approx: |err| < 2e-7
                 if (i < n) {
-                    a = r - m;
+                    a = r;
                     S += (double)m;
-                    if (alpha_out && j < L) alpha_out[(rowbase + i) * L + j] = a;
-                    if (ascale_out && j == 0) ascale_out[rowbase + i] = S;
                 }
+                if (j < KP) sts_v2(tile_s + (u & 1) * kRow + j * 8, a, ex2_fast(a * 1.4426950408889634f));
+                __syncwarp();
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) e_cur[u] = e_nxt[u];
     }
+    cp_async_wait<0>();
+    {
+        float pk[K];
+        gather(1, nchunks * CH, pk);        // record of the last step of full-length sentences (row 1: CH is even)
+    }
+
     // terminal: log_sum_exp_batch(alpha_len + A[STOP])  (:1381-1392)
     const float x = (j < L) ? a + trans[stop * L + j] : -CUDART_INF_F;
-    const float M2 = group_max<G>(x);
-    const float s2 = group_sum<G>(expf(x - M2));
+    const float M2 = group_max<Q>(x);
+    const float s2 = group_sum<Q>(expf(x - M2));
     // gold score (:2544-2591): lanes stride over the kept tokens
     float g = 0.0f;
-    for (int i = j; i < n; i += G) {
+    for (int i = j; i < n; i += Q) {
         const int t = pos ? pos[rowbase + i] : i;
         const int y = tags[rowbase + t];
         int prev = start;
@@ -154,7 +231,7 @@ crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
         }
         g += emis[(rowbase + t) * L + y] + trans[y * L + prev];
     }
-    g = group_sum<G>(g);
+    g = group_sum<Q>(g);
     if (valid && j == 0) {
         int last = start;
         if (n > 0) {
@@ -320,16 +397,16 @@ extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const i
                     "crf_nll_fwd: start/stop index out of range");
     KBNER_CHECK_ARG((alpha == nullptr) == (alpha_scale == nullptr), "crf_nll_fwd: alpha and alpha_scale go together");
     if (B == 0) return KBNER_OK;
-    const int W = 4;
     cudaStream_t st = (cudaStream_t)stream;
-    if (L <= 16) {
-        const int per_block = W * 2;
-        crf_nll_fwd_kernel<16><<<(B + per_block - 1) / per_block, W * 32, 0, st>>>(
-            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha, alpha_scale);
-    } else {
-        crf_nll_fwd_kernel<32><<<(B + W - 1) / W, W * 32, 0, st>>>(
-            emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, logz, gold, alpha, alpha_scale);
-    }
+    const int vec16 = (pos == nullptr && ((size_t)T * L) % 4 == 0 && (reinterpret_cast<uintptr_t>(emis) & 15) == 0) ? 1 : 0;
+#define KBNER_NLL(Q, K)                                                                                             \
+    crf_nll_fwd_kernel<Q, K><<<(B + NllCfg<Q, K>::SPW - 1) / NllCfg<Q, K>::SPW, 32, NllCfg<Q, K>::smem_bytes(L), st>>>( \
+        emis, tags, pos, klen, trans, B, T, L, start_idx, stop_idx, vec16, logz, gold, alpha, alpha_scale)
+    if (L == 13) KBNER_NLL(16, 13);
+    else if (L <= 16) KBNER_NLL(16, 16);
+    else if (L == 29) KBNER_NLL(32, 29);
+    else KBNER_NLL(32, 32);
+#undef KBNER_NLL
     KBNER_CHECK_LAUNCH("crf_nll_fwd");
     return KBNER_OK;
 }

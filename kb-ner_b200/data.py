@@ -168,30 +168,41 @@ class Sentence:
         for t in self.tokens:
             t.clear_embeddings(names)
 
-    def get_spans(self, tag_type: str):
-        """(type, start, end_exclusive, text) of every BIOES/BIO span (flair/data.py:455-532 semantics:
-        B-/S- open a span, a type change opens a new one, O closes)."""
-        spans, cur, cur_type = [], [], None
+    def get_spans(self, tag_type: str, min_score=-1):
+        """(type, start, end_exclusive, text) of every span, with the reference's rules (flair/data.py:455-532), which
+        matter for MALFORMED predicted sequences: anything that is not B-/I-/O-/E-/S- is a single-token tag; only B- and
+        S- (or a type change right after an S-) open a new span -- an E- does not close one and an I- of another type
+        does not split one; a span's type is the weighted majority of its tags (weight 1.1 for the tag that opened it,
+        first-seen wins ties); spans whose mean tag confidence is not above min_score are dropped."""
+        spans, cur, weights = [], [], {}
+        prev_prefix, prev_type = "O-", ""
 
-        def close():
-            nonlocal cur, cur_type
+        def emit():
+            nonlocal cur, weights
             if cur:
-                spans.append((cur_type, cur[0], cur[-1] + 1, " ".join(self.tokens[i].text for i in cur)))
-            cur, cur_type = [], None
+                scores = [self.tokens[i].get_tag(tag_type).score for i in cur]
+                if sum(scores) / len(scores) > min_score:
+                    best = max(weights.values())
+                    typ = next(t for t, w in weights.items() if w == best)      # dicts keep insertion order
+                    spans.append((typ, cur[0], cur[-1] + 1, " ".join(self.tokens[i].text for i in cur)))
+            cur, weights = [], {}
 
         for i, tok in enumerate(self.tokens):
             v = tok.get_tag(tag_type).value
-            if v in ("", "O"):
-                close()
-                continue
-            pre, typ = (v[:2], v[2:]) if len(v) > 2 and v[1] == "-" else ("I-", v)
-            if pre in ("B-", "S-") or typ != cur_type:
-                close()
-            cur.append(i)
-            cur_type = typ
-            if pre in ("S-", "E-"):
-                close()
-        close()
+            if v == "" or v == "O":
+                v = "O-"
+            if v[0:2] not in ("B-", "I-", "O-", "E-", "S-"):
+                v = "S-" + v
+            prefix, typ = v[0:2], v[2:]
+            in_span = prefix != "O-"
+            opens = prefix in ("B-", "S-") or (prev_prefix == "S-" and prev_type != typ and in_span)
+            if opens or not in_span:
+                emit()
+            if in_span:
+                cur.append(i)
+                weights[typ] = weights.get(typ, 0.0) + (1.1 if opens else 1.0)
+            prev_prefix, prev_type = prefix, typ
+        emit()
         return spans
 
     def __getitem__(self, i):

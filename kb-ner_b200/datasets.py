@@ -220,6 +220,33 @@ class ColumnCorpus(Corpus):
         return a, b
 
 
+class ListCorpus(Corpus):
+    """Several corpora side by side (flair/list_data.py:2-19): `train_list / dev_list / test_list` keep the per-corpus
+    splits (final_test reports per corpus, `targets` names them), `train / dev / test` are their concatenations.
+    Also accepts flat lists of sentences (one anonymous corpus)."""
+
+    def __init__(self, train, dev=None, test=None, name: str = "listcorpus", targets=None):
+        def as_lists(x):
+            x = list(x) if x is not None else []
+            if x and hasattr(x[0], "tokens"):          # a flat list of sentences
+                return [x]
+            return [list(d) for d in x]
+        self.train_list, self.dev_list, self.test_list = as_lists(train), as_lists(dev), as_lists(test)
+        cat = lambda ls: [s for d in ls for s in d]
+        super().__init__(cat(self.train_list), cat(self.dev_list), cat(self.test_list), name=name)
+        self.targets = list(targets) if targets is not None else ["corpus-%d" % i for i in range(len(self.train_list))]
+
+    def get_train_full_tokenset(self, max_tokens: int = -1, min_freq: int = -1, attr: str = "text"):
+        """[tokens of train+test sorted by frequency, character set] (flair/data.py:1018-1050 as the config parser calls it;
+        only the FastWord / character embeddings, which are outside the hot path, consume it)."""
+        from collections import Counter
+        cnt = Counter(getattr(t, attr, t.text) for s in self.train + self.test for t in s.tokens)
+        toks = [w for w, c in cnt.most_common() if c > min_freq]
+        if max_tokens > 0:
+            toks = toks[:max_tokens]
+        return [toks, sorted({ch for w in toks for ch in w})]
+
+
 class ColumnDataLoader:
     """Batch assembler (flair/custom_data_loader.py:25-149): sentences stably sorted by WORD count (use_bert=False is what
     the trainer passes for TransformerWordEmbeddings), then chunked either by sentence count (`sentence_level_batch`, the
@@ -261,6 +288,28 @@ class ColumnDataLoader:
         if curlen > 0:
             res.append(BatchedData(cur))
         return res
+
+    def assign_tags(self, tag_type: str, tag_dictionary, teacher_input=None, grouped_data: bool = False):
+        """Gold tag indices once per sentence (flair/custom_data_loader.py:199-382, the part the CRF loss reads): every
+        sentence gets `<tag_type>_tags` (int64, CPU), every batch a zero-padded `[B, T]` tensor of the same name
+        (0 = '<unk>' is the padding value, Appendix B.13)."""
+        import torch
+        if grouped_data:
+            raise NotImplementedError("grouped_data batches are not used by the KB-NER configs")
+        batches = [teacher_input] if teacher_input is not None else self.data
+        for batch in batches:
+            rows = []
+            for s in batch:
+                idx = torch.tensor([tag_dictionary.get_idx_for_item(t.get_tag(tag_type).value) for t in s.tokens],
+                                   dtype=torch.int64)
+                setattr(s, tag_type + "_tags", idx)
+                rows.append(idx)
+            T = max((r.numel() for r in rows), default=0)
+            padded = torch.zeros((len(rows), T), dtype=torch.int64)
+            for i, r in enumerate(rows):
+                padded[i, :r.numel()] = r
+            setattr(batch, tag_type + "_tags", padded)
+        return self
 
     def reshuffle(self):
         random.shuffle(self.data)

@@ -33,6 +33,7 @@ class SyntheticTokenizer:
     of every word carries the U+2581 prefix; ids are a stable hash into [3, vocab).  Exposes exactly the
     members the reference touches (embeddings.py:2951-2966, :3139-3181)."""
 
+    FILE = "synthetic_tokenizer.json"
     bos_token, eos_token, pad_token, unk_token = "<s>", "</s>", "<pad>", "<unk>"
     _bos_token, _eos_token, _sep_token, _cls_token = "<s>", "</s>", "</s>", "<s>"
     bos_token_id, pad_token_id, eos_token_id, unk_token_id = 0, 1, 2, 3
@@ -41,6 +42,23 @@ class SyntheticTokenizer:
         self.vocab_size = vocab_size
         self.piece_len = piece_len
         self.model_max_length = model_max_length
+
+    def save_pretrained(self, path):
+        """Written next to the encoder by `save_finetuned_embedding` (finetune_trainer.py:1297); a directory holding this
+        file loads back as a SyntheticTokenizer."""
+        import json
+        import os
+        os.makedirs(str(path), exist_ok=True)
+        with open(os.path.join(str(path), self.FILE), "w") as f:
+            json.dump({"vocab_size": self.vocab_size, "piece_len": self.piece_len,
+                       "model_max_length": self.model_max_length}, f)
+
+    @classmethod
+    def from_pretrained(cls, path):
+        import json
+        import os
+        with open(os.path.join(str(path), cls.FILE)) as f:
+            return cls(**json.load(f))
 
     def tokenize(self, text: str) -> List[str]:
         out = []
@@ -115,6 +133,8 @@ class TransformerWordEmbeddings(torch.nn.Module):
                 import os
                 if os.path.isdir(name) and os.path.exists(os.path.join(name, "config.json")):
                     self.model = XLMRobertaEncoderB200.from_pretrained(name)
+                    if tokenizer is None and os.path.exists(os.path.join(name, SyntheticTokenizer.FILE)):
+                        tokenizer = SyntheticTokenizer.from_pretrained(name)
                 else:
                     config = EncoderConfig.xlmr_base() if "base" in name else EncoderConfig.xlmr_large()
                     config.name = name

@@ -19,6 +19,7 @@ import torch
 
 from . import ops
 from .data import BatchedData, Dictionary, Label, LabelSeq, Sentence
+from .training_utils import Metric, Result, span_counts, store_embeddings
 
 log = logging.getLogger("kbner_b200")
 
@@ -296,11 +297,10 @@ class SequenceTagger(torch.nn.Module):
     @torch.no_grad()
     def evaluate(self, data_loader, out_path=None, embeddings_storage_mode: str = "none", prediction_mode=False,
                  speed_test=False):
-        """-> (Result-like dict, eval_loss).  Span micro-F1 with the remove-X filter (:2644-2686);
-        P/R/F rounded to 4 dp like Metric (training_utils.py:67-93)."""
+        """-> (Result, eval_loss) like the reference (:2593-2729): per-class span counts in a Metric, the remove-X filter
+        (:2653-2672) when self.remove_x, the prediction file "text gold pred score" streamed to out_path."""
         self.eval()
-        eval_loss, batches, lines = 0.0, 0, []
-        tp = fp = fn = 0
+        eval_loss, batches = 0.0, 0
         n_sent, t0 = 0, time.time()
         if speed_test:
             # forward + _obtain_labels only (:2611-2612, :2698-2700), software-pipelined: the Label lists of batch i
@@ -320,43 +320,34 @@ class SequenceTagger(torch.nn.Module):
             dt = time.time() - t0
             log.info("speed_test: %d sentences, %.2f sentences/s", n_sent, n_sent / max(dt, 1e-9))
             return {"sentences_per_sec": n_sent / max(dt, 1e-9), "sentences": n_sent}, 0.0
-        for batch in data_loader:
-            if not isinstance(batch, BatchedData):
-                batch = BatchedData(batch)
-            batches += 1
-            n_sent += len(batch)
-            features = self.forward(batch, prediction_mode=prediction_mode)
-            if not speed_test:
+        metric = Metric("Evaluation")
+        outfile = open(out_path, "w", encoding="utf-8") if out_path is not None else None
+        try:
+            for batch in data_loader:
+                if not isinstance(batch, BatchedData):
+                    batch = BatchedData(batch)
+                batches += 1
+                n_sent += len(batch)
+                features = self.forward(batch, prediction_mode=prediction_mode)
                 eval_loss += float(self._calculate_loss(features, batch, self.mask))     # (:2619-2621)
-            tags, _ = self._obtain_labels(features, batch)
-            if speed_test:
-                continue
-            for s, st in zip(batch, tags):
-                gold_x = [tok.get_tag(self.tag_type).value == "S-X" for tok in s.tokens]
-                gold_spans = [(ty, a, e, tx) for (ty, a, e, tx) in s.get_spans(self.tag_type) if ty != "X"]
-                for tok, lab in zip(s.tokens, st):
-                    tok.add_tag_label("predicted", lab)
-                    lines.append("%s %s %s %s\n" % (tok.text, tok.get_tag(self.tag_type).value, lab.value, lab.score))
-                lines.append("\n")
-                pred_spans = [(ty, a, e, tx) for (ty, a, e, tx) in s.get_spans("predicted")
-                              if ty != "X" and not any(gold_x[a:e])]
-                gs, ps = set(gold_spans), set(pred_spans)
-                tp += len(gs & ps)
-                fp += len(ps - gs)
-                fn += len(gs - ps)
-        if speed_test:
-            torch.cuda.synchronize()
-            dt = time.time() - t0
-            log.info("speed_test: %d sentences, %.2f sentences/s", n_sent, n_sent / max(dt, 1e-9))
-            return {"sentences_per_sec": n_sent / max(dt, 1e-9)}, 0.0
-        if out_path is not None:
-            with open(out_path, "w", encoding="utf-8") as f:
-                f.write("".join(lines))
-        p = round(tp / (tp + fp), 4) if tp + fp else 0.0
-        r = round(tp / (tp + fn), 4) if tp + fn else 0.0
-        f1 = round(2 * p * r / (p + r), 4) if p + r else 0.0
-        result = {"main_score": f1, "precision": p, "recall": r, "tp": tp, "fp": fp, "fn": fn,
-                  "log_line": "%s\t%s\t%s" % (p, r, f1)}
+                tags, _ = self._obtain_labels(features, batch)
+                for s, st in zip(batch, tags):
+                    for tok, lab in zip(s.tokens, st):
+                        tok.add_tag_label("predicted", lab)
+                        if outfile is not None:                                         # "text gold pred score" (:2626-2643)
+                            outfile.write("%s %s %s %s\n" % (tok.text, tok.get_tag(self.tag_type).value, lab.value, lab.score))
+                    if outfile is not None:
+                        outfile.write("\n")
+                    gold_x = [tok.get_tag(self.tag_type).value == "S-X" for tok in s.tokens] if self.remove_x else None
+                    span_counts(metric, s.get_spans(self.tag_type), s.get_spans("predicted"), gold_x, self.remove_x)
+                store_embeddings(batch, embeddings_storage_mode)
+                if embeddings_storage_mode == "none" and hasattr(batch, "features"):
+                    batch.features = {}
+        finally:
+            if outfile is not None:
+                outfile.close()
+        result = metric.to_result()
+        result.metric = metric
         return result, eval_loss / max(batches, 1)
 
     # ---- checkpoint (:435-477, :1824-1897; flair/nn.py:60-108) ----------------------------------------------

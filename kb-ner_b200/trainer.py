@@ -34,6 +34,7 @@ import torch
 from .data import BatchedData
 from .distributed import allreduce_counts, shard_indices
 from .optim import build_reference_optimizer
+from .training_utils import Metric
 
 log = logging.getLogger("kbner_b200")
 
@@ -47,8 +48,11 @@ def make_batches(sentences, mini_batch_size: int, sort: bool = True) -> List[Bat
 
 class ModelFinetuner:
     def __init__(self, model, teachers=None, corpus=None, optimizer=None, epoch: int = 0, config=None,
-                 distill_mode: bool = False, sentence_level_batch: bool = True, **kwargs):
-        if distill_mode or teachers:
+                 distill_mode: bool = False, sentence_level_batch: bool = True, is_test: bool = False,
+                 professors=None, **kwargs):
+        """Positional order (model, teachers, corpus) and the `config=..., **config['ModelFinetuner'], is_test=...`
+        keywords are what train.py passes (train.py:127-133; finetune_trainer.py:51-75)."""
+        if distill_mode or teachers or professors:
             raise NotImplementedError("knowledge distillation is outside the hot path (config: distill_mode false)")
         self.model = model
         self.corpus = corpus
@@ -56,13 +60,21 @@ class ModelFinetuner:
         self.epoch = epoch
         self.optimizer = optimizer
         self.sentence_level_batch = sentence_level_batch
+        self.is_test = is_test
+        self.use_bert = False                 # 'bert' is not in "TransformerWordEmbeddings" (finetune_trainer.py:304-309)
+        self.bert_tokenizer = None
+        self.embeddings_storage_mode = "none"
 
     # ------------------------------------------------------------------------------------------------------------
     def train(self, base_path, learning_rate: float = 5e-5, mini_batch_size: int = 32, eval_mini_batch_size: int = None,
               max_epochs: int = 100, gradient_accumulation_steps: int = 1, lr_rate: float = 1.0,
               train_with_dev: bool = False, shuffle: bool = True, true_reshuffle: bool = False,
               save_final_model: bool = True, fine_tune_mode: bool = True, embeddings_storage_mode: str = "none",
-              max_grad_norm: float = 5.0, seed: int = 1, log_every: int = 10, **kwargs):
+              max_grad_norm: float = 5.0, seed: int = 1, log_every: int = 10, select_model_by_macro: bool = False,
+              save_finetuned_embedding: bool = False, monitor_test: bool = False, use_warmup: bool = False, **kwargs):
+        """Keywords = the YAML `train:` block (Appendix B.12: unknown keys land in **kwargs like in the reference)."""
+        if use_warmup:
+            raise NotImplementedError("use_warmup: every KB-NER config trains with 0 warm-up steps (finetune_trainer.py:679-688)")
         os.makedirs(str(base_path), exist_ok=True)
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
@@ -112,15 +124,33 @@ class ModelFinetuner:
             entry = {"epoch": epoch + 1, "train_samples_per_sec": seen * world / max(time.time() - t0, 1e-9)}
             if not train_with_dev and getattr(self.corpus, "dev", None):
                 result, dev_loss = self.evaluate_split(self.corpus.dev, eval_mini_batch_size or mini_batch_size)
-                entry.update(dev_f1=result["main_score"], dev_loss=dev_loss)
-                if result["main_score"] > best and rank == 0:
-                    best = result["main_score"]
+                score = result.macro_score if select_model_by_macro else result.main_score     # (:1115-1118)
+                entry.update(dev_f1=result.main_score, dev_macro_f1=result.macro_score, dev_loss=dev_loss)
+                if score > best and rank == 0:
+                    best = score
                     model.save(os.path.join(str(base_path), "best-model.pt"))
+                    if save_finetuned_embedding:
+                        self.save_finetuned_embeddings(base_path)
+            if monitor_test and getattr(self.corpus, "test", None):
+                result, test_loss = self.evaluate_split(self.corpus.test, eval_mini_batch_size or mini_batch_size)
+                entry.update(test_f1=result.main_score, test_loss=test_loss)
             history.append(entry)
             log.info("EPOCH %d done: %s", epoch + 1, entry)
         if save_final_model and rank == 0:
             model.save(os.path.join(str(base_path), "final-model.pt"))
+            if save_finetuned_embedding and (train_with_dev or not getattr(self.corpus, "dev", None)):
+                self.save_finetuned_embeddings(base_path)
         return {"history": history, "best_dev_f1": best}
+
+    def save_finetuned_embeddings(self, base_path):
+        """tokenizer + encoder of every fine-tuned embedding under base_path/<last path component of its name>
+        (finetune_trainer.py:1290-1298; also what `train.py --save_embedding` writes)."""
+        for e in self.model.embeddings.embeddings:
+            if getattr(e, "fine_tune", False):
+                out = os.path.join(str(base_path), str(e.name).rstrip("/").split("/")[-1])
+                os.makedirs(out, exist_ok=True)
+                e.tokenizer.save_pretrained(out)
+                e.model.save_pretrained(out)
 
     # ------------------------------------------------------------------------------------------------------------
     def evaluate_split(self, sentences, mini_batch_size, out_path=None):
@@ -132,11 +162,12 @@ class ModelFinetuner:
         mine = [batches[i] for i in shard_indices(len(batches), rank, world, pad=False)]
         result, loss = self.model.evaluate(mine, out_path=out_path, embeddings_storage_mode="none")
         if world > 1:
-            tp, fp, fn = allreduce_counts([result["tp"], result["fp"], result["fn"]])
-            p = round(tp / (tp + fp), 4) if tp + fp else 0.0
-            r = round(tp / (tp + fn), 4) if tp + fn else 0.0
-            result.update(tp=tp, fp=fp, fn=fn, precision=p, recall=r,
-                          main_score=round(2 * p * r / (p + r), 4) if p + r else 0.0)
+            # every rank needs the same class order: tag types come from the shared tag dictionary
+            classes = sorted({it.split("-", 1)[1] for it in self.model.tag_dictionary.get_items() if "-" in it})
+            vec = allreduce_counts(result.metric.to_vector(classes))
+            merged = Metric.from_vector("Evaluation", classes, vec)
+            result = merged.to_result()
+            result.metric = merged
         return result, loss
 
     def final_test(self, base_path, eval_mini_batch_size: int = 32, overall_test: bool = True, quiet_mode: bool = False,
@@ -153,12 +184,22 @@ class ModelFinetuner:
         self.model.eval()
         result, loss = self.evaluate_split(self.corpus.test, eval_mini_batch_size,
                                            out_path=os.path.join(str(base_path), "test.tsv"))
-        log.info("final test: %s", result.get("log_line"))
-        return result["main_score"]
+        log.info("final test: %s", result.log_line)
+        if not quiet_mode:
+            log.info(result.detailed_results)
+        # per-corpus scores when several corpora were concatenated (:2216-2282)
+        lists = getattr(self.corpus, "test_list", None)
+        if overall_test and lists and len(lists) > 1:
+            for name, sub in zip(self.corpus.targets, lists):
+                if len(sub) == 0:
+                    continue
+                r, _ = self.evaluate_split(sub, eval_mini_batch_size,
+                                           out_path=os.path.join(str(base_path), "%s-test.tsv" % name))
+                log.info("%s\t%s\t%s", name, r.log_line, r.macro_score)
+        elif quiet_mode:
+            print("Average", end=" ")
+            print(result.main_score, end=" ")
+        return result.main_score
 
 
-class ListCorpus:
-    """train / dev / test lists of sentences (flair/list_data.py:2-19, reduced to what the trainer reads)."""
-
-    def __init__(self, train, dev=None, test=None):
-        self.train, self.dev, self.test = list(train), list(dev or []), list(test or [])
+from .datasets import ListCorpus  # noqa: E402,F401  (kept importable from here: the first version lived in this module)
