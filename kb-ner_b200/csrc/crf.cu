@@ -244,33 +244,78 @@ crf_nll_fwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
 }
 
 // ------------------------------------------------------------------------------------------
-// gradient of sum_b w[b] (logZ_b - gold_b).  Reverse (beta) recursion in the same normalised form
-// (beta_t = Sb_t + bhat_t, Sb in fp64); unary marginals -> d_emis, pairwise marginals accumulated
-// per lane as  acc[j][k] += c * q_j * a_k   (dT[j][k] = E[j][k] * acc[j][k]), persistent over
-// sentences, reduced through shared memory, one global atomic set per block.
+// gradient of sum_b w[b] (logZ_b - gold_b).  Reverse (beta) recursion in the same form as the forward pass:
+//   beta_i[k] = Sb_i + b_i[k],  u[j] = e_i[j] + b_{i+1}[j] + rmax_j,  M = max_j u[j],
+//   b_i[k] = log sum_j E[j][k] * exp(u[j]) - M,   Sb_i = Sb_{i+1} + M          (Sb in fp64)
+// unary marginals -> d_emis; pairwise marginals accumulated per lane as  acc[j][k] += c * exp(u[j]) * exp(ahat_i[k])
+// (dT[j][k] = E[j][k] * acc[j][k], c = w * exp(Sa_i + Sb_{i+1} - logZ)), persistent over the sentences of a block.
+//
+// Mapping (second design): one warp per block, Q lanes per sentence, lane j owns tag j and publishes the triple
+// (u[j], exp u[j], exp ahat_i[j]) in a two-row shared-memory tile (one STS.128, K broadcast LDS.128 per step); every
+// lane takes the max itself, so a step is ONE exchange.  Everything a step reads from global memory -- the emission row
+// (through the remove-X index list), the stored alpha row and scale, the gold tags -- is staged by cp.async into a
+// 3-stage ring, 16 steps per stage, walked backwards; lane q of a sentence fetches entry q of a chunk and the index-list
+// entries it needs are prefetched one chunk ahead.  The first design loaded all of this inside the step (a global
+// round trip on the dependent chain of every step) and reduced twice per step across lanes with shuffles.
 // ------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(128)
+template <int Q, int K>
+struct NllBwdCfg {
+    static constexpr int SPW = 32 / Q;
+    static constexpr int CH = 16, NST = 3;
+    static constexpr int PADB = (SPW > 1) ? 128 / SPW : 0;
+    static __host__ __device__ int padded(int bytes) { return bytes + (PADB - bytes % 128 + 128) % 128; }
+    // per sentence and stage: SAP[CH] f64 | E[CH][L] f32 | AP[CH][L] f32 | YP[CH] i32 | TL[CH] i32
+    static __host__ __device__ int off_e() { return CH * 8; }
+    static __host__ __device__ int off_ap(int L) { return off_e() + CH * L * 4; }
+    static __host__ __device__ int off_yp(int L) { return off_ap(L) + CH * L * 4; }
+    static __host__ __device__ int off_tl(int L) { return off_yp(L) + CH * 4; }
+    static __host__ __device__ int chunk_stride(int L) { return padded(off_tl(L) + CH * 4); }
+    static __host__ __device__ int tile_stride() { return padded(2 * K * 16); }
+    static __host__ __device__ size_t ring_bytes(int L) { return (size_t)NST * SPW * chunk_stride(L); }
+    static __host__ __device__ size_t dt_off(int L) { return ring_bytes(L) + (size_t)SPW * tile_stride(); }
+    static __host__ __device__ size_t smem_bytes(int L) { return dt_off(L) + (size_t)L * L * 4 + 64; }
+};
+
+__device__ __forceinline__ void cp_async8(uint32_t dst_s, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+template <int Q, int K>
+__global__ void __launch_bounds__(32)
 crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ tags,
                    const int32_t *__restrict__ pos, const int32_t *__restrict__ klen,
                    const float *__restrict__ trans, const float *__restrict__ alpha,
                    const double *__restrict__ ascale, const float *__restrict__ w, int B, int T, int L,
                    int start, int stop, float *__restrict__ d_emis, float *__restrict__ d_trans) {
-    __shared__ float s_dt[32 * 32];
-    constexpr int SPW = 32 / G;
-    const int W = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / G, j = lane % G;
-    for (int i = threadIdx.x; i < L * L; i += blockDim.x) s_dt[i] = 0.0f;
-    __syncthreads();
+    using C = NllBwdCfg<Q, K>;
+    constexpr int SPW = C::SPW, CH = C::CH, NST = C::NST;
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *s_dt = reinterpret_cast<float *>(smem + C::dt_off(L));
+    int *s_ctl = reinterpret_cast<int *>(smem + C::dt_off(L) + (size_t)L * L * 4);
+    const int lane = threadIdx.x;
+    const int sub = lane / Q, j = lane % Q;
+    for (int i = lane; i < L * L; i += 32) s_dt[i] = 0.0f;
 
     float rmax = -CUDART_INF_F;
     if (j < L)
         for (int k = 0; k < L; ++k) rmax = fmaxf(rmax, trans[j * L + k]);
     // Ecol[jj] = E[jj][j]: column j of the row-normalised exp(A)
-    float Ecol[G];
+    float Ecol[K];
 #pragma unroll
-    for (int jj = 0; jj < G; ++jj) {
+    for (int jj = 0; jj < K; ++jj) {
         float v = 0.0f;
         if (j < L && jj < L) {
             float rm = -CUDART_INF_F;
@@ -280,95 +325,160 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
         Ecol[jj] = v;
     }
     if (j >= L) rmax = 0.0f;
-    float acc[G];
+    float acc[K];
 #pragma unroll
-    for (int k = 0; k < G; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < K; ++k) acc[k] = 0.0f;
 
-    const int groups_total = gridDim.x * W * SPW;
-    const int g0 = (blockIdx.x * W + warp) * SPW + sub;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t chunk_b = C::chunk_stride(L), stage_b = SPW * chunk_b;
+    const uint32_t my_chunk_s = ring_s + sub * chunk_b;
+    const uint32_t tile_s = ring_s + (uint32_t)C::ring_bytes(L) + sub * C::tile_stride();
+    const uint32_t oE = C::off_e(), oAP = C::off_ap(L), oYP = C::off_yp(L), oTL = C::off_tl(L);
+    const uint32_t jc4 = min(j, L - 1) * 4, L4 = L * 4;
+    constexpr uint32_t kRow = K * 16;
+
+    const int groups_total = gridDim.x * SPW;
     const int iters = (B + groups_total - 1) / groups_total;
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const int b = g0 + it * groups_total;
+        const int b = (blockIdx.x + it * gridDim.x) * SPW + sub;
         const bool valid = b < B;
         const int n = valid ? klen[b] : 0;
-        const int nmax = warp_max_int(n);
         const size_t rowbase = (size_t)(valid ? b : 0) * T;
         const float wb = valid ? w[b] : 0.0f;
-        if (nmax == 0) continue;   // warp-uniform
+        __syncwarp();
+        {
+            const int nm = warp_max_int(n);
+            if (lane == 0) s_ctl[0] = nm;
+        }
+        __syncwarp();
+        const int nmax = s_ctl[0];               // block-uniform
+        if (nmax == 0) continue;
+        const int nchunks = (nmax + CH - 1) / CH;
 
         // beta_n[k] = A[STOP][k], normalised; logZ re-derived in fp64 from the stored alpha
         const float astop = (j < L) ? trans[stop * L + j] : -CUDART_INF_F;
-        const float mb0 = group_max<G>(astop);
-        float beta = astop - mb0;                                   // bhat_n
+        const float mb0 = group_max<Q>(astop);
+        float beta = astop - mb0;
         double Sb = (double)mb0;
-        const float a_n = (n > 0 && j < L) ? alpha[(rowbase + n - 1) * L + j] : -CUDART_INF_F;
-        const double Sa_n = (n > 0) ? ascale[rowbase + n - 1] : 0.0;
-        const float xt = (j < L) ? a_n + astop : -CUDART_INF_F;
-        const float Mt = group_max<G>(xt);
-        const float st = group_sum<G>(expf(xt - Mt));
-        const double lz = Sa_n + (double)Mt + (double)logf(st);
-        // terminal pairwise term: dT[STOP][k] += w * exp(alpha_n[k] + A[STOP][k] - logZ)
-        if (n > 0 && j < L) atomicAdd(&s_dt[stop * L + j], wb * expf(xt - Mt) / st);
-        for (int i = nmax - 1; i >= 0; --i) {
-            const bool act = i < n;
-            float e = 0.0f, anext = -CUDART_INF_F, aprev = -CUDART_INF_F;
-            double Sa_next = 0.0, Sa_prev = 0.0;
-            int t = 0, y = -1, yprev = start;
-            if (act) {
-                t = pos ? pos[rowbase + i] : i;
-                y = tags[rowbase + t];
-                Sa_next = ascale[rowbase + i];
-                if (i > 0) {
-                    const int tp = pos ? pos[rowbase + i - 1] : i - 1;
-                    yprev = tags[rowbase + tp];
-                    Sa_prev = ascale[rowbase + i - 1];
-                }
-                if (j < L) {
-                    e = emis[(rowbase + t) * L + j];
-                    anext = alpha[(rowbase + i) * L + j];
-                    aprev = (i > 0) ? alpha[(rowbase + i - 1) * L + j] : ((j == start) ? 0.0f : kNeg);
-                }
-            }
-            // unary marginal: exp(ahat_{i+1}[j] + bhat_{i+1}[j] + (Sa_{i+1} + Sb_{i+1} - logZ))
-            if (act && j < L) {
-                const float off = (float)(Sa_next + Sb - lz);
-                const float pj = expf(anext + beta + off);
-                d_emis[(rowbase + t) * L + j] = wb * (pj - ((j == y) ? 1.0f : 0.0f));
-            }
-            const float u = (j < L && act) ? (e + beta + rmax) : -CUDART_INF_F;
-            const float Mb = group_max<G>(u);
-            const float q = (act && j < L) ? expf(u - Mb) : 0.0f;
-            const float av = (act && j < L) ? expf(aprev) : 0.0f;      // ahat is normalised: max = 0
-            const float c = act ? wb * expf(fminf((float)(Sa_prev + Sb + (double)Mb - lz), 80.0f)) : 0.0f;
-            const float cq = c * q;
-            float s = 0.0f;
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                acc[k] = fmaf(cq, __shfl_sync(0xffffffffu, av, k, G), acc[k]);
-                s = fmaf(Ecol[k], __shfl_sync(0xffffffffu, q, k, G), s);
-            }
-            const float tk = (j < L) ? logf(s) : -CUDART_INF_F;
-            const float mt = group_max<G>(tk);
-            if (act) {
-                beta = tk - mt;
-                Sb += (double)Mb + (double)mt;
-            }
-            // gold transition count
-            if (act && j == 0) atomicAdd(&s_dt[y * L + yprev], -wb);
-        }
-        if (n > 0 && j == 0) {
+        float anext = (n > 0 && j < L) ? alpha[(rowbase + n - 1) * L + j] : -CUDART_INF_F;     // ahat_{i+1} of the step at hand
+        double Sa_next = (n > 0) ? ascale[rowbase + n - 1] : 0.0;
+        const float xt = (j < L) ? anext + astop : -CUDART_INF_F;
+        const float Mt = group_max<Q>(xt);
+        const float st = group_sum<Q>(expf(xt - Mt));
+        const double lz = Sa_next + (double)Mt + (double)logf(st);
+        int ycur = start;
+        if (n > 0) {
             const int tl = pos ? pos[rowbase + n - 1] : n - 1;
-            atomicAdd(&s_dt[stop * L + tags[rowbase + tl]], -wb);
+            ycur = tags[rowbase + tl];
+            // terminal pairwise term dT[STOP][k] += w * exp(alpha_n[k] + A[STOP][k] - logZ), and its gold count
+            if (j < L) atomicAdd(&s_dt[stop * L + j], wb * expf(xt - Mt) / st);
+            if (j == 0) atomicAdd(&s_dt[stop * L + ycur], -wb);
         }
+
+        // ring: chunk c = steps [c*CH, (c+1)*CH), walked from the last chunk down.  Lane q < CH of a sentence fetches
+        // entry q; (pf_t, pf_tm1) are the index-list entries of the NEXT chunk to issue, prefetched a chunk ahead.
+        auto index_of = [&](int i) -> int { return (i >= 0 && i < n) ? (pos ? __ldg(pos + rowbase + i) : i) : 0; };
+        int pf_t = 0, pf_tm1 = 0;
+        auto prefetch_idx = [&](int c) {
+            if (c >= 0 && j < CH) { pf_t = index_of(c * CH + j); pf_tm1 = index_of(c * CH + j - 1); }
+        };
+        auto issue = [&](int cc) {               // cc counts issued chunks; chunk number c = nchunks - 1 - cc
+            const int c = nchunks - 1 - cc;
+            if (c >= 0 && j < CH) {
+                const uint32_t dst = my_chunk_s + (cc % NST) * stage_b;
+                const int i = c * CH + j;
+                if (i < n) {
+                    const float *er = emis + (rowbase + pf_t) * L;
+                    for (int jj = 0; jj < L; ++jj) cp_async4(dst + oE + (j * L + jj) * 4, er + jj);
+                    sts_b32(dst + oTL + j * 4, (uint32_t)pf_t);
+                    if (i >= 1) {
+                        const float *ar = alpha + (rowbase + i - 1) * L;
+                        for (int jj = 0; jj < L; ++jj) cp_async4(dst + oAP + (j * L + jj) * 4, ar + jj);
+                        cp_async8(dst + j * 8, ascale + rowbase + i - 1);
+                        cp_async4(dst + oYP + j * 4, tags + rowbase + pf_tm1);
+                    }
+                }
+            }
+            cp_async_commit();
+            prefetch_idx(c - 1);
+        };
+        prefetch_idx(nchunks - 1);
+#pragma unroll
+        for (int cc = 0; cc < NST - 1; ++cc) issue(cc);
+
+        // tile: two rows of K (u, exp u, exp ahat, -) entries; row parity alternates per step
+        int par = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < nchunks; ++cc) {
+            const int c = nchunks - 1 - cc;
+            issue(cc + NST - 1);
+            cp_async_wait<NST - 1>();
+            __syncwarp();
+            const uint32_t stg = my_chunk_s + (cc % NST) * stage_b;
+#pragma unroll 4
+            for (int uu = 0; uu < CH; ++uu) {
+                const int u = CH - 1 - uu;
+                const int i = c * CH + u;
+                const bool act = i < n;
+                // staged inputs of step i (sanitised when the step is not part of this sentence)
+                float e = lds_f32(stg + oE + u * L4 + jc4);
+                float ap = lds_f32(stg + oAP + u * L4 + jc4);
+                double Sa_prev = lds_f64(stg + u * 8);
+                int yprev = lds_s32(stg + oYP + u * 4);
+                const int t = lds_s32(stg + oTL + u * 4);
+                if (i == 0) {
+                    ap = (j == start) ? 0.0f : kNeg;
+                    Sa_prev = 0.0;
+                    yprev = start;
+                }
+                if (!act) e = 0.0f;
+                if (!act || j >= L) ap = -CUDART_INF_F;
+                // unary marginal: exp(ahat_{i+1}[j] + b_{i+1}[j] + (Sa_{i+1} + Sb_{i+1} - logZ))
+                if (act && j < L) {
+                    const float off = (float)(Sa_next + Sb - lz);
+                    const float pj = expf(anext + beta + off);
+                    d_emis[(rowbase + t) * L + j] = wb * (pj - ((j == ycur) ? 1.0f : 0.0f));
+                }
+                const float uj = e + beta + rmax;                                   // -inf for j >= L
+                const float eu = ex2_fast(uj * 1.4426950408889634f);
+                const float av = ex2_fast(ap * 1.4426950408889634f);
+                if (j < K) sts_v4(tile_s + par * kRow + j * 16, uj, eu, av, 0.0f);
+                const float cq = act ? wb * expf(fminf((float)(Sa_prev + Sb - lz), 80.0f)) * eu : 0.0f;
+                __syncwarp();
+                float uk[K], s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4 x = lds_v4(tile_s + par * kRow + k * 16);
+                    uk[k] = x.x;
+                    s4[k & 3] = fmaf(Ecol[k], x.y, s4[k & 3]);
+                    acc[k] = fmaf(cq, x.z, acc[k]);
+                }
+                const float M = max_tree<K>(uk);
+                const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                if (act) {
+                    beta = (j < L) ? __logf(s) - M : -CUDART_INF_F;
+                    Sb += (double)M;
+                    if (j == 0) atomicAdd(&s_dt[ycur * L + yprev], -wb);           // gold transition count
+                    anext = ap;      // for j >= L this stays -inf; (ap was sanitised only when !act)
+                    Sa_next = Sa_prev;
+                    ycur = yprev;
+                }
+                par ^= 1;
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
     }
     // dT[j][k] += E[j][k] * acc[k]
+    __syncwarp();
     if (j < L) {
 #pragma unroll
-        for (int k = 0; k < G; ++k)
+        for (int k = 0; k < K; ++k)
             if (k < L && acc[k] != 0.0f) atomicAdd(&s_dt[j * L + k], expf(trans[j * L + k] - rmax) * acc[k]);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L * L; i += blockDim.x)
+    __syncwarp();
+    for (int i = lane; i < L * L; i += 32)
         if (s_dt[i] != 0.0f) atomicAdd(&d_trans[i], s_dt[i]);
 }
 
@@ -426,16 +536,20 @@ extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const i
         set_error("crf_nll_bwd: memset: %s", cudaGetErrorString(e));
         return KBNER_ECUDA;
     }
-    const int W = 4;
-    const int spw = (L <= 16) ? 2 : 1;
-    int blocks = (B + W * spw - 1) / (W * spw);
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;   // persistent over sentences beyond that
-    if (L <= 16)
-        crf_nll_bwd_kernel<16><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, alpha_scale, w,
-                                                          B, T, L, start_idx, stop_idx, d_emis, d_trans);
-    else
-        crf_nll_bwd_kernel<32><<<blocks, W * 32, 0, st>>>(emis, tags, pos, klen, trans, alpha, alpha_scale, w,
-                                                          B, T, L, start_idx, stop_idx, d_emis, d_trans);
+#define KBNER_NLLB(Q, K)                                                                                      \
+    do {                                                                                                      \
+        using C = NllBwdCfg<Q, K>;                                                                            \
+        int blocks = (B + C::SPW - 1) / C::SPW;                                                               \
+        if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;   /* persistent over sentences beyond that */         \
+        crf_nll_bwd_kernel<Q, K><<<blocks, 32, C::smem_bytes(L), st>>>(emis, tags, pos, klen, trans, alpha,    \
+                                                                      alpha_scale, w, B, T, L, start_idx,     \
+                                                                      stop_idx, d_emis, d_trans);             \
+    } while (0)
+    if (L == 13) KBNER_NLLB(16, 13);
+    else if (L <= 16) KBNER_NLLB(16, 16);
+    else if (L == 29) KBNER_NLLB(32, 29);
+    else KBNER_NLLB(32, 32);
+#undef KBNER_NLLB
     KBNER_CHECK_LAUNCH("crf_nll_bwd");
     return KBNER_OK;
 }

@@ -161,53 +161,77 @@ embed_ln_fwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ w
 // flair/nn.py:176-183 (WordDropout) and sequence_tagger_model.py:1027 (self.linear).
 // W (fp32, [L,H]) is staged once per block in shared memory; one warp per word.
 // ------------------------------------------------------------------------------------------
+// Two words per warp iteration share every W read from shared memory (the first version read the whole 53 KB of W per
+// WORD: 868 MB of shared-memory traffic at 16320 words, 74 us), and the 2 x L partial sums are reduced through a
+// conflict-free [2L][33] shared tile by 2L lanes instead of 2L five-step shuffle reductions.
+constexpr int kTagprojWarps = 8;
 template <int CPL>   // 8-element (16-byte bf16) chunks per lane: H = CPL * 256
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTagprojWarps * 32, 2)
 gather_tagproj_fwd_kernel(const uint16_t *__restrict__ hidden, const int32_t *__restrict__ row_of,
                           const int32_t *__restrict__ first_idx, const uint8_t *__restrict__ drop_keep,
                           const float *__restrict__ W, const float *__restrict__ bias, int B, int T, int S, int L,
                           float *__restrict__ logits) {
     constexpr int H = CPL * 256;
-    extern __shared__ __align__(16) float w_s[];     // [L][H]
+    extern __shared__ __align__(16) float w_s[];     // [L][H], then per warp a [2L][33] reduction tile
     for (int i = threadIdx.x; i < L * H / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    const float my_bias = (lane < L) ? bias[lane] : 0.0f;
-    for (int w = blockIdx.x * (blockDim.x >> 5) + warp; w < B * T; w += nwarps) {
-        const int b = w / T, t = w - b * T;
-        const int fi = first_idx[w];
-        const bool live = fi >= 0 && (!drop_keep || drop_keep[t] != 0);
-        float res = my_bias;                       // zero vector (0 sub-tokens / dropped word) => bias only
-        if (live) {                                // warp-uniform
-            const uint16_t *hr = hidden + ((size_t)row_of[b] * S + fi) * H;
-            float x[CPL * 8];
+    float *red = w_s + (size_t)L * H + (size_t)warp * 2 * L * 33;
+    const int words = B * T;
+    const int pairs = (words + 1) / 2;
+    const int stride = gridDim.x * kTagprojWarps;
+    for (int p = blockIdx.x * kTagprojWarps + warp; p < pairs; p += stride) {
+        float x[2][CPL * 8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int w = 2 * p + h;
+            bool live = false;
+            const uint16_t *hr = hidden;
+            if (w < words) {
+                const int b = w / T, t = w - b * T;
+                const int fi = first_idx[w];
+                live = fi >= 0 && (!drop_keep || drop_keep[t] != 0);
+                if (live) hr = hidden + ((size_t)row_of[b] * S + fi) * H;
+            }
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const uint4 u = ld_nc_v4(hr + c * 256 + lane * 8);
-                unpack_bf16x2(u.x, x[c * 8 + 0], x[c * 8 + 1]);
-                unpack_bf16x2(u.y, x[c * 8 + 2], x[c * 8 + 3]);
-                unpack_bf16x2(u.z, x[c * 8 + 4], x[c * 8 + 5]);
-                unpack_bf16x2(u.w, x[c * 8 + 6], x[c * 8 + 7]);
-            }
-            for (int l = 0; l < L; ++l) {
-                const float *wl = w_s + (size_t)l * H;
-                float acc = 0.0f;
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8 + 4);
-                    acc = fmaf(x[c * 8 + 0], w0.x, acc); acc = fmaf(x[c * 8 + 1], w0.y, acc);
-                    acc = fmaf(x[c * 8 + 2], w0.z, acc); acc = fmaf(x[c * 8 + 3], w0.w, acc);
-                    acc = fmaf(x[c * 8 + 4], w1.x, acc); acc = fmaf(x[c * 8 + 5], w1.y, acc);
-                    acc = fmaf(x[c * 8 + 6], w1.z, acc); acc = fmaf(x[c * 8 + 7], w1.w, acc);
-                }
-                acc = warp_sum(acc);
-                if (lane == l) res += acc;
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);          // zero vector (0 sub-tokens / dropped word) => bias only
+                if (live) u = ld_nc_v4(hr + c * 256 + lane * 8);
+                unpack_bf16x2(u.x, x[h][c * 8 + 0], x[h][c * 8 + 1]);
+                unpack_bf16x2(u.y, x[h][c * 8 + 2], x[h][c * 8 + 3]);
+                unpack_bf16x2(u.z, x[h][c * 8 + 4], x[h][c * 8 + 5]);
+                unpack_bf16x2(u.w, x[h][c * 8 + 6], x[h][c * 8 + 7]);
             }
         }
-        if (lane < L) logits[(size_t)w * L + lane] = res;
+        for (int l = 0; l < L; ++l) {
+            const float *wl = w_s + (size_t)l * H;
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wl + c * 256 + lane * 8 + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    a0 = fmaf(x[0][c * 8 + i], wv[i], a0);
+                    a1 = fmaf(x[1][c * 8 + i], wv[i], a1);
+                }
+            }
+            red[l * 33 + lane] = a0;                     // bank (l + lane) % 32: conflict-free
+            red[(L + l) * 33 + lane] = a1;
+        }
+        __syncwarp();
+        for (int v = lane; v < 2 * L; v += 32) {         // lane sums row v: bank (v + i) % 32
+            const float *r = red + v * 33;
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { s0 += r[i]; s1 += r[i + 1]; s2 += r[i + 2]; s3 += r[i + 3]; }
+            const int h = (v >= L) ? 1 : 0, l = v - h * L;
+            const int w = 2 * p + h;
+            if (w < words) logits[(size_t)w * L + l] = __ldg(bias + l) + ((s0 + s1) + (s2 + s3));
+        }
+        __syncwarp();
     }
 }
 
@@ -272,7 +296,7 @@ template <int CPL>
 static int launch_tagproj(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
                           const uint8_t *drop_keep, const float *W, const float *bias, int B, int T, int S, int L,
                           float *logits, cudaStream_t st) {
-    const size_t smem = (size_t)L * CPL * 256 * sizeof(float);
+    const size_t smem = ((size_t)L * CPL * 256 + (size_t)kTagprojWarps * 2 * L * 33) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gather_tagproj_fwd_kernel<CPL>,
@@ -283,10 +307,10 @@ static int launch_tagproj(const uint16_t *hidden, const int32_t *row_of, const i
         }
         configured = smem;
     }
-    const int words = B * T;
-    int blocks = (words + 7) / 8;
-    if (blocks > kNumSMs) blocks = kNumSMs;
-    gather_tagproj_fwd_kernel<CPL><<<blocks, 256, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L,
+    const int pairs = (B * T + 1) / 2;
+    int blocks = (pairs + kTagprojWarps - 1) / kTagprojWarps;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    gather_tagproj_fwd_kernel<CPL><<<blocks, kTagprojWarps * 32, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L,
                                                               logits);
     KBNER_CHECK_LAUNCH("gather_tagproj_fwd");
     return KBNER_OK;
@@ -297,7 +321,7 @@ extern "C" int kbner_gather_tagproj_fwd(const uint16_t *hidden, const int32_t *r
                                         int S, int H, int L, float *logits, void *stream) {
     KBNER_CHECK_ARG(hidden && row_of && first_idx && W && bias && logits, "gather_tagproj_fwd: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && S > 0 && L >= 1 && L <= 32, "gather_tagproj_fwd: need 1 <= L <= 32 (L=%d)", L);
-    KBNER_CHECK_ARG(H % 256 == 0 && (size_t)L * H * 4 <= 200 * 1024,
+    KBNER_CHECK_ARG(H % 256 == 0 && ((size_t)L * H + (size_t)kTagprojWarps * 2 * L * 33) * 4 <= 220 * 1024,
                     "gather_tagproj_fwd: H=%d must be a multiple of 256 with L*H*4 <= 200 KB", H);
     if (B == 0) return KBNER_OK;
     cudaStream_t st = (cudaStream_t)stream;

@@ -31,9 +31,16 @@ def main():
         lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
         tags = torch.randint(1, L - 2, (B, T), device="cuda", dtype=torch.int32)
         res = {"B": B}
+        _, _, alpha = ops.crf_nll_fwd(emis, tags, trans, lens, L - 2, L - 1, want_alpha=True)
+        w = torch.full((B,), 1.0 / B, device="cuda")
         for name, fn, bytes_per in (
                 ("viterbi", lambda: ops.crf_viterbi(emis, trans, lens, lens, L - 2, L - 1), T * L * 4 + T * 8),
-                ("nll_fwd", lambda: ops.crf_nll_fwd(emis, tags, trans, lens, L - 2, L - 1), T * L * 4 + T * 4 + 8)):
+                ("nll_fwd", lambda: ops.crf_nll_fwd(emis, tags, trans, lens, L - 2, L - 1), T * L * 4 + T * 4 + 8),
+                ("nll_fwd_alpha", lambda: ops.crf_nll_fwd(emis, tags, trans, lens, L - 2, L - 1, want_alpha=True),
+                 2 * T * L * 4 + T * 12 + 8),
+                # emissions + stored alpha (fp32 vector + fp64 scale) + tags read, d_emis written
+                ("nll_bwd", lambda: ops.crf_nll_bwd(emis, tags, trans, lens, alpha, w, L - 2, L - 1),
+                 3 * T * L * 4 + T * 12)):
             for _ in range(3):
                 fn()
             ts = []
