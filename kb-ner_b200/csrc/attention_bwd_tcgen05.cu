@@ -37,8 +37,8 @@ struct AttnBwdSmem {
     uint8_t dO[2][kT128];
     uint8_t pt[2][kT128];                // P^T  [128 keys][128 queries] as two 64-query sub-tiles
     uint8_t dst[2][kT128];               // dS^T, same layout (scaled by 1/8)
-    float lse2[2][128];                  // LSE * log2(e) of the query block (+inf beyond the window)
-    float dsum[2][128];                  // D of the query block
+    float lse2[512];                     // LSE * log2(e) of every query row of the window (+inf beyond it)
+    float dsum[512];                     // D of every query row
     uint64_t bar_kv;
     uint64_t qdo_full[2];
     uint64_t bar_sdp;                    // S^T and dP^T ready in TMEM
@@ -232,18 +232,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t kpair = (uint32_t)(jb * 128 + t) >> 1;          // this thread's key: pair index and half
         const bool khi = ((jb * 128 + t) & 1) != 0;
         const uint32_t dwin = (uint32_t)(r * heads + h) * 512u;        // same counter layout as attention_fwd_kernel
+        // LSE / D of the whole window are staged once, while the first TMA loads are in flight.  (Staging them per query block
+        // put a DRAM round trip at the top of every block: 23 % of the stall samples of profiles/r01/attn_bwd_ncu_r38.txt.)
+        for (int qi = threadIdx.x; qi < nqb * 128; qi += 256) {
+            const size_t off = ((size_t)r * heads + h) * S + qi;
+            s.lse2[qi] = (qi < S) ? __ldg(lse + off) * 1.4426950408889634f : CUDART_INF_F;
+            s.dsum[qi] = (qi < S) ? __ldg(Dsum + off) : 0.0f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
         for (int i = 0; i < nqb; ++i) {
-            // stage LSE / D of query block i (one value per row; both threads of a row write the same value)
-            {
-                const int qi = i * 128 + t;
-                const size_t off = ((size_t)r * heads + h) * S + qi;
-                s.lse2[i & 1][t] = (qi < S) ? lse[off] * 1.4426950408889634f : CUDART_INF_F;
-                s.dsum[i & 1][t] = (qi < S) ? Dsum[off] : 0.0f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
             ptx::mbar_wait(&s.bar_sdp, i & 1);
             ptx::tc_fence_after();
-            const float *lse2 = s.lse2[i & 1], *dsum = s.dsum[i & 1];
+            const float *lse2 = s.lse2 + i * 128, *dsum = s.dsum + i * 128;
 #pragma unroll
             for (int cl = 0; cl < 2; ++cl) {              // this thread's 2 chunks of 32 query columns
                 const int c = half * 2 + cl;

@@ -40,8 +40,9 @@ struct AttnSmem {
     uint8_t v[kKVStages][kKVBytes];
     uint8_t p[2][kQBytes];             // [buffer][128 rows x 64 keys]
     uint64_t bar_q;
-    uint64_t kv_full[kKVStages];
-    uint64_t kv_free[kKVStages];       // P_j.V_j retired: stage may be refilled
+    uint64_t k_full[kKVStages], v_full[kKVStages];
+    uint64_t k_free[kKVStages];        // S_j = Q.K_j^T retired: the K slot may be refilled (two blocks before its V slot)
+    uint64_t v_free[kKVStages];        // P_j.V_j retired: the V slot may be refilled
     uint64_t bar_s[2];                 // S_j ready in TMEM buffer j&1
     uint64_t bar_p[2];                 // P_j written to smem buffer j&1 (128 arrivals)
     uint64_t bar_o[2];                 // O_j ready in TMEM buffer j&1
@@ -92,8 +93,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::prefetch_tensormap(&tmKV);
         ptx::mbar_init(&s.bar_q, 1);
         for (int i = 0; i < kKVStages; ++i) {
-            ptx::mbar_init(&s.kv_full[i], 1);
-            ptx::mbar_init(&s.kv_free[i], 1);
+            ptx::mbar_init(&s.k_full[i], 1);
+            ptx::mbar_init(&s.v_full[i], 1);
+            ptx::mbar_init(&s.k_free[i], 1);
+            ptx::mbar_init(&s.v_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s.bar_s[i], 1);
@@ -113,39 +116,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     if (warp == 8) {
         if (lane == 0 && nkb > 0) {
-            auto load_kv = [&](int j) {
-                const int st = j % kKVStages;
-                ptx::mbar_expect_tx(&s.kv_full[st], 2 * kKVBytes);
-                ptx::tma_load_2d(s.k[st], &tmKV, &s.kv_full[st], H + h * kAttnD, row0 + j * kBKV);
-                ptx::tma_load_2d(s.v[st], &tmKV, &s.kv_full[st], 2 * H + h * kAttnD, row0 + j * kBKV);
+            // K and V travel separately.  K_m is consumed by S_m, which is issued two key blocks ahead of the softmax, so
+            // its slot is free -- and is refilled with K_{m+3} -- as soon as S_m has retired; V_m's slot is refilled after
+            // P_m.V_m.  Both loads then have two block times to land.  (The first version refilled the K|V pair of block m
+            // only after P_m.V_m and needed it one block later: 84 % of the softmax warps' first polls of `bar_s` failed,
+            // 18 % of all stall samples sat on that wait -- profiles/r01/attn_fwd_ncu_r38.txt.)
+            auto load_k = [&](int m) {
+                const int st = m % kKVStages;
+                ptx::mbar_expect_tx(&s.k_full[st], kKVBytes);
+                ptx::tma_load_2d(s.k[st], &tmKV, &s.k_full[st], H + h * kAttnD, row0 + m * kBKV);
+            };
+            auto load_v = [&](int m) {
+                const int st = m % kKVStages;
+                ptx::mbar_expect_tx(&s.v_full[st], kKVBytes);
+                ptx::tma_load_2d(s.v[st], &tmKV, &s.v_full[st], 2 * H + h * kAttnD, row0 + m * kBKV);
             };
             ptx::mbar_expect_tx(&s.bar_q, kQBytes);
             ptx::tma_load_2d(s.q, &tmQ, &s.bar_q, h * kAttnD, row0 + qb * kBQ);
-            for (int j = 0; j < nkb && j < kKVStages; ++j) load_kv(j);
+            for (int m = 0; m < nkb && m < kKVStages; ++m) load_k(m);
+            for (int m = 0; m < nkb && m < kKVStages; ++m) load_v(m);
 
             constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);   // S = Q.K^T : both K-major
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);   // O = P.V   : V is MN-major
             const uint32_t q_addr = ptx::smem_u32(s.q);
-            auto issue_s = [&](int j) {
-                const int st = j % kKVStages;
-                ptx::mbar_wait(&s.kv_full[st], (j / kKVStages) & 1);
+            auto issue_s = [&](int m) {
+                const int st = m % kKVStages;
+                ptx::mbar_wait(&s.k_full[st], (m / kKVStages) & 1);
                 ptx::tc_fence_after();
                 const uint32_t k_addr = ptx::smem_u32(s.k[st]);
 #pragma unroll
                 for (int kk = 0; kk < kAttnD / 16; ++kk) {
                     const uint64_t da = ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024);
                     const uint64_t db = ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024);
-                    ptx::mma_f16_ss(tmem_s + (j & 1) * 64, da, db, idesc_s, kk != 0);
+                    ptx::mma_f16_ss(tmem_s + (m & 1) * 64, da, db, idesc_s, kk != 0);
                 }
-                ptx::mma_commit(&s.bar_s[j & 1]);
+                ptx::mma_commit(&s.bar_s[m & 1]);
+                ptx::mma_commit(&s.k_free[st]);
+            };
+            auto refill_k = [&](int m) {           // K_m into the slot of K_{m-3}, whose S has retired
+                if (m < nkb) {
+                    ptx::mbar_wait(&s.k_free[m % kKVStages], ((m - kKVStages) / kKVStages) & 1);
+                    load_k(m);
+                }
             };
             ptx::mbar_wait(&s.bar_q, 0);
             issue_s(0);
             if (nkb > 1) issue_s(1);
+            refill_k(kKVStages);
             for (int j = 0; j < nkb; ++j) {
                 const int st = j % kKVStages;
                 // P_j in smem (the softmax warps executed fence.proxy.async before arriving)
                 ptx::mbar_wait(&s.bar_p[j & 1], (j >> 1) & 1);
+                ptx::mbar_wait(&s.v_full[st], (j / kKVStages) & 1);
                 ptx::tc_fence_after();
                 const uint32_t v_addr = ptx::smem_u32(s.v[st]);
                 const uint32_t p_addr = ptx::smem_u32(s.p[j & 1]);
@@ -157,11 +179,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     ptx::mma_f16_ss(tmem_o, da, db, idesc_o, (j != 0) || (kk != 0));   // O accumulates in TMEM over the key blocks
                 }
                 ptx::mma_commit(&s.bar_o[j & 1]);
-                ptx::mma_commit(&s.kv_free[st]);
+                ptx::mma_commit(&s.v_free[st]);
                 if (j + 2 < nkb) issue_s(j + 2);   // S buffer j&1 was drained before P_j was published
-                if (j + kKVStages < nkb) {         // refill this stage once P_j.V_j has retired
-                    ptx::mbar_wait(&s.kv_free[st], (j / kKVStages) & 1);
-                    load_kv(j + kKVStages);
+                refill_k(j + 1 + kKVStages);       // slot of K_{j+1}: S_{j+1} was issued one block ago
+                if (j >= 1 && j + 2 < nkb) {       // slot of V_{j-1}: P_{j-1}.V_{j-1} was issued one block ago
+                    ptx::mbar_wait(&s.v_free[(j - 1) % kKVStages], ((j - 1) / kKVStages) & 1);
+                    load_v(j + 2);
                 }
             }
         }

@@ -273,7 +273,8 @@ struct NllBwdCfg {
     static __host__ __device__ int tile_stride() { return padded(2 * K * 16); }
     static __host__ __device__ size_t ring_bytes(int L) { return (size_t)NST * SPW * chunk_stride(L); }
     static __host__ __device__ size_t dt_off(int L) { return ring_bytes(L) + (size_t)SPW * tile_stride(); }
-    static __host__ __device__ size_t smem_bytes(int L) { return dt_off(L) + (size_t)L * L * 4 + 64; }
+    // dT partials [L][L] | control word (64 B) | gold transition counts [SPW][L][L]
+    static __host__ __device__ size_t smem_bytes(int L) { return dt_off(L) + (size_t)(1 + SPW) * L * L * 4 + 64; }
 };
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_s, const void *src) {
@@ -307,7 +308,10 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
     int *s_ctl = reinterpret_cast<int *>(smem + C::dt_off(L) + (size_t)L * L * 4);
     const int lane = threadIdx.x;
     const int sub = lane / Q, j = lane % Q;
-    for (int i = lane; i < L * L; i += 32) s_dt[i] = 0.0f;
+    // gold transition counts: lane 0 of a sentence owns a private [L][L] table and updates it with a plain load / add /
+    // store per step (an fp32 shared-memory atomicAdd is a compare-and-swap loop, and it sat on every step of the chain)
+    float *s_gold = reinterpret_cast<float *>(smem + C::dt_off(L) + (size_t)L * L * 4 + 64) + (size_t)sub * L * L;
+    for (int i = lane; i < (1 + SPW) * L * L + 16; i += 32) s_dt[i] = 0.0f;
 
     float rmax = -CUDART_INF_F;
     if (j < L)
@@ -459,7 +463,7 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
                 if (act) {
                     beta = (j < L) ? __logf(s) - M : -CUDART_INF_F;
                     Sb += (double)M;
-                    if (j == 0) atomicAdd(&s_dt[ycur * L + yprev], -wb);           // gold transition count
+                    if (j == 0) s_gold[ycur * L + yprev] -= wb;                   // gold transition count
                     anext = ap;      // for j >= L this stays -inf; (ap was sanitised only when !act)
                     Sa_next = Sa_prev;
                     ycur = yprev;
@@ -478,8 +482,12 @@ crf_nll_bwd_kernel(const float *__restrict__ emis, const int32_t *__restrict__ t
             if (k < L && acc[k] != 0.0f) atomicAdd(&s_dt[j * L + k], expf(trans[j * L + k] - rmax) * acc[k]);
     }
     __syncwarp();
-    for (int i = lane; i < L * L; i += 32)
-        if (s_dt[i] != 0.0f) atomicAdd(&d_trans[i], s_dt[i]);
+    for (int i = lane; i < L * L; i += 32) {
+        float v = s_dt[i];
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) v += s_dt[(1 + q) * L * L + 16 + i];
+        if (v != 0.0f) atomicAdd(&d_trans[i], v);
+    }
 }
 
 }  // namespace kbner

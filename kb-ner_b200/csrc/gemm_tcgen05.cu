@@ -45,6 +45,7 @@ struct GemmSmem {
     uint64_t empty[kStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t aux_full[kEpiWarps][2];        // DGELU: the warp's aux (pre-activation) chunk has landed in cstage[warp][b]
     uint32_t tmem_base;
 };
 
@@ -113,6 +114,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s.tmem_full[i], 1);
             ptx::mbar_init(&s.tmem_empty[i], 2 * kEpiWarps);   // epilogue warps of BOTH CTAs arrive on the leader's
+        }
+        if (EPI == KBNER_EPI_DGELU_BF16) {
+            ptx::prefetch_tensormap(&tmAux);
+            for (int i = 0; i < kEpiWarps; ++i) {
+                ptx::mbar_init(&s.aux_full[i][0], 1);
+                ptx::mbar_init(&s.aux_full[i][1], 1);
+            }
         }
         ptx::fence_barrier_init();
     }
@@ -215,6 +223,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t *stage_base = s.cstage[ew][0];
         const uint32_t stage_u32 = ptx::smem_u32(stage_base);
         uint32_t nstores = 0;                           // staging-buffer uses so far (lane 0 owns the bulk groups)
+        uint32_t aux_phase = 0;                         // bit b: parity of the next completion of aux_full[ew][b]
         auto stage_and_store = [&](const uint4 (&q)[8], const CUtensorMap *map, int col0, int row_base, bool reduce_add) {
             const uint32_t buf = nstores & 1;
             if (nstores >= 2) {                         // the store that last read this buffer must have drained it
@@ -248,9 +257,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = row_base + lane;
             const bool row_ok = row < M;
             const int colbase = n_blk * BN + half * (BN / 2);
-            // operand rows that do not depend on the accumulator: fetch them while the main loop still runs
-            uint4 raux[16];
-            if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
+            // operand rows that do not depend on the accumulator: fetch them while the main loop still runs.
+            // DGELU: the two 32-row x 64-column chunks of the saved pre-activation come in by TMA, into the very staging
+            // buffers their products leave from (same box, same SWIZZLE_128B; a lane only ever touches its own 128-byte
+            // row, so reading the operand and overwriting it with the result needs no cross-lane ordering).  The
+            // row-per-lane ld.global this replaces was 32 sectors per request and made this epilogue (57 us at
+            // 4096 x 4096 x 1024) twice as long as the main loop it is supposed to hide behind.
+            const uint32_t nb = nstores;                 // chunk c of this tile uses staging buffer (nb + c) & 1
+            if (EPI == KBNER_EPI_DGELU_BF16) {
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // last tile's stores have read both buffers
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int col0 = colbase + c * CW;
+                        if (col0 < N) {
+                            const uint32_t b = (nb + c) & 1;
+                            ptx::mbar_expect_tx(&s.aux_full[ew][b], 4096);
+                            ptx::tma_load_2d(stage_base + b * 4096, &tmAux, &s.aux_full[ew][b], col0, row_base);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            uint4 raux[EPI == KBNER_EPI_BIAS_RESID_F32 ? 16 : 1];
+            if (EPI == KBNER_EPI_BIAS_RESID_F32) {
                 const uint16_t *rrow = g.aux + (size_t)(row_ok ? row : 0) * ldc + colbase;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -307,10 +337,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
                 }
+                if (EPI == KBNER_EPI_DGELU_BF16) {
+                    const uint32_t b = (nb + c) & 1;
+                    ptx::mbar_wait(&s.aux_full[ew][b], (aux_phase >> b) & 1u);
+                    aux_phase ^= 1u << b;
+                }
                 if (EPI == KBNER_EPI_BIAS_RESID_F32 || EPI == KBNER_EPI_DGELU_BF16) {
 #pragma unroll
                     for (int i = 0; i < CW; i += 8) {
-                        const uint4 rv = raux[(c * CW + i) / 8];
+                        uint4 rv;
+                        if (EPI == KBNER_EPI_DGELU_BF16)
+                            rv = *reinterpret_cast<const uint4 *>(stage_base + ((nb + c) & 1) * 4096 + lane * 128 +
+                                                                  (((i / 8) ^ (lane & 7)) << 4));
+                        else
+                            rv = raux[EPI == KBNER_EPI_BIAS_RESID_F32 ? (c * CW + i) / 8 : 0];
                         float a[8];
                         unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
                         unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
@@ -406,8 +446,8 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     rc = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, bf16_out ? 64 : 32, bf16_out ? 2 : 4);
     if (rc) return rc;
     tmAux = tmC;
-    if (aux_out) {
-        rc = make_tmap_2d(&tmAux, aux_out, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 64, 2);
+    if (aux_out || epilogue == KBNER_EPI_DGELU_BF16) {
+        rc = make_tmap_2d(&tmAux, aux_out ? aux_out : aux, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 64, 2);
         if (rc) return rc;
     }
     const int num_kb_h = (K + BK - 1) / BK;

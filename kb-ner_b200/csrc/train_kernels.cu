@@ -6,54 +6,85 @@
 
 namespace kbner {
 
+__device__ __forceinline__ void red_add_v4(float *p, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void f4_add(float4 &a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm backward.  x = saved fp32 pre-LN sum, dout = grad w.r.t. the LN output (fp32),
 //   xhat = (x - mean) * rstd,  g = dout * gamma,
 //   dx   = rstd * (g - mean_H(g) - xhat * mean_H(g * xhat))          -> bf16 (operand of the dgrad / wgrad GEMMs)
 //   dgamma += sum_rows dout * xhat,  dbeta += sum_rows dout          (fp32, accumulated)
-// One warp per row, rows strided over a persistent grid; per-lane partial dgamma/dbeta in registers, reduced
-// through shared memory, one atomic per column per block.
+// Mapping (second design): H / 256 warps per row, a lane owns 8 columns (two float4), a block works on two rows at a
+// time.  The row sums cross the warps of a row through shared memory and a named barrier.  The first design (one warp per
+// row, 32 columns per lane) needed 255 registers -- 8 warps per SM, 3.5 sequential rows each at M = 4096 -- and reduced
+// its column partials with fp32 shared-memory atomics (CAS loops): 24 us for 59 MB.  Here ~32 warps per SM keep 8 rows in
+// flight, the column partials of the two row slots are combined by plain shared-memory read-modify-writes and leave as
+// 16-byte red.global.add.v4.f32.
 // ------------------------------------------------------------------------------------------
-template <int VPL, bool FUSED>
-__global__ void __launch_bounds__(256)
+template <int WPR, bool FUSED>
+__global__ void __launch_bounds__(WPR * 64, 2)
 layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias, const uint16_t *__restrict__ resid,
                      const float *__restrict__ dout, const uint16_t *__restrict__ dres, const float *__restrict__ gamma,
                      const float *__restrict__ mean, const float *__restrict__ rstd, int M,
                      uint16_t *__restrict__ dx, uint16_t *__restrict__ dxm, float *__restrict__ dgamma,
                      float *__restrict__ dbeta, float *__restrict__ dxsum, const Dropout drop) {
-    constexpr int H = VPL * 128;
-    __shared__ float s_red[3][H];
+    constexpr int H = WPR * 256, NT = WPR * 64;
+    __shared__ float2 s_part[2][2][WPR];        // [row slot][iteration parity][warp of the row]
+    __shared__ float4 s_col[3][H / 4];          // column partials of row slot 0 (dgamma, dbeta, sum of dx)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
-    __syncthreads();
-    float4 gm[VPL];
+    const int slot = warp / WPR, wr = warp - slot * WPR;
+    float4 gm[2], ag[2], ab[2], ax[2];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + i * 32 + lane);
-    float4 ag[VPL], ab[VPL], ax[VPL];      // per-lane partial column sums: dgamma, dbeta, sum of dx (bias gradient)
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ax[i] = make_float4(0, 0, 0, 0); }
+    for (int i = 0; i < 2; ++i) {
+        gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + wr * 64 + i * 32 + lane);
+        ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); ax[i] = make_float4(0, 0, 0, 0);
+    }
     const uint32_t key = (FUSED && drop.thresh) ? drop_key(drop) : 0u;
-    for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
-        const float mu = mean[row], rs = rstd[row];
-        const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * H);
-        const float4 *dr = reinterpret_cast<const float4 *>(dout + (size_t)row * H);
-        float4 xh[VPL], g[VPL];
-        uint32_t keep[VPL];                 // 4 keep bits per float4 (FUSED + dropout only)
+    // raw operands of one row for this lane; the NEXT row's are requested before the current row is reduced, so the DRAM
+    // round trip of row k+1 overlaps the arithmetic, the barrier and the stores of row k (without it the capture in
+    // profiles/r01/trainhbm_ncu_r38.txt shows 33 % DRAM and 42 % issue utilisation: latency-bound)
+    struct RowRaw { uint4 x[2], d[2]; uint2 r[2], dr[2]; float mu, rs; };
+    auto load_row = [&](int row, RowRaw &q) {
+        q.mu = __ldg(mean + row);
+        q.rs = __ldg(rstd + row);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c4 = wr * 64 + i * 32 + lane;
+            q.x[i] = ld_nc_v4(reinterpret_cast<const float4 *>(x + (size_t)row * H) + c4);
+            q.d[i] = ld_nc_v4(reinterpret_cast<const float4 *>(dout + (size_t)row * H) + c4);
+            q.r[i] = make_uint2(0u, 0u);
+            q.dr[i] = make_uint2(0u, 0u);
+            if (FUSED && resid) q.r[i] = __ldg(reinterpret_cast<const uint2 *>(resid + (size_t)row * H) + c4);
+            if (FUSED && dres) q.dr[i] = __ldg(reinterpret_cast<const uint2 *>(dres + (size_t)row * H) + c4);
+        }
+    };
+    float4 bs[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+    if (FUSED && bias) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bs[i] = __ldg(reinterpret_cast<const float4 *>(bias) + wr * 64 + i * 32 + lane);
+    }
+    int it = 0;
+    const int row_first = blockIdx.x * 2 + slot, row_step = gridDim.x * 2;
+    RowRaw cur, nxt;
+    if (row_first < M) load_row(row_first, cur);
+    for (int row = row_first; row < M; row += row_step, ++it) {
+        if (row + row_step < M) load_row(row + row_step, nxt);
+        const float mu = cur.mu, rs = cur.rs;
+        float4 xh[2], g[2];
+        uint32_t keep[2];                 // 4 keep bits per float4 (FUSED + dropout only)
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int c4 = i * 32 + lane;
-            const uint4 ux = ld_nc_v4(xr + c4), ud = ld_nc_v4(dr + c4);
+        for (int i = 0; i < 2; ++i) {
+            const int c4 = wr * 64 + i * 32 + lane;
+            const uint4 ux = cur.x[i], ud = cur.d[i];
             float4 xv = make_float4(__uint_as_float(ux.x), __uint_as_float(ux.y), __uint_as_float(ux.z), __uint_as_float(ux.w));
             float4 dv = make_float4(__uint_as_float(ud.x), __uint_as_float(ud.y), __uint_as_float(ud.z), __uint_as_float(ud.w));
             keep[i] = 0xfu;
             if (FUSED) {
                 // the LayerNorm input is recomputed exactly as the forward built it: z = dropout(x + bias) + resid
-                if (bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
-                    xv.x += b.x; xv.y += b.y; xv.z += b.z; xv.w += b.w;
-                }
+                if (bias) { xv.x += bs[i].x; xv.y += bs[i].y; xv.z += bs[i].z; xv.w += bs[i].w; }
                 if (drop.thresh) {
                     const uint32_t pair = (uint32_t)row * (H / 2) + (uint32_t)c4 * 2u;
                     const uint32_t b0 = drop_bits(key, pair), b1 = drop_bits(key, pair + 1u);
@@ -65,17 +96,15 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias
                     xv.w = (keep[i] & 8u) ? xv.w * drop.scale : 0.0f;
                 }
                 if (resid) {
-                    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(resid + (size_t)row * H) + c4);
                     float r0, r1, r2, r3;
-                    unpack_bf16x2(r.x, r0, r1);
-                    unpack_bf16x2(r.y, r2, r3);
+                    unpack_bf16x2(cur.r[i].x, r0, r1);
+                    unpack_bf16x2(cur.r[i].y, r2, r3);
                     xv.x += r0; xv.y += r1; xv.z += r2; xv.w += r3;
                 }
                 if (dres) {                 // gradient arriving over the residual connection (bf16) joins the GEMM's fp32 dgrad
-                    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(dres + (size_t)row * H) + c4);
                     float r0, r1, r2, r3;
-                    unpack_bf16x2(r.x, r0, r1);
-                    unpack_bf16x2(r.y, r2, r3);
+                    unpack_bf16x2(cur.dr[i].x, r0, r1);
+                    unpack_bf16x2(cur.dr[i].y, r2, r3);
                     dv.x += r0; dv.y += r1; dv.z += r2; dv.w += r3;
                 }
             }
@@ -86,16 +115,29 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias
             ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
             ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
         }
-        const float m1 = warp_sum(s1) * (1.0f / H), m2 = warp_sum(s2) * (1.0f / H);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (WPR > 1) {
+            // the warps of a row slot run the same trip count; parity double-buffers the exchange (a warp can be at most
+            // one barrier ahead of the slowest reader)
+            if (lane == 0) s_part[slot][it & 1][wr] = make_float2(s1, s2);
+            if (slot == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPR * 32) : "memory");
+            else asm volatile("bar.sync 2, %0;" ::"n"(WPR * 32) : "memory");
+            s1 = 0.0f; s2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < WPR; ++k) { const float2 t = s_part[slot][it & 1][k]; s1 += t.x; s2 += t.y; }
+        }
+        const float m1 = s1 * (1.0f / H), m2 = s2 * (1.0f / H);
         uint16_t *o = dx + (size_t)row * H;
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
+        for (int i = 0; i < 2; ++i) {
+            const int c4 = wr * 64 + i * 32 + lane;
             float d0 = rs * (g[i].x - m1 - xh[i].x * m2), d1 = rs * (g[i].y - m1 - xh[i].y * m2);
             float d2 = rs * (g[i].z - m1 - xh[i].z * m2), d3 = rs * (g[i].w - m1 - xh[i].w * m2);
             uint2 p;
             p.x = pack_bf16x2(d0, d1);
             p.y = pack_bf16x2(d2, d3);
-            *reinterpret_cast<uint2 *>(o + (i * 32 + lane) * 4) = p;           // grad w.r.t. z: the residual path
+            *reinterpret_cast<uint2 *>(o + c4 * 4) = p;                          // grad w.r.t. z: the residual path
             if (FUSED && drop.thresh) {
                 // grad w.r.t. the Linear's output: through the dropout mask (what dgrad / wgrad / the bias gradient consume)
                 d0 = (keep[i] & 1u) ? d0 * drop.scale : 0.0f;
@@ -104,42 +146,62 @@ layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias
                 d3 = (keep[i] & 8u) ? d3 * drop.scale : 0.0f;
                 p.x = pack_bf16x2(d0, d1);
                 p.y = pack_bf16x2(d2, d3);
-                *reinterpret_cast<uint2 *>(dxm + (size_t)row * H + (i * 32 + lane) * 4) = p;
+                *reinterpret_cast<uint2 *>(dxm + (size_t)row * H + c4 * 4) = p;
             }
             ax[i].x += d0; ax[i].y += d1; ax[i].z += d2; ax[i].w += d3;
         }
+        cur = nxt;
     }
+    // column partials: slot 0 publishes, slot 1 adds its own on top and flushes
+    if (slot == 0) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        atomicAdd(&s_red[0][c + 0], ag[i].x); atomicAdd(&s_red[0][c + 1], ag[i].y);
-        atomicAdd(&s_red[0][c + 2], ag[i].z); atomicAdd(&s_red[0][c + 3], ag[i].w);
-        atomicAdd(&s_red[1][c + 0], ab[i].x); atomicAdd(&s_red[1][c + 1], ab[i].y);
-        atomicAdd(&s_red[1][c + 2], ab[i].z); atomicAdd(&s_red[1][c + 3], ab[i].w);
-        if (dxsum) {
-            atomicAdd(&s_red[2][c + 0], ax[i].x); atomicAdd(&s_red[2][c + 1], ax[i].y);
-            atomicAdd(&s_red[2][c + 2], ax[i].z); atomicAdd(&s_red[2][c + 3], ax[i].w);
+        for (int i = 0; i < 2; ++i) {
+            const int c4 = wr * 64 + i * 32 + lane;
+            s_col[0][c4] = ag[i]; s_col[1][c4] = ab[i]; s_col[2][c4] = ax[i];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) {
-        atomicAdd(&dgamma[i], s_red[0][i]);
-        atomicAdd(&dbeta[i], s_red[1][i]);
-        if (dxsum) atomicAdd(&dxsum[i], s_red[2][i]);
+    if (slot == 1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c4 = wr * 64 + i * 32 + lane;
+            f4_add(ag[i], s_col[0][c4]); f4_add(ab[i], s_col[1][c4]); f4_add(ax[i], s_col[2][c4]);
+            red_add_v4(dgamma + c4 * 4, ag[i]);
+            red_add_v4(dbeta + c4 * 4, ab[i]);
+            if (dxsum) red_add_v4(dxsum + c4 * 4, ax[i]);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// bias gradient: db[n] += sum_m dY[m][n]   (dY bf16).  Block = 32 x 8 threads over a 256-column strip.
+// bias gradient: db[n] += sum_m dY[m][n]   (dY bf16).  Block = 32 x 8 threads over a 256-column strip; a thread walks its
+// rows eight at a time (eight independent 16-byte loads in flight) and the eight row groups of a block are combined in
+// shared memory before ONE 16-byte red per 4 columns.  The first version used 96 row groups per strip and 8 scalar
+// atomics per thread: 393 K same-address atomics for a 4096 x 4096 matrix, 15 us for 33 MB.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const uint16_t *__restrict__ dY, int M, int N, float *__restrict__ db) {
-    __shared__ float s[8][33 * 8];
+    __shared__ float4 s[8][32][2];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = (blockIdx.x * 32 + tx) * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (col < N) {
-        for (int r = blockIdx.y * 8 + ty; r < M; r += gridDim.y * 8) {
+        const int step = gridDim.y * 8;
+        int r = blockIdx.y * 8 + ty;
+        for (; r + 7 * step < M; r += 8 * step) {
+            uint4 u[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = ld_nc_v4(dY + (size_t)(r + k * step) * N + col);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float a, b;
+                unpack_bf16x2(u[k].x, a, b); acc[0] += a; acc[1] += b;
+                unpack_bf16x2(u[k].y, a, b); acc[2] += a; acc[3] += b;
+                unpack_bf16x2(u[k].z, a, b); acc[4] += a; acc[5] += b;
+                unpack_bf16x2(u[k].w, a, b); acc[6] += a; acc[7] += b;
+            }
+        }
+        for (; r < M; r += step) {
             const uint4 u = ld_nc_v4(dY + (size_t)r * N + col);
             float a, b;
             unpack_bf16x2(u.x, a, b); acc[0] += a; acc[1] += b;
@@ -148,17 +210,14 @@ colsum_bf16_kernel(const uint16_t *__restrict__ dY, int M, int N, float *__restr
             unpack_bf16x2(u.w, a, b); acc[6] += a; acc[7] += b;
         }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[ty][tx * 8 + i + (tx >> 2)] = acc[i];
+    s[ty][tx][0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    s[ty][tx][1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     __syncthreads();
-    if (ty == 0 && col < N) {
+    if (ty < 2 && col < N) {              // warp 0 sums the low four columns of every lane, warp 1 the high four
+        float4 t = s[0][tx][ty];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float t = 0.0f;
-#pragma unroll
-            for (int y = 0; y < 8; ++y) t += s[y][tx * 8 + i + (tx >> 2)];
-            atomicAdd(&db[col + i], t);
-        }
+        for (int y = 1; y < 8; ++y) f4_add(t, s[y][tx][ty]);
+        red_add_v4(db + col + ty * 4, t);
     }
 }
 
@@ -260,66 +319,102 @@ embed_ln_bwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ w
 //   d_hidden[row(b,t)] = keep * sum_l dlogits[b,t,l] * W[l]      (fp32 rows; the buffer is pre-zeroed, rows are unique)
 //   dW[l] += sum_{b,t} dlogits[b,t,l] * keep * x[row(b,t)],  db[l] += sum dlogits[b,t,l]
 // ------------------------------------------------------------------------------------------
-template <int CPL>
-__global__ void __launch_bounds__(256)
+// Mapping (second design): block = H / 8 threads, thread c owns columns [8c, 8c+8) of EVERY word the block handles and
+// keeps its slice of dW in registers (LG tags x 8 columns; tags beyond LG take another pass over the words), so the
+// weight gradient needs no atomics inside the word loop and leaves as one red.global.add.v4.f32 per 4 columns per block.
+// dlogits and the gather rows of up to kTpbWords words are staged in shared memory per round; the next word's hidden row is
+// fetched while the current one is multiplied.  The first design gave a warp one word and accumulated dW with L x 32
+// fp32 shared-memory atomics (CAS loops) per lane per word: 235 us for 4080 words.
+constexpr int kTpbWords = 32;
+template <int CPL, int LG>
+__global__ void __launch_bounds__(CPL * 32)
 gather_tagproj_bwd_kernel(const uint16_t *__restrict__ hidden, const int32_t *__restrict__ row_of,
                           const int32_t *__restrict__ first_idx, const uint8_t *__restrict__ drop_keep,
                           const float *__restrict__ W, const float *__restrict__ dlogits, int B, int T, int S, int L,
                           float *__restrict__ d_hidden, float *__restrict__ dW, float *__restrict__ db) {
-    constexpr int H = CPL * 256;
-    extern __shared__ __align__(16) float sm[];     // W [L][H] then dW accumulators [L][H]
-    float *w_s = sm, *dw_s = sm + (size_t)L * H;
-    __shared__ float db_s[32];
-    for (int i = threadIdx.x; i < L * H; i += blockDim.x) { w_s[i] = W[i]; dw_s[i] = 0.0f; }
-    if (threadIdx.x < 32) db_s[threadIdx.x] = 0.0f;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int w = blockIdx.x * (blockDim.x >> 5) + warp; w < B * T; w += nwarps) {
-        const int b = w / T, t = w - b * T;
-        const float dl = (lane < L) ? dlogits[(size_t)w * L + lane] : 0.0f;
-        if (lane < L && dl != 0.0f) atomicAdd(&db_s[lane], dl);
-        const int fi = first_idx[w];
-        const bool live = fi >= 0 && (!drop_keep || drop_keep[t] != 0);
-        if (!live) continue;                  // warp-uniform
-        const size_t rowi = (size_t)row_of[b] * S + fi;
-        const uint16_t *hr = hidden + rowi * H;
-        float x[CPL * 8], dh[CPL * 8];
+    constexpr int H = CPL * 256, NT = CPL * 32;
+    extern __shared__ __align__(16) float sm[];     // W [L][H], then dlogits of the staged words [kTpbWords][L]
+    float *w_s = sm, *dl_s = sm + (size_t)L * H;
+    __shared__ long long row_s[kTpbWords];           // gather row of a staged word, -1 = no sub-token / dropped / past the end
+    for (int i = threadIdx.x; i < L * H / 4; i += NT)
+        reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    const int words = B * T;
+    const int col = threadIdx.x * 8;
+    float dbacc = 0.0f;                              // thread l < L: db[l] over this block's words
+    for (int l0 = 0; l0 < L; l0 += LG) {
+        float acc[LG][8];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const uint4 u = ld_nc_v4(hr + c * 256 + lane * 8);
-            unpack_bf16x2(u.x, x[c * 8 + 0], x[c * 8 + 1]);
-            unpack_bf16x2(u.y, x[c * 8 + 2], x[c * 8 + 3]);
-            unpack_bf16x2(u.z, x[c * 8 + 4], x[c * 8 + 5]);
-            unpack_bf16x2(u.w, x[c * 8 + 6], x[c * 8 + 7]);
+        for (int l = 0; l < LG; ++l)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) dh[c * 8 + e] = 0.0f;
-        }
-        for (int l = 0; l < L; ++l) {
-            const float d = __shfl_sync(0xffffffffu, dl, l);
-            const float *wl = w_s + (size_t)l * H;
-            float *dwl = dw_s + (size_t)l * H;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int col = c * 256 + lane * 8 + e;
-                    dh[c * 8 + e] = fmaf(d, wl[col], dh[c * 8 + e]);
-                    atomicAdd(&dwl[col], d * x[c * 8 + e]);
+            for (int e = 0; e < 8; ++e) acc[l][e] = 0.0f;
+        for (int base = blockIdx.x; base < words; base += gridDim.x * kTpbWords) {
+            __syncthreads();                         // previous round consumed (and, first round, W staged)
+            for (int idx = threadIdx.x; idx < kTpbWords * L; idx += NT) {
+                const int i = idx / L, l = idx - i * L;
+                const int w = base + i * gridDim.x;
+                dl_s[idx] = (w < words) ? __ldg(dlogits + (size_t)w * L + l) : 0.0f;
+            }
+            if (threadIdx.x < kTpbWords) {
+                const int w = base + threadIdx.x * gridDim.x;
+                long long r = -1;
+                if (w < words) {
+                    const int b = w / T, t = w - b * T;
+                    const int fi = first_idx[w];
+                    if (fi >= 0 && (!drop_keep || drop_keep[t] != 0)) r = (long long)row_of[b] * S + fi;
                 }
+                row_s[threadIdx.x] = r;
+            }
+            __syncthreads();
+            if (l0 == 0 && threadIdx.x < L) {
+#pragma unroll 4
+                for (int i = 0; i < kTpbWords; ++i) dbacc += dl_s[i * L + threadIdx.x];
+            }
+            uint4 unext = make_uint4(0u, 0u, 0u, 0u);
+            if (row_s[0] >= 0) unext = ld_nc_v4(hidden + (size_t)row_s[0] * H + col);
+#pragma unroll 1
+            for (int i = 0; i < kTpbWords; ++i) {
+                const long long r = row_s[i];
+                const uint4 u = unext;
+                if (i + 1 < kTpbWords && row_s[i + 1] >= 0) unext = ld_nc_v4(hidden + (size_t)row_s[i + 1] * H + col);
+                if (r < 0) continue;                 // block-uniform
+                float x[8], dh[8];
+                unpack_bf16x2(u.x, x[0], x[1]); unpack_bf16x2(u.y, x[2], x[3]);
+                unpack_bf16x2(u.z, x[4], x[5]); unpack_bf16x2(u.w, x[6], x[7]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dh[e] = 0.0f;
+#pragma unroll
+                for (int l = 0; l < LG; ++l) {
+                    if (l0 + l < L) {                // block-uniform
+                        const float d = dl_s[i * L + l0 + l];
+                        const float4 w0 = *reinterpret_cast<const float4 *>(w_s + (size_t)(l0 + l) * H + col);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(w_s + (size_t)(l0 + l) * H + col + 4);
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            dh[e] = fmaf(d, wv[e], dh[e]);
+                            acc[l][e] = fmaf(d, x[e], acc[l][e]);
+                        }
+                    }
+                }
+                float4 *o = reinterpret_cast<float4 *>(d_hidden + (size_t)r * H + col);
+                if (l0 > 0) {                        // later tag groups add to what the first pass wrote (same thread)
+                    const float4 p0 = o[0], p1 = o[1];
+                    dh[0] += p0.x; dh[1] += p0.y; dh[2] += p0.z; dh[3] += p0.w;
+                    dh[4] += p1.x; dh[5] += p1.y; dh[6] += p1.z; dh[7] += p1.w;
+                }
+                o[0] = make_float4(dh[0], dh[1], dh[2], dh[3]);
+                o[1] = make_float4(dh[4], dh[5], dh[6], dh[7]);
             }
         }
-        float *o = d_hidden + rowi * H;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            *reinterpret_cast<float4 *>(o + c * 256 + lane * 8) = make_float4(dh[c * 8], dh[c * 8 + 1], dh[c * 8 + 2], dh[c * 8 + 3]);
-            *reinterpret_cast<float4 *>(o + c * 256 + lane * 8 + 4) = make_float4(dh[c * 8 + 4], dh[c * 8 + 5], dh[c * 8 + 6], dh[c * 8 + 7]);
+        for (int l = 0; l < LG; ++l) {
+            if (l0 + l < L) {
+                red_add_v4(dW + (size_t)(l0 + l) * H + col, make_float4(acc[l][0], acc[l][1], acc[l][2], acc[l][3]));
+                red_add_v4(dW + (size_t)(l0 + l) * H + col + 4, make_float4(acc[l][4], acc[l][5], acc[l][6], acc[l][7]));
+            }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L * H; i += blockDim.x)
-        if (dw_s[i] != 0.0f) atomicAdd(&dW[i], dw_s[i]);
-    if (threadIdx.x < L && db_s[threadIdx.x] != 0.0f) atomicAdd(&db[threadIdx.x], db_s[threadIdx.x]);
+    if (threadIdx.x < L && dbacc != 0.0f) atomicAdd(&db[threadIdx.x], dbacc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,15 +537,16 @@ extern "C" int kbner_add_layernorm_bwd(const float *x, const float *bias, const 
     KBNER_CHECK_ARG(!drop.thresh || dx_masked, "layernorm_bwd: dropout needs the dx_masked output");
     KBNER_CHECK_ARG((uint64_t)M * (uint64_t)(H / 2) < (1ull << 32), "layernorm_bwd: M*H/2 exceeds the 32-bit dropout counter");
     if (M == 0) return KBNER_OK;
-    int blocks = (M + 7) / 8;
-    if (blocks > kNumSMs) blocks = kNumSMs;       // one block per SM: the per-block column partials end in 3*H global atomics
+    KBNER_CHECK_ARG(H % 256 == 0, "layernorm_bwd: hidden size %d must be a multiple of 256", H);
+    int blocks = (M + 1) / 2;                     // two rows per block pass
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;   // <= 128 registers x 256 threads: two blocks per SM, one row prefetched each
     cudaStream_t st = (cudaStream_t)stream;
     if (bias || resid || dres || drop.thresh) {
-        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL, true><<<blocks, 256, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
-                                                                                  dx, dx_masked, dgamma, dbeta, dxsum, drop)));
+        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL / 2, true><<<blocks, VPL * 32, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
+                                                                                          dx, dx_masked, dgamma, dbeta, dxsum, drop)));
     } else {
-        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL, false><<<blocks, 256, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
-                                                                                   dx, dx_masked, dgamma, dbeta, dxsum, drop)));
+        DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL / 2, false><<<blocks, VPL * 32, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
+                                                                                           dx, dx_masked, dgamma, dbeta, dxsum, drop)));
     }
     KBNER_CHECK_LAUNCH("layernorm_bwd");
     return KBNER_OK;
@@ -466,7 +562,8 @@ extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const floa
 extern "C" int kbner_colsum_bf16(const uint16_t *dY, int M, int N, float *db, void *stream) {
     KBNER_CHECK_ARG(dY && db && M >= 0 && N > 0 && N % 8 == 0, "colsum_bf16: bad arguments");
     if (M == 0) return KBNER_OK;
-    dim3 grid((N + 255) / 256, 96);            // ~ a few hundred blocks: the pass is latency-bound otherwise
+    dim3 grid((N + 255) / 256, 1);
+    grid.y = (4 * kNumSMs + grid.x - 1) / grid.x;             // ~4 blocks per SM in total, 8 loads in flight per thread
     if ((int)grid.y * 8 > M) grid.y = (M + 7) / 8;
     colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, M, N, db);
     KBNER_CHECK_LAUNCH("colsum_bf16");
@@ -492,20 +589,21 @@ template <int CPL>
 static int launch_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
                               const uint8_t *drop_keep, const float *W, const float *dlogits, int B, int T, int S, int L,
                               float *d_hidden, float *dW, float *db, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)L * CPL * 256 * sizeof(float);
+    constexpr int LG = 16;
+    const size_t smem = ((size_t)L * CPL * 256 + (size_t)kTpbWords * L) * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gather_tagproj_bwd_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gather_tagproj_bwd_kernel<CPL, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("gather_tagproj_bwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
             return KBNER_ECUDA;
         }
         configured = smem;
     }
-    int blocks = (B * T + 7) / 8;
-    if (blocks > kNumSMs) blocks = kNumSMs;
-    gather_tagproj_bwd_kernel<CPL><<<blocks, 256, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L,
-                                                              d_hidden, dW, db);
+    int blocks = B * T;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    gather_tagproj_bwd_kernel<CPL, LG><<<blocks, CPL * 32, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L,
+                                                                      d_hidden, dW, db);
     KBNER_CHECK_LAUNCH("gather_tagproj_bwd");
     return KBNER_OK;
 }
@@ -514,8 +612,8 @@ extern "C" int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *r
                                         const uint8_t *drop_keep, const float *W, const float *dlogits, int B, int T,
                                         int S, int H, int L, float *d_hidden, float *dW, float *db, void *stream) {
     KBNER_CHECK_ARG(hidden && row_of && first_idx && W && dlogits && d_hidden && dW && db, "gather_tagproj_bwd: null pointer");
-    KBNER_CHECK_ARG(L >= 1 && L <= 32 && H % 256 == 0 && (size_t)2 * L * H * 4 <= 200 * 1024,
-                    "gather_tagproj_bwd: needs L <= 32 and 2*L*H*4 <= 200 KB (L=%d H=%d)", L, H);
+    KBNER_CHECK_ARG(L >= 1 && L <= 32 && H % 256 == 0 && (size_t)L * H * 4 <= 200 * 1024,
+                    "gather_tagproj_bwd: needs L <= 32 and L*H*4 <= 200 KB (L=%d H=%d)", L, H);
     if (B == 0) return KBNER_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (H / 256) {

@@ -180,12 +180,18 @@ class SequenceTagger(torch.nn.Module):
     def _calculate_loss(self, features: torch.Tensor, sentences, mask: torch.Tensor):
         B, T, L = features.shape
         tags = self._gold_tags(sentences, T)
-        keep = mask.bool()
-        if self.remove_x:
-            keep = keep & (tags != self.x_idx)                   # (:2448-2453)
-            self.mask = keep.to(features.dtype)
-        keep_u8 = keep.to(torch.uint8).contiguous()
-        pos, klen = ops.crf_compact(keep_u8)                      # (:2474-2488)
+        if not self.remove_x and mask is self.mask and getattr(self, "lengths_t", None) is not None \
+                and self.lengths_t.numel() == B:
+            # the mask forward() built is the prefix mask of the word counts: no compaction, no index list -- the CRF
+            # kernels stream the emission rows with 16-byte copies
+            pos, klen = None, self.lengths_t
+        else:
+            keep = mask.bool()
+            if self.remove_x:
+                keep = keep & (tags != self.x_idx)               # (:2448-2453)
+                self.mask = keep.to(features.dtype)
+            keep_u8 = keep.to(torch.uint8).contiguous()
+            pos, klen = ops.crf_compact(keep_u8)                  # (:2474-2488)
         self._keep = (pos, klen)
         nll = _CrfNll.apply(features, self.transitions, tags.contiguous(), pos, klen, self.start_idx, self.stop_idx)
         labelled = torch.tensor([0.0 if getattr(s, "is_unlabel", False) else 1.0 for s in sentences],
