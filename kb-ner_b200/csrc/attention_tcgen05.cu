@@ -29,7 +29,7 @@ namespace kbner {
 
 constexpr int kAttnD = 64;
 constexpr int kBQ = 128, kBKV = 64, kKVStages = 3, kMaxS = 512;
-constexpr int kAttnThreads = 288;      // 8 softmax warps (2 threads per query row) + 1 TMA/MMA warp
+constexpr int kAttnThreads = 320;      // 8 softmax warps (2 threads per query row) + MMA warp + TMA producer warp
 constexpr uint32_t kQBytes = 128 * 64 * 2;     // [128 rows][64 bf16], SWIZZLE_128B
 constexpr uint32_t kKVBytes = 64 * 64 * 2;     // [64 keys][64 bf16]
 constexpr uint32_t kAttnTmemCols = 256;
@@ -39,7 +39,9 @@ struct AttnSmem {
     uint8_t k[kKVStages][kKVBytes];
     uint8_t v[kKVStages][kKVBytes];
     uint8_t p[2][kQBytes];             // [buffer][128 rows x 64 keys]
-    uint64_t bar_q;
+    uint64_t bar_q;                    // Q tile of the next work item has landed
+    uint64_t q_free;                   // the last S = Q.K^T of an item has retired: the Q tile may be replaced
+    uint32_t blk_flags[8];             // per key block g (slot g & 7), written by the producer: bit 0 = first of its item, bit 1 = last
     uint64_t k_full[kKVStages], v_full[kKVStages];
     uint64_t k_free[kKVStages];        // S_j = Q.K_j^T retired: the K slot may be refilled (two blocks before its V slot)
     uint64_t v_free[kKVStages];        // P_j.V_j retired: the V slot may be refilled
@@ -47,7 +49,7 @@ struct AttnSmem {
     uint64_t bar_p[2];                 // P_j written to smem buffer j&1 (128 arrivals)
     uint64_t bar_o[2];                 // O_j ready in TMEM buffer j&1
     float xchg[2][2][128];             // [parity][column half][row]: block row-max exchange between the two halves
-    float xsum[2][128];                // [column half][row]: final row-sum exchange
+    float xsum[2][2][128];             // [item parity][column half][row]: final row-sum exchange
     uint32_t tmem_base;
 };
 
@@ -70,18 +72,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Position in a CTA's stream of key blocks: work item w = ((window * heads + head) * nqb + query block), key block j.
+struct BlockCursor {
+    int w, j, nkb, row0, h, qb;
+};
+
 template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                     const int32_t *__restrict__ key_len, int S, int H, int heads, uint16_t *__restrict__ out,
+                     const int32_t *__restrict__ key_len, int R, int S, int H, int heads, uint16_t *__restrict__ out,
                      float *__restrict__ lse_out, const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     AttnSmem &s = *reinterpret_cast<AttnSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
-    const int klen = min(key_len[r], S);
-    const int nkb = (klen + kBKV - 1) / kBKV;        // key blocks that hold at least one valid key
-    const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
+    const int nqb = (S + kBQ - 1) / kBQ;
+    const int total = R * heads * nqb;               // work items; this CTA takes blockIdx.x, blockIdx.x + gridDim.x, ...
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
@@ -92,6 +97,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::prefetch_tensormap(&tmQ);
         ptx::prefetch_tensormap(&tmKV);
         ptx::mbar_init(&s.bar_q, 1);
+        ptx::mbar_init(&s.q_free, 1);
         for (int i = 0; i < kKVStages; ++i) {
             ptx::mbar_init(&s.k_full[i], 1);
             ptx::mbar_init(&s.v_full[i], 1);
@@ -110,40 +116,107 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const uint32_t tmem_s = tmem_base;            // 2 x 64 columns
-    const uint32_t tmem_o = tmem_base + 128;      // 2 x 64 columns
-    pdl_wait();                // Q / K / V come from the preceding GEMM (key_len above is a step input, not a kernel output)
+    const uint32_t tmem_s = tmem_base;            // 2 x 64 columns: S of key block g in buffer g & 1
+    const uint32_t tmem_o = tmem_base + 128;      // 2 x 64 columns: O of the CTA's n-th work item in buffer n & 1
+    pdl_wait();                // Q / K / V come from the preceding GEMM (key_len is a step input, not a kernel output)
 
-    if (warp == 8) {
-        if (lane == 0 && nkb > 0) {
-            // K and V travel separately.  K_m is consumed by S_m, which is issued two key blocks ahead of the softmax, so
-            // its slot is free -- and is refilled with K_{m+3} -- as soon as S_m has retired; V_m's slot is refilled after
-            // P_m.V_m.  Both loads then have two block times to land.  (The first version refilled the K|V pair of block m
-            // only after P_m.V_m and needed it one block later: 84 % of the softmax warps' first polls of `bar_s` failed,
-            // 18 % of all stall samples sat on that wait -- profiles/r01/attn_fwd_ncu_r38.txt.)
-            auto load_k = [&](int m) {
-                const int st = m % kKVStages;
-                ptx::mbar_expect_tx(&s.k_full[st], kKVBytes);
-                ptx::tma_load_2d(s.k[st], &tmKV, &s.k_full[st], H + h * kAttnD, row0 + m * kBKV);
-            };
-            auto load_v = [&](int m) {
-                const int st = m % kKVStages;
-                ptx::mbar_expect_tx(&s.v_full[st], kKVBytes);
-                ptx::tma_load_2d(s.v[st], &tmKV, &s.v_full[st], 2 * H + h * kAttnD, row0 + m * kBKV);
-            };
-            ptx::mbar_expect_tx(&s.bar_q, kQBytes);
-            ptx::tma_load_2d(s.q, &tmQ, &s.bar_q, h * kAttnD, row0 + qb * kBQ);
-            for (int m = 0; m < nkb && m < kKVStages; ++m) load_k(m);
-            for (int m = 0; m < nkb && m < kKVStages; ++m) load_v(m);
+    // every barrier and ring slot is indexed by g, the running count of key blocks this CTA has gone through (all items)
+    auto open_item = [&](BlockCursor &c) {           // decode c.w, skipping windows without a valid key; c.nkb == 0 at the end
+        c.nkb = 0;
+        while (c.w < total) {
+            const int rh = c.w / nqb;
+            const int r = rh / heads;
+            const int nkb = (min(__ldg(key_len + r), S) + kBKV - 1) / kBKV;
+            if (nkb > 0) {
+                c.qb = c.w - rh * nqb;
+                c.h = rh - r * heads;
+                c.row0 = r * S;
+                c.nkb = nkb;
+                return;
+            }
+            c.w += gridDim.x;
+        }
+    };
+    auto advance = [&](BlockCursor &c) {
+        if (++c.j == c.nkb) {
+            c.w += gridDim.x;
+            c.j = 0;
+            open_item(c);
+        }
+    };
 
-            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);   // S = Q.K^T : both K-major
-            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);   // O = P.V   : V is MN-major
-            const uint32_t q_addr = ptx::smem_u32(s.q);
-            auto issue_s = [&](int m) {
-                const int st = m % kKVStages;
-                ptx::mbar_wait(&s.k_full[st], (m / kKVStages) & 1);
-                ptx::tc_fence_after();
-                const uint32_t k_addr = ptx::smem_u32(s.k[st]);
+    if (warp == 9) {
+        // ===================== TMA producer (warp-uniform; the copy itself under elect.sync) =====================
+        // Walks this CTA's key-block stream once for K (and the Q tile at each item's first block) and, two blocks behind,
+        // once for V.  K_t goes into slot t % 3 as soon as S_{t-3} has retired, V_t after P.V of block t-3; the Q tile of the
+        // next item replaces the current one when the item's last S has retired.  All the per-item address arithmetic
+        // (integer divisions, the key_len load) lives here, off the MMA warp's serial instruction stream.
+        BlockCursor kc{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        open_item(kc);
+        BlockCursor vc = kc;
+        uint32_t t = 0, kslot = 0, kuse = 0, vslot = 0, vuse = 0, nq = 0;     // use = how often the slot has been filled
+        while (kc.nkb != 0 || vc.nkb != 0) {
+            if (kc.nkb != 0) {
+                if (kuse > 0) ptx::mbar_wait(&s.k_free[kslot], (kuse - 1) & 1);
+                const bool first = kc.j == 0;
+                if (ptx::elect_one()) {
+                    s.blk_flags[t & 7] = (first ? 1u : 0u) | (kc.j == kc.nkb - 1 ? 2u : 0u);
+                    ptx::mbar_expect_tx(&s.k_full[kslot], kKVBytes);
+                    ptx::tma_load_2d(s.k[kslot], &tmKV, &s.k_full[kslot], H + kc.h * kAttnD, kc.row0 + kc.j * kBKV);
+                }
+                __syncwarp();
+                if (++kslot == kKVStages) { kslot = 0; ++kuse; }
+            }
+            if (t >= 2 && vc.nkb != 0) {
+                if (vuse > 0) ptx::mbar_wait(&s.v_free[vslot], (vuse - 1) & 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(&s.v_full[vslot], kKVBytes);
+                    ptx::tma_load_2d(s.v[vslot], &tmKV, &s.v_full[vslot], 2 * H + vc.h * kAttnD, vc.row0 + vc.j * kBKV);
+                }
+                __syncwarp();
+                if (++vslot == kKVStages) { vslot = 0; ++vuse; }
+                advance(vc);
+            }
+            if (kc.nkb != 0) {
+                if (kc.j == 0) {                     // Q of this item (after the previous item's last S)
+                    if (nq > 0) ptx::mbar_wait(&s.q_free, (nq - 1) & 1);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(&s.bar_q, kQBytes);
+                        ptx::tma_load_2d(s.q, &tmQ, &s.bar_q, kc.h * kAttnD, kc.row0 + kc.qb * kBQ);
+                    }
+                    __syncwarp();
+                    ++nq;
+                }
+                advance(kc);
+            }
+            ++t;
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer: WARP-UNIFORM, only the issuing instructions sit under elect.sync ===============
+        // (Under `if (lane == 0)` ptxas wraps every UTCHMMA / UTCBAR in an ELECT / PLOP3 / BRA.U.ANY loop.)  This warp's
+        // instruction stream is serial and shares a scheduler with four softmax warps -- measured ~10 cycles per
+        // instruction -- so it carries nothing but waits, 8 MMAs and their commits per key block: S = Q.K^T runs two blocks
+        // ahead of the softmax, P.V follows it; item boundaries arrive as flags from the producer.
+        int G = 0;                                   // key blocks in this CTA's stream
+        for (int w = blockIdx.x + lane * gridDim.x; w < total; w += 32 * gridDim.x)
+            G += (min(__ldg(key_len + w / (nqb * heads)), S) + kBKV - 1) / kBKV;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) G += __shfl_xor_sync(0xffffffffu, G, o);
+        constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);   // S = Q.K^T : both K-major
+        constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, 64, 0, 1);   // O = P.V   : V is MN-major
+        const uint32_t q_addr = ptx::smem_u32(s.q);
+        const uint32_t k_addr0 = ptx::smem_u32(s.k[0]), v_addr0 = ptx::smem_u32(s.v[0]), p_addr0 = ptx::smem_u32(s.p[0]);
+        uint32_t kslot = 0, kuse = 0, vslot = 0, vuse = 0, nq = 0, obuf = 0;
+        auto issue_s = [&](int m) {                  // S of block m into TMEM buffer m & 1
+            ptx::mbar_wait(&s.k_full[kslot], kuse & 1);
+            const uint32_t f = s.blk_flags[m & 7];
+            if (f & 1u) {
+                ptx::mbar_wait(&s.bar_q, nq & 1);
+                ++nq;
+            }
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t k_addr = k_addr0 + kslot * kKVBytes;
 #pragma unroll
                 for (int kk = 0; kk < kAttnD / 16; ++kk) {
                     const uint64_t da = ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024);
@@ -151,42 +224,37 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     ptx::mma_f16_ss(tmem_s + (m & 1) * 64, da, db, idesc_s, kk != 0);
                 }
                 ptx::mma_commit(&s.bar_s[m & 1]);
-                ptx::mma_commit(&s.k_free[st]);
-            };
-            auto refill_k = [&](int m) {           // K_m into the slot of K_{m-3}, whose S has retired
-                if (m < nkb) {
-                    ptx::mbar_wait(&s.k_free[m % kKVStages], ((m - kKVStages) / kKVStages) & 1);
-                    load_k(m);
-                }
-            };
-            ptx::mbar_wait(&s.bar_q, 0);
-            issue_s(0);
-            if (nkb > 1) issue_s(1);
-            refill_k(kKVStages);
-            for (int j = 0; j < nkb; ++j) {
-                const int st = j % kKVStages;
-                // P_j in smem (the softmax warps executed fence.proxy.async before arriving)
-                ptx::mbar_wait(&s.bar_p[j & 1], (j >> 1) & 1);
-                ptx::mbar_wait(&s.v_full[st], (j / kKVStages) & 1);
-                ptx::tc_fence_after();
-                const uint32_t v_addr = ptx::smem_u32(s.v[st]);
-                const uint32_t p_addr = ptx::smem_u32(s.p[j & 1]);
+                ptx::mma_commit(&s.k_free[kslot]);
+                if (f & 2u) ptx::mma_commit(&s.q_free);
+            }
+            __syncwarp();
+            if (++kslot == kKVStages) { kslot = 0; ++kuse; }
+        };
+        if (G > 0) issue_s(0);
+        if (G > 1) issue_s(1);
+        for (int g = 0; g < G; ++g) {
+            // P_g in smem (the softmax warps executed fence.proxy.async before arriving)
+            ptx::mbar_wait(&s.bar_p[g & 1], (g >> 1) & 1);
+            ptx::mbar_wait(&s.v_full[vslot], vuse & 1);
+            const uint32_t f = s.blk_flags[g & 7];
+            if ((f & 1u) && g > 0) obuf ^= 1u;       // a new item accumulates into the other O buffer
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t v_addr = v_addr0 + vslot * kKVBytes;
+                const uint32_t p_addr = p_addr0 + (g & 1) * kQBytes;
 #pragma unroll
                 for (int kk = 0; kk < kBKV / 16; ++kk) {
                     const uint64_t da = ptx::make_sw128_desc(p_addr + kk * 32, 16, 1024);
                     // V tile [key][d]: 16 keys per MMA = two 8-row swizzle atoms, 1024 B apart (SBO)
                     const uint64_t db = ptx::make_sw128_desc(v_addr + kk * 16 * 128, 16, 1024);
-                    ptx::mma_f16_ss(tmem_o, da, db, idesc_o, (j != 0) || (kk != 0));   // O accumulates in TMEM over the key blocks
+                    ptx::mma_f16_ss(tmem_o + obuf * 64, da, db, idesc_o, !(f & 1u) || (kk != 0));   // O accumulates in TMEM
                 }
-                ptx::mma_commit(&s.bar_o[j & 1]);
-                ptx::mma_commit(&s.v_free[st]);
-                if (j + 2 < nkb) issue_s(j + 2);   // S buffer j&1 was drained before P_j was published
-                refill_k(j + 1 + kKVStages);       // slot of K_{j+1}: S_{j+1} was issued one block ago
-                if (j >= 1 && j + 2 < nkb) {       // slot of V_{j-1}: P_{j-1}.V_{j-1} was issued one block ago
-                    ptx::mbar_wait(&s.v_free[(j - 1) % kKVStages], ((j - 1) / kKVStages) & 1);
-                    load_v(j + 2);
-                }
+                ptx::mma_commit(&s.bar_o[g & 1]);
+                ptx::mma_commit(&s.v_free[vslot]);
             }
+            __syncwarp();
+            if (++vslot == kKVStages) { vslot = 0; ++vuse; }
+            if (g + 2 < G) issue_s(g + 2);           // its S buffer was drained before P_g was published
         }
     } else {
         // ===================== softmax warps: two threads per query row =====================
@@ -195,133 +263,143 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // resident CTAs) instead of two: the round-1 kernel was latency-bound with MUFU and issue both at ~40 %.
         const int quarter = warp & 3, half = warp >> 2;
         const int row = quarter * 32 + lane;              // TMEM lane == row in the query block
-        const int qrow = qb * kBQ + row;                  // sub-token index inside the window
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
-        float m_run = -CUDART_INF_F, l_run = 0.0f;
         const uint32_t dkey = DROP ? drop_key(drop) : 0u;
-        // dropout counter of (window, head, query): 256 key PAIRS per row (kMaxS / 2), the same in the backward kernel
-        const uint32_t drow = (((uint32_t)(r * heads + h) * (uint32_t)kMaxS) + (uint32_t)qrow) * (uint32_t)(kMaxS / 2);
-        const uint32_t o_addr = tmem_o + lane_addr + half * 32;     // this thread's 32 of the 64 output columns
+        uint32_t g = 0, n_item = 0, n_epi = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x, ++n_epi) {
+            const int rh = w / nqb;
+            const int qb = w - rh * nqb, r = rh / heads;
+            const int h = rh - r * heads;
+            const int klen = min(__ldg(key_len + r), S);
+            const int nkb = (klen + kBKV - 1) / kBKV;        // key blocks that hold at least one valid key
+            const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
+            const int qrow = qb * kBQ + row;                  // sub-token index inside the window
+            float m_run = -CUDART_INF_F, l_run = 0.0f;
+            // dropout counter of (window, head, query): 256 key PAIRS per row (kMaxS / 2), the same in the backward kernel
+            const uint32_t drow = (((uint32_t)(r * heads + h) * (uint32_t)kMaxS) + (uint32_t)qrow) * (uint32_t)(kMaxS / 2);
+            const uint32_t o_addr = tmem_o + (n_item & 1) * 64 + lane_addr + half * 32;     // this thread's 32 of the 64 output columns
 
-        for (int j = 0; j < nkb; ++j) {
-            ptx::mbar_wait(&s.bar_s[j & 1], (j >> 1) & 1);
-            ptx::tc_fence_after();
-            float sc[32];
-            {
-                uint32_t rs[32];
-                ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (j & 1) * 64 + half * 32, rs);
-                ptx::tmem_ld_wait();
+            for (int j = 0; j < nkb; ++j, ++g) {
+                ptx::mbar_wait(&s.bar_s[g & 1], (g >> 1) & 1);
+                ptx::tc_fence_after();
+                float sc[32];
+                {
+                    uint32_t rs[32];
+                    ptx::tmem_ld_32x32b_x32(tmem_s + lane_addr + (g & 1) * 64 + half * 32, rs);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sc[i] = __uint_as_float(rs[i]);
+                    for (int i = 0; i < 32; ++i) sc[i] = __uint_as_float(rs[i]);
+                }
+                ptx::tc_fence_before();
+                const int kbase = j * kBKV + half * 32;
+                if (kbase + 32 > klen) {         // only the last block of the window is ragged
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (kbase + i >= klen) sc[i] = -CUDART_INF_F;
+                }
+                float m_half = sc[0];
+#pragma unroll
+                for (int i = 1; i < 31; i += 2) m_half = fmax3(m_half, sc[i], sc[i + 1]);      // FMNMX3: 16 instead of 31 issue slots
+                m_half = fmaxf(m_half, sc[31]);
+                // row max over both halves: exchange through shared memory, pair barrier = the two warps of this quarter
+                s.xchg[g & 1][half][row] = m_half;
+                asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+                const float m_blk = fmaxf(m_half, s.xchg[g & 1][half ^ 1][row]) * scale_log2;   // finite: the block has >= 1 valid key
+                // LAZY rescaling: the running O lives in TMEM and is only touched when the row maximum grows by more than 2^8;
+                // otherwise the stale maximum stays the reference (probabilities up to 256 are exact enough in bf16 / fp32 and the
+                // final division by the row sum cancels the common factor).  Both threads of a row take the same decision (same
+                // m_blk, same m_run).  tcgen05.ld / .st are warp-collective: the decision is taken per WARP (any row of the warp
+                // over the threshold -> all 32 rows do the exact online-softmax update); warps w and w+4 see identical per-row
+                // values, so both halves of a row agree.
+                if (j == 0) {
+                    m_run = m_blk;
+                } else if (__any_sync(0xffffffffu, m_blk > m_run + 8.0f)) {
+                    const float m_new = fmaxf(m_run, m_blk);
+                    const float alpha = ex2_approx(m_run - m_new);
+                    m_run = m_new;
+                    l_run *= alpha;
+                    ptx::mbar_wait(&s.bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // P.V of the previous block has retired
+                    ptx::tc_fence_after();
+                    uint32_t ro[32];
+                    ptx::tmem_ld_32x32b_x32(o_addr, ro);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                    tmem_st_32x32b_x32(o_addr, ro);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    ptx::tc_fence_before();
+                }
+                const float neg_m = -m_run;
+                float l_blk = 0.0f, l_blk1 = 0.0f;
+                uint8_t *prow = s.p[g & 1] + row * 128;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    float pv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {          // packed fp32: one FFMA2 + one FADD2 per two scores
+                        float x0, x1;
+                        ffma2(x0, x1, sc[cc * 8 + e], sc[cc * 8 + e + 1], scale_log2, neg_m);
+                        pv[e] = ex2_approx(x0);
+                        pv[e + 1] = ex2_approx(x1);
+                        fadd2(l_blk, l_blk1, pv[e], pv[e + 1]);
+                    }
+                    if (DROP) {                  // the softmax denominator is of the un-dropped row; only P.V sees the mask
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const uint32_t bits = drop_bits(dkey, drow + (uint32_t)((kbase + cc * 8) >> 1) + e2);
+                            if (!drop_keep_lo(bits, drop.thresh)) pv[2 * e2] = 0.0f;
+                            if (!drop_keep_hi(bits, drop.thresh)) pv[2 * e2 + 1] = 0.0f;
+                        }
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16x2(pv[0], pv[1]);
+                    pk.y = pack_bf16x2(pv[2], pv[3]);
+                    pk.z = pack_bf16x2(pv[4], pv[5]);
+                    pk.w = pack_bf16x2(pv[6], pv[7]);
+                    *reinterpret_cast<uint4 *>(prow + (((half * 4 + cc) ^ (row & 7)) << 4)) = pk;
+                }
+                l_run += l_blk + l_blk1;            // partial row sum over this thread's columns (both halves share m_run)
+                ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
+                ptx::mbar_arrive(&s.bar_p[g & 1]);
             }
-            ptx::tc_fence_before();
-            const int kbase = j * kBKV + half * 32;
-            if (kbase + 32 > klen) {         // only the last block of the window is ragged
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (kbase + i >= klen) sc[i] = -CUDART_INF_F;
-            }
-            float m_half = sc[0];
-#pragma unroll
-            for (int i = 1; i < 31; i += 2) m_half = fmax3(m_half, sc[i], sc[i + 1]);      // FMNMX3: 16 instead of 31 issue slots
-            m_half = fmaxf(m_half, sc[31]);
-            // row max over both halves: exchange through shared memory, pair barrier = the two warps of this quarter
-            s.xchg[j & 1][half][row] = m_half;
-            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-            const float m_blk = fmaxf(m_half, s.xchg[j & 1][half ^ 1][row]) * scale_log2;   // finite: the block has >= 1 valid key
-            // LAZY rescaling: the running O lives in TMEM and is only touched when the row maximum grows by more than 2^8;
-            // otherwise the stale maximum stays the reference (probabilities up to 256 are exact enough in bf16 / fp32 and the
-            // final division by the row sum cancels the common factor).  Both threads of a row take the same decision (same
-            // m_blk, same m_run).  Removes a TMEM load + 32 FMAs + a barrier wait per block from the round-1 kernel.
-            // tcgen05.ld / .st are warp-collective: the decision is taken per WARP (any row of the warp over the threshold ->
-            // all 32 rows do the exact online-softmax update); warps w and w+4 see identical per-row values, so both halves
-            // of a row agree.
-            if (j == 0) {
-                m_run = m_blk;
-            } else if (__any_sync(0xffffffffu, m_blk > m_run + 8.0f)) {
-                const float m_new = fmaxf(m_run, m_blk);
-                const float alpha = ex2_approx(m_run - m_new);
-                m_run = m_new;
-                l_run *= alpha;
-                ptx::mbar_wait(&s.bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);    // P_{j-1}.V_{j-1} has retired
+            float o_acc[32];
+            if (nkb > 0) {
+                ptx::mbar_wait(&s.bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);
                 ptx::tc_fence_after();
                 uint32_t ro[32];
                 ptx::tmem_ld_32x32b_x32(o_addr, ro);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-                tmem_st_32x32b_x32(o_addr, ro);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(ro[i]);
                 ptx::tc_fence_before();
+                ++n_item;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
             }
-            const float neg_m = -m_run;
-            float l_blk = 0.0f, l_blk1 = 0.0f;
-            uint8_t *prow = s.p[j & 1] + row * 128;
+            // total row sum = both halves.  The exchange slot alternates per item: the partner warp reads slot p after this
+            // pair barrier and cannot see the slot rewritten before it has passed the NEXT pair barrier.
+            s.xsum[n_epi & 1][half][row] = l_run;
+            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+            const float l_tot = l_run + s.xsum[n_epi & 1][half ^ 1][row];
+            // epilogue: normalise, bf16, 64 contiguous bytes per thread
+            if (qrow < S) {
+                const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
+                uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                float pv[8];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {          // packed fp32: one FFMA2 + one FADD2 per two scores
-                    float x0, x1;
-                    ffma2(x0, x1, sc[cc * 8 + e], sc[cc * 8 + e + 1], scale_log2, neg_m);
-                    pv[e] = ex2_approx(x0);
-                    pv[e + 1] = ex2_approx(x1);
-                    fadd2(l_blk, l_blk1, pv[e], pv[e + 1]);
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 o;
+                    o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+                    o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+                    o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+                    o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                    *reinterpret_cast<uint4 *>(orow + i) = o;
                 }
-                if (DROP) {                  // the softmax denominator is of the un-dropped row; only P.V sees the mask
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const uint32_t bits = drop_bits(dkey, drow + (uint32_t)((kbase + cc * 8) >> 1) + e2);
-                        if (!drop_keep_lo(bits, drop.thresh)) pv[2 * e2] = 0.0f;
-                        if (!drop_keep_hi(bits, drop.thresh)) pv[2 * e2 + 1] = 0.0f;
-                    }
-                }
-                uint4 pk;
-                pk.x = pack_bf16x2(pv[0], pv[1]);
-                pk.y = pack_bf16x2(pv[2], pv[3]);
-                pk.z = pack_bf16x2(pv[4], pv[5]);
-                pk.w = pack_bf16x2(pv[6], pv[7]);
-                *reinterpret_cast<uint4 *>(prow + (((half * 4 + cc) ^ (row & 7)) << 4)) = pk;
+                if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
+                    lse_out[((size_t)r * heads + h) * S + qrow] =
+                        (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
             }
-            l_run += l_blk + l_blk1;            // partial row sum over this thread's columns (both halves share m_run)
-            ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
-            ptx::mbar_arrive(&s.bar_p[j & 1]);
-        }
-        float o_acc[32];
-        if (nkb > 0) {
-            ptx::mbar_wait(&s.bar_o[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
-            ptx::tc_fence_after();
-            uint32_t ro[32];
-            ptx::tmem_ld_32x32b_x32(o_addr, ro);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(ro[i]);
-            ptx::tc_fence_before();
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
-        }
-        // total row sum = both halves
-        s.xsum[half][row] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-        const float l_tot = l_run + s.xsum[half ^ 1][row];
-        // epilogue: normalise, bf16, 64 contiguous bytes per thread
-        if (qrow < S) {
-            const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
-            uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-                o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-                o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-                o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-                *reinterpret_cast<uint4 *>(orow + i) = o;
-            }
-            if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
-                lse_out[((size_t)r * heads + h) * S + qrow] =
-                    (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
         }
     }
     ptx::tc_fence_before();
@@ -364,14 +442,19 @@ extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *k
         }
         configured = true;
     }
-    dim3 grid((S + kBQ - 1) / kBQ, heads, R);
+    // persistent: two CTAs per SM, each walking work items (window, head, query block) blockIdx.x, blockIdx.x + grid, ...
+    // One CTA per item spent 41 % of its life outside the key-block loop (3.9 k cycles until the first S was ready, ~5 k
+    // for the last P.V, the read-out, teardown and the next launch) -- measured with clock64 stamps, see profiles/README.md.
+    const long long total = (long long)R * heads * ((S + kBQ - 1) / kBQ);
+    KBNER_CHECK_ARG(total < (1ll << 30), "attention_fwd: too many work items");
+    dim3 grid((unsigned)(total < 2 * kNumSMs ? total : 2 * kNumSMs));
     cudaError_t le;
     if (drop.thresh)
         le = launch_kernel(attention_fwd_kernel<true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, S, H, heads, out, lse, drop);
+                           key_len, R, S, H, heads, out, lse, drop);
     else
         le = launch_kernel(attention_fwd_kernel<false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, S, H, heads, out, lse, drop);
+                           key_len, R, S, H, heads, out, lse, drop);
     if (le != cudaSuccess) {
         set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
         return KBNER_ECUDA;

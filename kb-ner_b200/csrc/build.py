@@ -17,7 +17,7 @@ SOURCES = ["runtime.cu", "crf.cu", "crf_viterbi.cu", "elementwise.cu", "gemm_tcg
 HEADERS = ["common.cuh", "crf_common.cuh", "tc_ptx.cuh", "cluster_ptx.cuh", "tma_host.cuh", os.path.join("..", "..", "include", "kbner_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"] + os.environ.get("KBNER_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _stale(target, deps):
