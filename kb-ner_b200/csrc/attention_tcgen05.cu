@@ -72,6 +72,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+#ifdef KBNER_ATTN_DEBUG
+// timeline probe (debug builds only, scripts/attn_timeline.py): clock64 stamps of CTA 0 / CTA 150,
+// [cta][role 0 = MMA warp, 1 = softmax warp 0, 2 = softmax warp 7][key block g < 24][stamp]
+__device__ unsigned long long g_attn_dbg[2 * 3 * 24 * 4];
+#define ATTN_STAMP(role, g, k)                                                                                      \
+    do {                                                                                                            \
+        if (dbg_cta >= 0 && (role) >= 0 && lane == 0 && (g) < 24)                                                   \
+            g_attn_dbg[((dbg_cta * 3 + (role)) * 24 + (g)) * 4 + (k)] = clock64();                                   \
+    } while (0)
+#else
+#define ATTN_STAMP(role, g, k) do { } while (0)
+#endif
+
 // Position in a CTA's stream of key blocks: work item w = ((window * heads + head) * nqb + query block), key block j.
 struct BlockCursor {
     int w, j, nkb, row0, h, qb;
@@ -88,6 +101,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int nqb = (S + kBQ - 1) / kBQ;
     const int total = R * heads * nqb;               // work items; this CTA takes blockIdx.x, blockIdx.x + gridDim.x, ...
 
+#ifdef KBNER_ATTN_DEBUG
+    const int dbg_cta = blockIdx.x == 0 ? 0 : (blockIdx.x == 150 ? 1 : -1);
+#endif
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) {
@@ -235,7 +251,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int g = 0; g < G; ++g) {
             // P_g in smem (the softmax warps executed fence.proxy.async before arriving)
             ptx::mbar_wait(&s.bar_p[g & 1], (g >> 1) & 1);
+            ATTN_STAMP(0, g, 0);
             ptx::mbar_wait(&s.v_full[vslot], vuse & 1);
+            ATTN_STAMP(0, g, 1);
             const uint32_t f = s.blk_flags[g & 7];
             if ((f & 1u) && g > 0) obuf ^= 1u;       // a new item accumulates into the other O buffer
             ptx::tc_fence_after();
@@ -254,7 +272,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             __syncwarp();
             if (++vslot == kKVStages) { vslot = 0; ++vuse; }
+            ATTN_STAMP(0, g, 2);
             if (g + 2 < G) issue_s(g + 2);           // its S buffer was drained before P_g was published
+            ATTN_STAMP(0, g, 3);
         }
     } else {
         // ===================== softmax warps: two threads per query row =====================
@@ -267,11 +287,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float scale_log2 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
         const uint32_t dkey = DROP ? drop_key(drop) : 0u;
         uint32_t g = 0, n_item = 0, n_epi = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x, ++n_epi) {
+        // The read-out of an item (wait for its last P.V, O from TMEM, normalise, store) is DEFERRED until this warp has
+        // finished the first key block of the NEXT item: O is double-buffered in TMEM and the next S is already waiting, so
+        // the all-warps-arrive -> last P.V -> read-out chain (3.9-4.5 k cycles per item in the clock64 timeline) leaves the
+        // critical path.  `pend_*` is the item whose read-out is outstanding.
+        bool pend = false;
+        float pend_m = 0.0f, pend_l = 0.0f;
+        int pend_qrow = 0, pend_row0 = 0, pend_h = 0, pend_r = 0;
+        uint32_t pend_o = 0, pend_g = 0;
+        auto read_out = [&](bool from_tmem, uint32_t o_addr, uint32_t g_last, float m_run, float l_run, int qrow, int row0,
+                            int h, int r) {
+            float o_acc[32];
+            if (from_tmem) {
+                ptx::mbar_wait(&s.bar_o[g_last & 1], (g_last >> 1) & 1);
+                ptx::tc_fence_after();
+                uint32_t ro[32];
+                ptx::tmem_ld_32x32b_x32(o_addr, ro);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(ro[i]);
+                ptx::tc_fence_before();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
+            }
+            // total row sum = both halves.  The exchange slot alternates per read-out: the partner warp reads slot p after
+            // this pair barrier and cannot see the slot rewritten before it has passed the NEXT pair barrier.
+            s.xsum[n_epi & 1][half][row] = l_run;
+            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+            const float l_tot = l_run + s.xsum[n_epi & 1][half ^ 1][row];
+            ++n_epi;
+            // normalise, bf16, 64 contiguous bytes per thread
+            if (qrow < S) {
+                const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
+                uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 o;
+                    o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+                    o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+                    o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+                    o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                    *reinterpret_cast<uint4 *>(orow + i) = o;
+                }
+                if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
+                    lse_out[((size_t)r * heads + h) * S + qrow] =
+                        (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
+            }
+        };
+        int klen_next = (int)blockIdx.x < total ? __ldg(key_len + blockIdx.x / (nqb * heads)) : 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int rh = w / nqb;
             const int qb = w - rh * nqb, r = rh / heads;
             const int h = rh - r * heads;
-            const int klen = min(__ldg(key_len + r), S);
+            const int klen = min(klen_next, S);
+            if (w + (int)gridDim.x < total) klen_next = __ldg(key_len + (w + gridDim.x) / (nqb * heads));   // lands during this item
             const int nkb = (klen + kBKV - 1) / kBKV;        // key blocks that hold at least one valid key
             const int row0 = r * S;                          // first row of this window in the [R*S, 3H] matrix
             const int qrow = qb * kBQ + row;                  // sub-token index inside the window
@@ -281,7 +351,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t o_addr = tmem_o + (n_item & 1) * 64 + lane_addr + half * 32;     // this thread's 32 of the 64 output columns
 
             for (int j = 0; j < nkb; ++j, ++g) {
+                ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 0);
                 ptx::mbar_wait(&s.bar_s[g & 1], (g >> 1) & 1);
+                ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 1);
                 ptx::tc_fence_after();
                 float sc[32];
                 {
@@ -330,6 +402,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     ptx::tc_fence_before();
                 }
+                ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 2);
                 const float neg_m = -m_run;
                 float l_blk = 0.0f, l_blk1 = 0.0f;
                 uint8_t *prow = s.p[g & 1] + row * 128;
@@ -362,45 +435,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 l_run += l_blk + l_blk1;            // partial row sum over this thread's columns (both halves share m_run)
                 ptx::fence_proxy_async_smem();      // generic-proxy writes -> async proxy (tensor core)
                 ptx::mbar_arrive(&s.bar_p[g & 1]);
-            }
-            float o_acc[32];
-            if (nkb > 0) {
-                ptx::mbar_wait(&s.bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                ptx::tc_fence_after();
-                uint32_t ro[32];
-                ptx::tmem_ld_32x32b_x32(o_addr, ro);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[i] = __uint_as_float(ro[i]);
-                ptx::tc_fence_before();
-                ++n_item;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
-            }
-            // total row sum = both halves.  The exchange slot alternates per item: the partner warp reads slot p after this
-            // pair barrier and cannot see the slot rewritten before it has passed the NEXT pair barrier.
-            s.xsum[n_epi & 1][half][row] = l_run;
-            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
-            const float l_tot = l_run + s.xsum[n_epi & 1][half ^ 1][row];
-            // epilogue: normalise, bf16, 64 contiguous bytes per thread
-            if (qrow < S) {
-                const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
-                uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 o;
-                    o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-                    o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-                    o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-                    o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-                    *reinterpret_cast<uint4 *>(orow + i) = o;
+                ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 3);
+                if (j == 0 && pend) {            // the previous item's read-out, now that this item's first block is under way
+                    read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    pend = false;
                 }
-                if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
-                    lse_out[((size_t)r * heads + h) * S + qrow] =
-                        (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
+            }
+            if (nkb > 0) {
+                pend = true;
+                pend_m = m_run; pend_l = l_run; pend_qrow = qrow; pend_row0 = row0; pend_h = h; pend_r = r;
+                pend_o = o_addr; pend_g = g - 1;
+                ++n_item;
+            } else {                             // window without a valid key: zeros (flush the outstanding read-out first)
+                if (pend) {
+                    read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    pend = false;
+                }
+                read_out(false, 0u, 0u, m_run, l_run, qrow, row0, h, r);
             }
         }
+        if (pend) read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -462,6 +516,12 @@ extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *k
     KBNER_CHECK_LAUNCH("attention_fwd");
     return KBNER_OK;
 }
+
+#ifdef KBNER_ATTN_DEBUG
+extern "C" int kbner_attention_debug_read(unsigned long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_attn_dbg, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                    uint16_t *out, float *lse, void *stream) {
