@@ -396,10 +396,10 @@ def run_train(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-        for i in range(ACC):
-            step(i)
-        opt.zero_grad()
-        torch.cuda.synchronize()
+    for i in range(ACC):          # every rank: step() contains the gradient all-reduce
+        step(i)
+    opt.zero_grad()
+    torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     l0 = kbner_b200._lib.launch_count()

@@ -14,8 +14,11 @@ g = torch.Generator(device=dev).manual_seed(0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timeit(fn, reps=9):
-    for _ in range(3):
+REPS, WARM = int(os.environ.get("REPS", "9")), int(os.environ.get("WARM", "3"))   # REPS=1 WARM=0: one launch each (ncu)
+
+
+def timeit(fn, reps=REPS):
+    for _ in range(WARM):
         fn()
     ts = []
     for _ in range(reps):
