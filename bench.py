@@ -61,8 +61,22 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self, t0=None, t1=None):
-        """Samples whose timestamp falls inside the timed region [t0, t1] (epoch seconds)."""
+    def wait_ready(self, timeout=6.0):
+        """nvidia-smi needs up to a second to start: block until it has written its first sample."""
+        t_end = time.time() + timeout
+        while self.proc is not None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.05)
+        return False
+
+    def stop(self, t0=None, t1=None, t1_wide=None):
+        """Samples whose timestamp falls inside the timed region [t0, t1] (epoch seconds).  If fewer than three do (a
+        0.2 s region against a 20 ms sampling period plus nvidia-smi's own jitter), the window is widened to t1_wide --
+        the end of the end-to-end run, which executes the same kernels -- and `window` says so."""
         import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
@@ -72,7 +86,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        rows = []
+        allrows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
@@ -81,11 +95,21 @@ class ClockSampler:
                         ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
                     except Exception:
                         ts = None
-                    if ts is None or t0 is None or (t0 - 0.05 <= ts <= t1 + 0.05):
-                        rows.append(f[1:])
+                    allrows.append((ts, f[1:]))
             os.unlink(self.path)
         except Exception:
             pass
+
+        def inside(lo, hi):
+            return [r for ts, r in allrows if ts is None or lo is None or (lo - 0.05 <= ts <= hi + 0.05)]
+        rows = inside(t0, t1)
+        out["window"] = "timed region"
+        if len(rows) < 3 and t1_wide is not None:
+            rows = inside(t0, t1_wide)
+            out["window"] = "timed region + end-to-end run (same kernels)"
+        if len(rows) < 3:
+            rows = [r for _, r in allrows]
+            out["window"] = "whole sampler lifetime (warm-up included)"
         if rows:
             sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
             if sm:
@@ -219,6 +243,7 @@ def run_b200(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+            sampler.wait_ready()
             time.sleep(0.3)
             for i in range(W):
                 device_step(i)
@@ -227,13 +252,13 @@ def run_b200(args):
         ms_dev, _ = timed(device_step, K)
         tw1 = time.time()
         launches = kbner_b200._lib.launch_count() - l0
-        clocks = sampler.stop(tw0, tw1) if rank == 0 else {}
         api_run(W)
         barrier()
         t0 = time.perf_counter()
         api_run(K, offset=W)
         torch.cuda.synchronize()
         wall_e2e = time.perf_counter() - t0
+        clocks = sampler.stop(tw0, tw1, time.time()) if rank == 0 else {}
         if dist is not None:
             t = torch.tensor([wall_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,6 +420,7 @@ def run_train(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
         time.sleep(0.3)
     for i in range(ACC):          # every rank: step() contains the gradient all-reduce
         step(i)
