@@ -3,22 +3,24 @@
 // flash-style: the [S,S] score matrix the reference's transformers-3.0.0 path materialises in
 // fp32 (call site /root/reference/flair/embeddings.py:3269) never leaves the SM.
 //
-// One CTA = one (window r, head h, block of 128 query rows); TWO CTAs are resident per SM (96 KB of shared
-// memory, 256 TMEM columns, <= 200 registers each) so the softmax of one overlaps the MMAs of the other --
-// the round-1 version (1 CTA/SM, 1 softmax warp per scheduler) was latency-bound at 162 us per layer.
-//   warp 8        TMA + MMA issuer (one lane): K/V stream through a 3-stage ring of 64-key blocks;
-//                 S_j = Q.K_j^T -> TMEM (2 buffers x 64 cols), O_j = P_j.V_j -> TMEM (2 buffers x 64 cols);
+// PERSISTENT CTAs, two resident per SM (97 KB of shared memory, 256 TMEM columns, 96 registers each), each walking the work
+// items (window r, head h, block of 128 query rows) blockIdx.x, blockIdx.x + gridDim.x, ...; every barrier, ring slot and
+// TMEM buffer is indexed by g, the running count of 64-key blocks the CTA has gone through, so the pipeline never drains
+// between items.  (One CTA per item spent 41 % of its life outside the key-block loop -- profiles/README.md, steps 17-19.)
+//   warp 9        TMA producer: K and V in separate 3-slot rings, the Q tile of the next item; per-item address arithmetic
+//   warp 8        MMA issuer (warp-uniform, elect.sync around the issue): S_g = Q.K_g^T -> TMEM (2 buffers x 64 cols) two
+//                 blocks ahead of the softmax, O += P_g.V_g -> TMEM (2 buffers x 64 cols, one per item in flight);
 //                 tcgen05.mma kind::f16, V consumed MN-major straight from its row-major [key][d] tile
 //   warps 0..7    softmax, two threads per query row (= TMEM lane; warps w and w+4 share a lane quarter and split the
-//                 64 key columns): tcgen05.ld the scores, online max / ex2 / sum in fp32 registers, P_j -> bf16 ->
-//                 shared memory in the SWIZZLE_128B K-major layout the MMA reads; running O in registers
-//                 (O = O*alpha + P_j.V_j): no TMEM read-modify-write pass.
-// Training (DROP): attention-probability dropout (transformers BertSelfAttention.dropout, p = 0.1) is applied to P_j
+//                 64 key columns): tcgen05.ld the scores, online max / ex2 / sum in fp32 registers, P_g -> bf16 ->
+//                 shared memory in the SWIZZLE_128B K-major layout the MMA reads; O stays in TMEM and is rescaled lazily
+//                 (only when a row maximum grows by more than 2^8); an item's read-out is deferred past the next item's
+//                 first key block.
+// Training (DROP): attention-probability dropout (transformers BertSelfAttention.dropout, p = 0.1) is applied to P_g
 // after the row sum has been taken, with the stateless counter-hash mask of common.cuh indexed by
 // (window, head, query, key); the 1/(1-p) scale is folded into the final normalisation.
-// Pipeline inside a CTA: S_{j+1} is issued before softmax(j) finishes; P / O are double-buffered and the
-// accumulation of O_{j-1} is deferred until P_j has been published.
-// Bound: MUFU (one ex2 per score: 16/clk/SM => 512 clk per 128x64 block), not the tensor pipe.
+// Bound: MUFU (one ex2 per score: 16/clk/SM => 512 clk per 128x64 block) + issue + the per-block latency chain; the
+// tensor pipe is ~21 % busy.
 #include <math_constants.h>
 
 #include "common.cuh"
