@@ -324,3 +324,30 @@ def test_attention(ops, R, S, heads, lens):
     assert diff.max().item() < 2e-2, diff.max().item()
     assert (diff.mean() / ref.abs().mean()).item() < 5e-3
     torch.testing.assert_close(lse, ref_lse, rtol=1e-3, atol=1e-3)
+
+
+def test_attention_persistent_many_items_ragged(ops):
+    """More work items (window, head, query block) than resident CTAs (2 x 148): every CTA of the persistent kernel walks
+    2-3 items back to back, with ragged windows -- single key, block boundaries +-1, full -- and one window WITHOUT a
+    valid key (its rows must come out as zeros, LSE = -inf), so item boundaries, the deferred read-out and the
+    empty-item path are all on the tested path."""
+    R, S, heads = 40, 512, 4                      # 40 * 4 * 4 = 640 items
+    lens = [512, 1, 64, 65, 127, 128, 129, 300, 0, 511] * 4
+    g = torch.Generator(device="cuda").manual_seed(7)
+    H = heads * 64
+    qkv = torch.randn(R * S, 3 * H, device="cuda", generator=g).bfloat16()
+    key_len = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    out, lse = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True)
+    ref, ref_lse = _attn_ref(qkv, key_len, R, S, heads)
+    empty = (key_len == 0)
+    rows_empty = empty[:, None].expand(R, S).reshape(-1)
+    assert bool((out[rows_empty] == 0).all())
+    assert bool(torch.isinf(lse[empty]).all()) and bool((lse[empty] < 0).all())
+    ok = ~rows_empty
+    diff = (out.float()[ok] - ref[ok]).abs()
+    assert diff.max().item() < 2e-2, diff.max().item()
+    assert (diff.mean() / ref[ok].abs().mean()).item() < 5e-3
+    torch.testing.assert_close(lse[~empty], ref_lse[~empty], rtol=1e-3, atol=1e-3)
+    # and the same call twice gives the same bits (no dependence on which CTA took which item)
+    out2, _ = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True)
+    assert torch.equal(out, out2)
