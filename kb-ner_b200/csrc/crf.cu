@@ -4,11 +4,11 @@
 // _forward_alg :1329-1394, _score_sentence :2544-2591, _calculate_loss :2448-2506,
 // _obtain_labels :1193-1210).
 //
-// Mapping: one group of G lanes per sentence (G = 16 when L <= 16, two sentences per warp;
-// else G = 32), lane j owns tag j.  The recurrence state lives in registers, the transition
-// row of the lane in registers, the all-to-all exchange of the previous state is G width-G
-// shuffles.  These kernels are bound by the dependent chain / issue rate, their HBM traffic
-// is the emissions read once ("CRF kernels").
+// Mapping: one warp per block, Q lanes per sentence (Q = 16 when L <= 16: two sentences per warp; else 32), lane j owns
+// tag j, its transition row in registers.  A step is ONE exchange: the lane publishes its state in a two-row shared-memory
+// tile, every lane gathers the K states with broadcast loads and reduces them itself; what a step reads from global
+// memory streams through a cp.async ring.  These kernels are bound by the per-step instruction count / the dependent
+// chain, not by HBM: their traffic is the emissions (and, for the gradient, the stored alpha) read once ("CRF").
 #include <math_constants.h>
 
 #include "crf_common.cuh"
