@@ -396,13 +396,21 @@ def run_train(args):
     opt.set_linear_schedule(1000)
     arenas = [g["arena"] for g in opt.groups]
 
+    from kbner_b200.distributed import OverlappedGradAllReduce
+    overlap = dist is not None and OverlappedGradAllReduce.enabled()
+
     def step(i):
         b = batches[i % len(batches)]
         b.features = {}
         loss = tagger.forward_loss(b) / ACC
-        loss.backward()
-        if (i + 1) % ACC == 0:
-            if dist is not None:
+        last = (i + 1) % ACC == 0
+        if last and overlap:          # all-reduce of finished layer chunks runs under the rest of this backward
+            with OverlappedGradAllReduce(emb.model, arenas):
+                loss.backward()
+        else:
+            loss.backward()
+        if last:
+            if dist is not None and not overlap:
                 for ar in arenas:
                     dist.all_reduce(ar.grad)
             opt.step(grad_scale=1.0 / world)
@@ -456,7 +464,7 @@ def run_train(args):
             "dtype": "bf16", "data": "synthetic (seeded random-init weights and sentences)",
             "config": {"workload": "XLM-R-large+CRF fine-tune seq_len=512 batch=8 grad-accum=4 (BASELINE configs[2]/[3])",
                        "micro_batch_per_gpu": MB, "grad_accum": ACC, "seq_len": S_LEN, "tags": N_TAGS,
-                       "parallelism": "dp%d (NCCL all-reduce of gradients only)" % world, "dropout": "hidden %.2f / attention %.2f as in transformers (stateless counter-hash masks, regenerated in the backward)" % (cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob),
+                       "parallelism": "dp%d (NCCL all-reduce of gradients only%s)" % (world, ", overlapped with the last backward" if overlap else ""), "dropout": "hidden %.2f / attention %.2f as in transformers (stateless counter-hash masks, regenerated in the backward)" % (cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob),
                        "l2": "working set (2.2 GB fp32 masters + 0.6 GB bf16 + activations) exceeds the 126 MB L2"},
             "e2e": {"value": round(n_sent / wall, 2), "unit": "sentences/s", "h2d_bytes_per_step": MB * S_LEN * 4 * 2,
                     "d2h_bytes_per_step": 4, "api": "FastSequenceTagger.forward_loss + loss.backward + FusedAdamW.step"},

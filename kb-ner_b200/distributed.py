@@ -83,3 +83,44 @@ def global_grad_norm(params: Iterable[torch.nn.Parameter]) -> torch.Tensor:
     """L2 norm over all gradients (identical on every rank after GradBucketReducer.reduce)."""
     sq = [p.grad.float().pow(2).sum() for p in params if p.grad is not None]
     return torch.sqrt(torch.stack(sq).sum()) if sq else torch.zeros(())
+
+
+class OverlappedGradAllReduce:
+    """All-reduce of the flat gradient arenas that overlaps the backward pass of the LAST accumulation micro-step.
+
+    `with OverlappedGradAllReduce(encoder, arenas) as sync: loss.backward()` makes the encoder run its backward in layer
+    chunks (encoder._backward_chunked) and starts the all-reduce of every finalised arena slice asynchronously while the
+    next chunk computes; on exit the remaining arenas (tag projection, transitions) are reduced and every handle is
+    waited for.  Sum only -- the caller divides by the world size (FusedAdamW.step(grad_scale=1/world)).  Without an
+    initialised process group (or world size 1) it changes nothing.  Enabled with KBNER_OVERLAP_ALLREDUCE=1."""
+
+    def __init__(self, encoder, arenas):
+        self.encoder, self.arenas, self.handles = encoder, list(arenas), []
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    @staticmethod
+    def enabled():
+        import os
+        return os.environ.get("KBNER_OVERLAP_ALLREDUCE", "0") == "1"
+
+    def _slice_done(self, lo, hi):
+        if hi > lo:
+            self.handles.append(dist.all_reduce(self.encoder.arena.grad[lo:hi], async_op=True))
+
+    def __enter__(self):
+        if self.active:
+            self.encoder._grad_sync = self._slice_done
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if not self.active:
+            return False
+        self.encoder._grad_sync = None
+        if exc_type is None:
+            for ar in self.arenas:
+                if ar is not self.encoder.arena:
+                    self.handles.append(dist.all_reduce(ar.grad, async_op=True))
+            for h in self.handles:
+                h.wait()
+        self.handles = []
+        return False

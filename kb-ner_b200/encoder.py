@@ -454,19 +454,24 @@ def _forward_train(self, ids, key_len):
 
 
 @torch.no_grad()
-def _backward_eager(self, saved, dout):
+def _backward_workspace(self, saved, dev):
+    c = self.config
+    R, S = saved["R"], saved["S"]
+    return (torch.empty((R, c.num_attention_heads, S), dtype=torch.float32, device=dev),
+            torch.empty((R * S, c.hidden_size), dtype=torch.float32, device=dev))
+
+
+def _backward_layers(self, saved, dout, dres, li_hi, li_lo, ws):
+    """Backward through layers li_hi .. li_lo (descending).  `dout` (fp32) + `dres` (bf16, or None) is the gradient w.r.t.
+    the output of layer li_hi: the dgrad GEMMs keep a plain fp32 epilogue and the gradient that arrives over the residual
+    connection is added by the LayerNorm backward pass.  Returns the pair for layer li_lo - 1."""
     c = self.config
     ar = self.arena
     R, S = saved["R"], saved["S"]
     M, H, F = R * S, c.hidden_size, c.intermediate_size
     heads = c.num_attention_heads
     key_len = saved["key_len"]
-    dev = dout.device
-    ws = (torch.empty((R, heads, S), dtype=torch.float32, device=dev), torch.empty((M, H), dtype=torch.float32, device=dev))
-    # `dout` (fp32) + `dres` (bf16, or None) is the gradient w.r.t. the current layer's output: the dgrad GEMMs keep a plain
-    # fp32 epilogue and the gradient that arrives over the residual connection is added by the LayerNorm backward pass
-    dres = None
-    for li in range(len(self.encoder.layer) - 1, -1, -1):
+    for li in range(li_hi, li_lo - 1, -1):
         lyr, w = self.encoder.layer[li], self._compute[li]
         a = lyr.attention
         d_attn, d_h1, d_h2 = _dropout_sites(self, li) if saved.get("dropout") else (None, None, None)
@@ -495,6 +500,11 @@ def _backward_eager(self, saved, dout):
             dres = dz1
         else:      # the embedding backward takes one fp32 tensor: let this last dgrad add the residual gradient itself
             dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_BIAS_RESID_F32, aux=dz1, b_mn=True)
+    return dout, dres
+
+
+def _backward_embed(self, saved, dout):
+    c = self.config
     if saved.get("dropout") and c.hidden_dropout_prob > 0:
         ops.dropout_apply(dout, (self._drop_seed, 4 * len(self._compute), c.hidden_dropout_prob))
     e = self.embeddings
@@ -504,11 +514,81 @@ def _backward_eager(self, saved, dout):
                      e.token_type_embeddings.weight.grad[0], e.LayerNorm.weight.grad, e.LayerNorm.bias.grad)
 
 
+
+
+def _backward_eager(self, saved, dout):
+    ws = _backward_workspace(self, saved, dout.device)
+    dout, _ = _backward_layers(self, saved, dout, None, len(self.encoder.layer) - 1, 0, ws)
+    _backward_embed(self, saved, dout)
+
+
+def _chunk_plan(self, n_chunks=4):
+    """Layer chunks of the backward pass (descending) with the arena slice each one finalises: the arena is laid out
+    layer 0 .. layer L-1, embeddings (_arena_order), so a chunk of consecutive layers owns one contiguous slice."""
+    L = len(self.encoder.layer)
+    n = max(1, min(n_chunks, L))
+    bounds = [(L * k) // n for k in range(n + 1)]
+    ar = self.arena
+
+    def start(li):
+        if li >= L:
+            return ar.offsets[id(self.embeddings.word_embeddings.weight)]
+        return ar.offsets[id(self.encoder.layer[li].attention.self.query.weight)]
+    plan = [(bounds[k + 1] - 1, bounds[k], start(bounds[k]), start(bounds[k + 1])) for k in reversed(range(n))]
+    return plan, (start(L), ar.numel)
+
+
+@torch.no_grad()
+def _backward_chunked(self, saved, dout, sync):
+    """The backward pass in layer chunks; after each chunk `sync(lo, hi)` is called with the slice of the gradient arena
+    that chunk has finalised, so the caller can start its all-reduce (async, NCCL's own stream) while the next chunk
+    runs.  Used on the last gradient-accumulation micro-step of a multi-GPU run; chunks are captured / replayed as CUDA
+    graphs like the one-piece backward (own pool; the tensors carried from chunk to chunk stay referenced)."""
+    plan, emb_slice = _chunk_plan(self)
+    st = saved.get("graph_state")
+    if st is None:
+        ws = _backward_workspace(self, saved, dout.device)
+        dres = None
+        for k, (hi, lo, a, b) in enumerate(plan):
+            dout, dres = _backward_layers(self, saved, dout, dres, hi, lo, ws)
+            if k == len(plan) - 1:
+                _backward_embed(self, saved, dout)
+            sync(a, b)
+        sync(*emb_slice)
+        return
+    from . import _lib
+    if st.get("bwd_chunks") is None:
+        st["dout_c"] = dout.clone()
+        st["bwd_ws"] = _backward_workspace(self, saved, dout.device)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        chunks, cur, dres = [], st["dout_c"], None
+        for k, (hi, lo, a, b) in enumerate(plan):
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(g, pool=pool):
+                cur, dres = _backward_layers(self, saved, cur, dres, hi, lo, st["bwd_ws"])
+                if k == len(plan) - 1:
+                    _backward_embed(self, saved, cur)
+            chunks.append((g, _lib.launch_count() - l0, cur, dres))
+        st["bwd_chunks"] = chunks
+    else:
+        st["dout_c"].copy_(dout, non_blocking=True)
+    for (g, n, _, _), (hi, lo, a, b) in zip(st["bwd_chunks"], plan):
+        g.replay()
+        _lib_note_launches(n)
+        sync(a, b)
+    sync(*emb_slice)
+
+
 @torch.no_grad()
 def _backward(self, saved, dout):
     """dout: gradient w.r.t. the last hidden state, fp32 [R*S, H].  Accumulates into the gradient arena.
     When `saved` came from a replayed forward graph, the backward launches are captured / replayed as a graph too
     (same pool; the activations, the arena and dout's static copy keep their addresses)."""
+    sync = getattr(self, "_grad_sync", None)
+    if sync is not None:
+        return _backward_chunked(self, saved, dout, sync)
     st = saved.get("graph_state")
     if st is None:
         return _backward_eager(self, saved, dout)

@@ -32,7 +32,7 @@ from typing import List, Optional
 import torch
 
 from .data import BatchedData
-from .distributed import allreduce_counts, shard_indices
+from .distributed import OverlappedGradAllReduce, allreduce_counts, shard_indices
 from .optim import build_reference_optimizer
 from .training_utils import Metric
 
@@ -106,10 +106,16 @@ class ModelFinetuner:
                 tail = len(mine) - (len(mine) // gradient_accumulation_steps) * gradient_accumulation_steps
                 denom = tail if (tail and bi >= len(mine) - tail) else gradient_accumulation_steps
                 loss = model.forward_loss(batch) / denom
-                loss.backward()
+                boundary = (bi + 1) % gradient_accumulation_steps == 0 or bi == len(mine) - 1
+                overlap = boundary and world > 1 and OverlappedGradAllReduce.enabled()
+                if overlap:       # the all-reduce of finished layer chunks runs under the rest of this backward
+                    with OverlappedGradAllReduce(emb.model, arenas):
+                        loss.backward()
+                else:
+                    loss.backward()
                 seen += len(batch)
-                if (bi + 1) % gradient_accumulation_steps == 0 or bi == len(mine) - 1:
-                    if world > 1:
+                if boundary:
+                    if world > 1 and not overlap:
                         for ar in arenas:
                             torch.distributed.all_reduce(ar.grad)
                     opt.step(grad_scale=1.0 / world)

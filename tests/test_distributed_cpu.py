@@ -34,7 +34,34 @@ def _worker(rank, world, port, q):
     ref.load_state_dict(model.state_dict())
     ((ref(x) - y) ** 2).mean().backward()
     err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
-    q.put((rank, allidx, counts, err, norm))
+    # overlapped all-reduce of the gradient arenas: a stand-in encoder whose chunked "backward" reports the arena slices
+    # the real one finalises (encoder._chunk_plan); every rank must end with the SUM over ranks in every arena, the hook
+    # must be gone afterwards, and the plan must tile the arena exactly
+    from kbner_b200.distributed import OverlappedGradAllReduce
+    from kbner_b200.encoder import EncoderConfig, XLMRobertaEncoderB200, _chunk_plan
+    cfg = EncoderConfig(name="t", vocab_size=50, hidden_size=256, num_hidden_layers=5, num_attention_heads=4,
+                        intermediate_size=256, max_position_embeddings=32)
+    enc = XLMRobertaEncoderB200(cfg)
+    ar = enc.ensure_arena()
+    plan, emb_slice = _chunk_plan(enc)
+    tiles = sorted([(a, b) for _, _, a, b in plan] + [emb_slice])
+    tiled = tiles[0][0] == 0 and tiles[-1][1] == ar.numel and all(tiles[i][1] == tiles[i + 1][0] for i in range(len(tiles) - 1))
+    descending = all(plan[i][1] == plan[i + 1][0] + 1 for i in range(len(plan) - 1)) and plan[-1][1] == 0
+
+    class Head:
+        def __init__(self):
+            self.grad = torch.full((7,), float(rank + 1))
+    head = Head()
+    ar.grad.fill_(float(rank + 1))
+    with OverlappedGradAllReduce(enc, [ar, head]) as red:
+        hook_set = enc._grad_sync is not None
+        for _, _, a, b in plan:                   # what encoder._backward_chunked does after each chunk
+            enc._grad_sync(a, b)
+        enc._grad_sync(*emb_slice)
+    total = float(sum(range(1, world + 1)))
+    overlap_ok = (tiled and descending and hook_set and enc._grad_sync is None and bool((ar.grad == total).all())
+                  and bool((head.grad == total).all()))
+    q.put((rank, allidx, counts, err, norm, overlap_ok))
     dist.destroy_process_group()
 
 
@@ -50,11 +77,12 @@ def test_two_rank_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     res.sort()
-    for rank, allidx, counts, err, norm in res:
+    for rank, allidx, counts, err, norm, overlap_ok in res:
         assert sorted(set(sum(allidx, []))) == list(range(11))          # every sentence covered
         assert len(allidx[0]) == len(allidx[1]) == 6                    # same number of steps on every rank
         assert counts[1] == 3 and counts[2] == 14
         assert err < 1e-6                                               # mean of rank grads == global-batch grad
+        assert overlap_ok                                               # chunked all-reduce: arena tiled, sums right, hook removed
     assert abs(res[0][4] - res[1][4]) < 1e-7                            # identical clip norm on both ranks
 
 
