@@ -86,3 +86,64 @@ def test_span_counts_remove_x():
     span_counts(m, s.get_spans("ner"), s.get_spans("predicted"), None, remove_x=False)
     # without the filter the context prediction is a false positive and the X spans are unmatched gold spans
     assert m.get_tp() == 1 and m.get_fp() == 2 and m.get_fn("X") == 4
+
+
+def test_linear_schedule_matches_transformers():
+    """finetune_trainer.py:679-688 builds transformers' get_linear_schedule_with_warmup(optimizer, 0, t_total) and steps it
+    after every optimizer step; FusedAdamW.scheduler_step must produce the same learning-rate sequence for both groups."""
+    import pytest
+    import torch
+    from transformers import get_linear_schedule_with_warmup
+    from kbner_b200.encoder import ParamArena
+    from kbner_b200.optim import FusedAdamW
+    t_total, base, rate = 7, 5e-6, 10000.0
+    p = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    ref_opt = torch.optim.SGD([{"params": [p[0]], "lr": base * rate}, {"params": [p[1]], "lr": base}], lr=base)
+    sched = get_linear_schedule_with_warmup(ref_opt, num_warmup_steps=0, num_training_steps=t_total)
+    q = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    opt = FusedAdamW([{"arena": ParamArena([q[0]]), "lr": base * rate}, {"arena": ParamArena([q[1]]), "lr": base}])
+    opt.set_linear_schedule(t_total)
+    for _ in range(t_total + 2):                  # two steps past the end: the factor clamps at zero
+        want = [g["lr"] for g in ref_opt.param_groups]
+        got = [g["lr"] for g in opt.groups]
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-18)
+        ref_opt.step()
+        sched.step()
+        opt.steps += 1                            # what FusedAdamW.step() does before its kernels (CUDA only)
+        opt.scheduler_step()
+
+
+def test_parameter_groups_follow_the_reference_name_rule():
+    """finetune_trainer.py:552-553 groups parameters by NAME: 'embedding' in the name, or linear.weight / linear.bias ->
+    learning_rate; everything else (the CRF transitions) -> learning_rate * lr_rate.  Applied to OUR tagger's
+    named_parameters() that rule must give exactly the arenas build_reference_optimizer creates, with every parameter in
+    exactly one of them."""
+    import torch
+    from kbner_b200.data import Dictionary
+    from kbner_b200.embeddings import StackedEmbeddings, SyntheticTokenizer, TransformerWordEmbeddings
+    from kbner_b200.encoder import EncoderConfig
+    from kbner_b200.optim import build_reference_optimizer
+    from kbner_b200.sequence_tagger import FastSequenceTagger
+    cfg = EncoderConfig(name="t", vocab_size=64, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                        intermediate_size=256, max_position_embeddings=40)
+    emb = TransformerWordEmbeddings(model="t", layers="-1", pooling_operation="first", fine_tune=True,
+                                    tokenizer=SyntheticTokenizer(64), config=cfg, device="cpu")
+    d = Dictionary.make_tag_dictionary(["B-A", "I-A", "E-A", "S-A"], with_x=True)
+    tagger = FastSequenceTagger(hidden_size=256, embeddings=StackedEmbeddings([emb]), tag_dictionary=d, tag_type="ner",
+                                use_crf=True, use_rnn=False, word_dropout=0.0, locked_dropout=0.0)
+    named = list(tagger.named_parameters())
+    finetune = {n for n, _ in named if "embedding" in n or n == "linear.weight" or n == "linear.bias"}      # :552
+    other = {n for n, _ in named if "embedding" not in n and n != "linear.weight" and n != "linear.bias"}   # :553
+    assert other == {"transitions"} and finetune | other == {n for n, _ in named}
+    lr, rate = 5e-6, 10000.0
+    opt = build_reference_optimizer(tagger, lr=lr, lr_rate=rate)
+    by_ptr = {}
+    for g in opt.groups:
+        ar = g["arena"]
+        lo, hi = ar.flat.data_ptr(), ar.flat.data_ptr() + ar.flat.numel() * 4
+        by_ptr[(lo, hi)] = g["lr"]
+    for n, p in tagger.named_parameters():                   # after the arenas took the parameters over
+        owners = [v for (lo, hi), v in by_ptr.items() if lo <= p.data_ptr() < hi]
+        assert len(owners) == 1, n
+        assert owners[0] == (lr * rate if n in other else lr), n
+        assert p.grad is not None and p.grad.shape == p.shape        # .grad is a view into the arena's gradient buffer
