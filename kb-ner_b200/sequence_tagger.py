@@ -358,12 +358,25 @@ class SequenceTagger(torch.nn.Module):
 
     # ---- checkpoint (:435-477, :1824-1897; flair/nn.py:60-108) ----------------------------------------------
     def _get_state_dict(self):
-        return {"state_dict": self.state_dict(), "embeddings": self.embeddings, "hidden_size": self.hidden_size,
-                "tag_dictionary": self.tag_dictionary, "tag_type": self.tag_type, "use_crf": self.use_crf,
-                "use_rnn": self.use_rnn, "use_cnn": self.use_cnn, "rnn_layers": self.rnn_layers,
-                "use_word_dropout": self.use_word_dropout, "use_locked_dropout": self.use_locked_dropout,
-                "remove_x": self.remove_x, "sentence_level_loss": self.sentence_level_loss,
-                "target_languages": self.target_languages, "config": self.config}
+        """The reference's checkpoint dictionary, key for key (sequence_tagger_model.py:435-477; pinned by
+        tests/golden/state_dict_golden.json).  Every option outside the hot path is written with its OFF value on purpose:
+        the reference's loader falls back to defaults that are not all off when a key is missing
+        (`relearn_embeddings = True if "relearn_embeddings" not in state`, :1881), which would rebuild a different head."""
+        off = {k: False for k in (
+            "train_initial_hidden_state", "use_mfvi", "use_language_attention", "use_language_vector", "enhanced_crf",
+            "use_language_id", "use_transition_attention", "biaf_attention", "token_level_attention",
+            "relearn_embeddings", "map_embeddings", "embedding_selector", "new_drop", "use_rl", "use_embedding_masks",
+            "embedding_attention", "use_gumbel", "multi_view_training", "calculate_l2_loss", "l2_loss_only")}
+        state = {"state_dict": self.state_dict(), "embeddings": self.embeddings, "hidden_size": self.hidden_size,
+                 "tag_dictionary": self.tag_dictionary, "tag_type": self.tag_type, "use_crf": self.use_crf,
+                 "use_rnn": self.use_rnn, "use_cnn": self.use_cnn, "rnn_layers": self.rnn_layers,
+                 "use_word_dropout": self.use_word_dropout, "use_locked_dropout": self.use_locked_dropout,
+                 "remove_x": self.remove_x, "sentence_level_loss": self.sentence_level_loss,
+                 "target_languages": self.target_languages, "config": self.config,
+                 "teacher_hidden": 256, "num_teachers": 4, "relearn_size": -1,
+                 "word_map": self.word_map, "char_map": self.char_map}
+        state.update(off)
+        return state
 
     @classmethod
     def _init_model_with_state_dict(cls, state, testing=False):

@@ -97,3 +97,38 @@ def test_cli_flag_set_matches_the_reference():
     assert (ns.batch_size, ns.keep_embedding, ns.num_columns, ns.output_dir, ns.spliter) == (-1, -1, 2, "outputs", "\t")
     with pytest.raises(NotImplementedError, match="--zeroshot"):
         main(["--config", "c.yaml", "--zeroshot"])
+
+
+def test_checkpoint_dictionary_matches_the_reference_key_for_key():
+    """tests/golden/state_dict_golden.json is what the REFERENCE's FastSequenceTagger._get_state_dict() writes for the
+    KB-NER head (oracle/make_golden_statedict.py).  Ours must carry every key with the same value, so the reference's
+    loader (sequence_tagger_model.py:1824-1897) rebuilds the same head from a checkpoint written here."""
+    import json
+    import os
+    from kbner_b200.data import Dictionary
+    from kbner_b200.embeddings import StackedEmbeddings, SyntheticTokenizer, TransformerWordEmbeddings
+    from kbner_b200.encoder import EncoderConfig
+    from kbner_b200.sequence_tagger import FastSequenceTagger
+    with open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_golden.json")) as f:
+        ref = json.load(f)
+    cfg = EncoderConfig(name="t", vocab_size=64, hidden_size=256, num_hidden_layers=1, num_attention_heads=4,
+                        intermediate_size=256, max_position_embeddings=40)
+    emb = TransformerWordEmbeddings(model="t", layers="-1", pooling_operation="first", fine_tune=True,
+                                    tokenizer=SyntheticTokenizer(64), config=cfg, device="cpu")
+    d = Dictionary.make_tag_dictionary(["%s-T%d" % ("BIES"[i % 4], i // 4) for i in range(8)], with_x=True)
+    assert len(d) == 13
+    tagger = FastSequenceTagger(hidden_size=256, embeddings=StackedEmbeddings([emb]), tag_dictionary=d, tag_type="ner",
+                                use_crf=True, use_rnn=False, remove_x=True, word_dropout=0.1, sentence_loss=True,
+                                testing=True)
+    mine = tagger._get_state_dict()
+    assert set(ref) <= set(mine), sorted(set(ref) - set(mine))
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            continue                               # state_dict / embeddings / tag_dictionary: objects, checked below
+        assert mine[k] == v, (k, mine[k], v)
+    head = {n: list(t.shape) for n, t in mine["state_dict"].items() if not n.startswith("embeddings.")}
+    want = {n: ([s[0], 256] if n == "linear.weight" else s) for n, s in ref["state_dict"].items()}   # golden used D = 16
+    assert head == want
+    # and the loader reads its own checkpoint back to the same head
+    again = FastSequenceTagger._init_model_with_state_dict(mine, testing=True)
+    assert again.remove_x and again.use_word_dropout == 0.1 and again.tagset_size == 13
