@@ -199,7 +199,8 @@ int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t
 
 /* LayerNorm backward: x = saved fp32 pre-LN sum, dout = grad w.r.t. the LN output (fp32);
  * dx (bf16) = grad w.r.t. the pre-LN sum; dgamma / dbeta are ACCUMULATED into; dxsum (optional, [H]) accumulates the
- * column sums of dx = the bias gradient of the Linear whose output fed this LayerNorm (saves a pass over dx). */
+ * column sums of dx = the bias gradient of the Linear whose output fed this LayerNorm (saves a pass over dx).
+ * H must be a multiple of 256 (H / 256 warps share a row); KBNER_EUNSUPPORTED otherwise. */
 int kbner_layernorm_bwd(const float *x /*[M,H]*/, const float *dout /*[M,H]*/, const float *gamma,
                         const float *mean /*[M]*/, const float *rstd /*[M]*/, int M, int H,
                         uint16_t *dx /*[M,H] bf16*/, float *dgamma /*[H]*/, float *dbeta /*[H]*/,
@@ -231,7 +232,7 @@ int kbner_embed_ln_bwd(const int32_t *ids, const float *word_emb, const float *p
                        float *d_type /*[H]*/, float *dgamma, float *dbeta, void *stream);
 
 /* Backward of kbner_gather_tagproj_fwd: d_hidden (fp32 [R*S,H], pre-zeroed by the caller; touched rows are
- * written), dW / db ACCUMULATED into. */
+ * written), dW / db ACCUMULATED into.  L <= 32, H a multiple of 256 with L*H*4 <= 200 KB (W is staged in shared memory). */
 int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
                              const uint8_t *drop_keep, const float *W, const float *dlogits /*[B,T,L]*/,
                              int B, int T, int S, int H, int L,
