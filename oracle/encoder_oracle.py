@@ -92,6 +92,41 @@ def encoder_forward(params, ids, key_len, cfg, all_layers=False, masks=None):
     return states if all_layers else x
 
 
+def encoder_forward_bf16_points(params, ids, key_len, cfg):
+    """The same arithmetic with the ROUNDING POINTS of the B200 inference path restated in torch: every GEMM operand is
+    bf16 (weights and activations), accumulation and everything between a GEMM and the next store is fp32, and a value is
+    rounded to bf16 exactly where the kernels store bf16 -- embedding LayerNorm output, fused QKV output, the unnormalised
+    probabilities exp(s - rowmax) that feed P.V, the attention output, GELU(FFN-up) and both LayerNorm outputs.  Not a
+    second oracle: it exists to separate the cost of the number FORMAT from kernel error (DESIGN.md section 5 reports
+    |this - fp32 oracle| next to |kernels - fp32 oracle|).  Returns the last hidden state [R,S,H] (bf16 values in fp32)."""
+    r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    H, heads, NL, eps = cfg["hidden"], cfg["heads"], cfg["layers"], cfg.get("eps", 1e-5)
+    pad = cfg.get("pad_id", 1)
+    R, S = ids.shape
+    d = H // heads
+    x = (params["embeddings.word_embeddings.weight"][ids]
+         + params["embeddings.token_type_embeddings.weight"][0][None, None, :]
+         + params["embeddings.position_embeddings.weight"][position_ids(ids, pad)])
+    x = r(F.layer_norm(x, (H,), params["embeddings.LayerNorm.weight"], params["embeddings.LayerNorm.bias"], eps))
+    kmask = torch.arange(S, device=ids.device)[None, :] < key_len[:, None].to(ids.device)
+    for i in range(NL):
+        pre = "encoder.layer.%d." % i
+        lin = lambda t, nm: F.linear(t, r(params[pre + nm + ".weight"]), params[pre + nm + ".bias"])
+        q = r(lin(x, "attention.self.query")).view(R, S, heads, d).transpose(1, 2)
+        k = r(lin(x, "attention.self.key")).view(R, S, heads, d).transpose(1, 2)
+        v = r(lin(x, "attention.self.value")).view(R, S, heads, d).transpose(1, 2)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+        sc = sc.masked_fill(~kmask[:, None, None, :], float("-inf"))
+        p = torch.exp(sc - sc.amax(-1, keepdim=True))                     # fp32, row sum taken before the rounding
+        ctx = r((r(p) @ v) / p.sum(-1, keepdim=True)).transpose(1, 2).reshape(R, S, H)
+        x = r(F.layer_norm(lin(ctx, "attention.output.dense") + x, (H,), params[pre + "attention.output.LayerNorm.weight"],
+                           params[pre + "attention.output.LayerNorm.bias"], eps))
+        h = r(F.gelu(lin(x, "intermediate.dense")))
+        x = r(F.layer_norm(lin(h, "output.dense") + x, (H,), params[pre + "output.LayerNorm.weight"],
+                           params[pre + "output.LayerNorm.bias"], eps))
+    return x
+
+
 def first_subtoken_pool(hidden, row_of, first_idx):
     """flair/embeddings.py:3300-3345 ('first' pooling): word t of sentence b = hidden[row_of[b], first_idx[b,t]];
     first_idx < 0 (word with 0 sub-tokens / padding) -> zero vector (:3306-3308)."""
