@@ -382,6 +382,7 @@ def run_train(args):
     cfg = emb.model.config
     MB, ACC = 8, 4
     K, W = args.steps, args.warmup
+    K = (K + ACC - 1) // ACC * ACC            # whole accumulation cycles: every optimizer step of the region is counted
     rnd = random.Random(17 + rank)
     names = tagger.tag_dictionary.get_items()
     legal = [n for n in names if n not in ("<unk>", "S-X", "<START>", "<STOP>")]
@@ -596,7 +597,8 @@ def _gemm_traffic():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50,
+                    help="timed steps (default 50: ~0.6 s of device time; the end-to-end arm pays one batch of pipeline fill per run)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--base", action="store_true", help="xlm-roberta-base shapes (debug)")
