@@ -96,7 +96,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const int32_t *__restrict__ key_len, int R, int S, int H, int heads, uint16_t *__restrict__ out,
-                     float *__restrict__ lse_out, const Dropout drop) {
+                     int ldo, int split, float *__restrict__ lse_out, const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     AttnSmem &s = *reinterpret_cast<AttnSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,8 +297,35 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float pend_m = 0.0f, pend_l = 0.0f;
         int pend_qrow = 0, pend_row0 = 0, pend_h = 0, pend_r = 0;
         uint32_t pend_o = 0, pend_g = 0;
-        auto read_out = [&](bool from_tmem, uint32_t o_addr, uint32_t g_last, float m_run, float l_run, int qrow, int row0,
-                            int h, int r) {
+        // The output tile leaves through shared memory: a thread owns one query ROW (TMEM lane), so storing its 64 bytes
+        // directly made every 16-byte store instruction touch 32 rows = 32 half-written sectors per request (round-1 ncu:
+        // 2 097 152 sectors / 65 536 requests).  Instead the two warps of a quarter write their halves of the 32 rows into
+        // the P buffer of the item's LAST key block -- free once bar_o has confirmed that P.V retired, in the same
+        // SWIZZLE_128B pattern P uses (conflict-free) -- and read it back transposed: 8 lanes per row, 4 rows per store
+        // instruction = 16 fully written sectors per request.  Only this quarter's rows of the buffer are touched and
+        // the next P write to it sits behind the row-max pair barrier of the next key block.
+        auto stage_store = [&](uint8_t *stage, const uint32_t (&pk)[16], uint16_t *gbase, int qrow0, bool again, int again_off) {
+            uint8_t *srow = stage + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4 *>(srow + (((half * 4 + c) ^ (row & 7)) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rq = quarter * 32 + half * 16 + i * 4 + (lane >> 3);      // row inside the 128-query block
+                const int chunk = lane & 7;
+                const uint4 v = *reinterpret_cast<const uint4 *>(stage + rq * 128 + ((chunk ^ (rq & 7)) << 4));
+                if (qrow0 + rq < S) {
+                    uint16_t *gp = gbase + (size_t)rq * ldo + chunk * 8;
+                    *reinterpret_cast<uint4 *>(gp) = v;
+                    if (again) *reinterpret_cast<uint4 *>(gp + again_off) = v;
+                }
+            }
+        };
+        auto read_out = [&](bool from_tmem, uint32_t o_addr, uint32_t g_last, uint8_t *stage, float m_run, float l_run, int qrow,
+                            int row0, int h, int r) {
+            const int qrow0 = qrow - row;                       // first query row of the item's 128-row block
             float o_acc[32];
             if (from_tmem) {
                 ptx::mbar_wait(&s.bar_o[g_last & 1], (g_last >> 1) & 1);
@@ -319,23 +346,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
             const float l_tot = l_run + s.xsum[n_epi & 1][half ^ 1][row];
             ++n_epi;
-            // normalise, bf16, 64 contiguous bytes per thread
-            if (qrow < S) {
-                const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
-                uint16_t *orow = out + (size_t)(row0 + qrow) * H + h * kAttnD + half * 32;
+            const float inv = (l_tot > 0.0f) ? (DROP ? drop.scale : 1.0f) / l_tot : 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 o;
-                    o.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-                    o.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-                    o.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-                    o.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-                    *reinterpret_cast<uint4 *>(orow + i) = o;
+            for (int i = 0; i < 32; ++i) o_acc[i] *= inv;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(o_acc[2 * i], o_acc[2 * i + 1]);
+            uint16_t *gbase = out + (size_t)(row0 + qrow0) * ldo + h * kAttnD;
+            // split (the "bf16x3" precise mode): out row = [ hi | lo | hi ], each H wide, hi + lo = the fp32 value to 2^-17
+            stage_store(stage, pk, gbase, qrow0, split != 0, 2 * H);
+            if (split) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float h0, h1;
+                    unpack_bf16x2(pk[i], h0, h1);
+                    pk[i] = pack_bf16x2(o_acc[2 * i] - h0, o_acc[2 * i + 1] - h1);
                 }
-                if (lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
-                    lse_out[((size_t)r * heads + h) * S + qrow] =
-                        (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
+                asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");     // the partner has read the hi tile back
+                stage_store(stage, pk, gbase + H, qrow0, false, 0);
             }
+            if (qrow < S && lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
+                lse_out[((size_t)r * heads + h) * S + qrow] =
+                    (l_tot > 0.0f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -CUDART_INF_F;
         };
         int klen_next = (int)blockIdx.x < total ? __ldg(key_len + blockIdx.x / (nqb * heads)) : 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -439,7 +471,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::mbar_arrive(&s.bar_p[g & 1]);
                 ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 3);
                 if (j == 0 && pend) {            // the previous item's read-out, now that this item's first block is under way
-                    read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
                     pend = false;
                 }
             }
@@ -450,13 +482,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ++n_item;
             } else {                             // window without a valid key: zeros (flush the outstanding read-out first)
                 if (pend) {
-                    read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
                     pend = false;
                 }
-                read_out(false, 0u, 0u, m_run, l_run, qrow, row0, h, r);
+                read_out(false, 0u, 0u, s.p[g & 1], m_run, l_run, qrow, row0, h, r);   // every earlier P.V has retired
             }
         }
-        if (pend) read_out(true, pend_o, pend_g, pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+        if (pend) read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -470,10 +502,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 using namespace kbner;
 
-extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
-                                           uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
-                                           float drop_p, void *stream) {
+extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                      uint16_t *out, int ldo, int split, float *lse, const uint32_t *drop_seed,
+                                      uint32_t drop_site, float drop_p, void *stream) {
     KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
+    KBNER_CHECK_ARG(ldo >= heads * kAttnD * (split ? 3 : 1) && ldo % 8 == 0 && ((uintptr_t)out & 15u) == 0,
+                    "attention_fwd: output row stride %d (split=%d) / alignment", ldo, split);
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_fwd: dropout probability %f", (double)drop_p);
     KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * kMaxS * (kMaxS / 2) < (1ull << 32),
                     "attention_fwd: R*heads exceeds the 32-bit dropout counter");
@@ -507,10 +541,10 @@ extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *k
     cudaError_t le;
     if (drop.thresh)
         le = launch_kernel(attention_fwd_kernel<true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, R, S, H, heads, out, lse, drop);
+                           key_len, R, S, H, heads, out, ldo, split, lse, drop);
     else
         le = launch_kernel(attention_fwd_kernel<false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, R, S, H, heads, out, lse, drop);
+                           key_len, R, S, H, heads, out, ldo, split, lse, drop);
     if (le != cudaSuccess) {
         set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
         return KBNER_ECUDA;
@@ -525,7 +559,13 @@ extern "C" int kbner_attention_debug_read(unsigned long long *host, int n) {
 }
 #endif
 
+extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
+                                           uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
+                                           float drop_p, void *stream) {
+    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, 0, lse, drop_seed, drop_site, drop_p, stream);
+}
+
 extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                    uint16_t *out, float *lse, void *stream) {
-    return kbner_attention_fwd_dropout(qkv, key_len, R, S, heads, out, lse, nullptr, 0u, 0.0f, stream);
+    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, 0, lse, nullptr, 0u, 0.0f, stream);
 }

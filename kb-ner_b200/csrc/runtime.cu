@@ -109,7 +109,7 @@ int make_tmap_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t col
 
 }  // namespace kbner
 
-extern "C" int kbner_abi_version(void) { return 1; }
+extern "C" int kbner_abi_version(void) { return 2; }
 extern "C" const char *kbner_last_error(void) { return kbner::g_err; }
 extern "C" uint64_t kbner_launch_count(void) { return kbner::g_launches.load(); }
 extern "C" void kbner_add_launches(uint64_t n) { kbner::count_launch((int)n); }

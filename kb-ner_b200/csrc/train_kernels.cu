@@ -462,6 +462,75 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
     }
 }
 
+// The arena form: 16-byte accesses (28 B / parameter of HBM traffic is the whole cost of the step), the gradient either
+// fp32 (single GPU) or the bf16 buffer the NCCL all-reduce left behind (GBF16), and -- for the first n_shadow4 groups,
+// the encoder layers -- the updated parameter written a second time as bf16 into the shadow arena the tensor-core GEMMs
+// read: the 96 copy kernels that refreshed the bf16 weights after every step (a 1.8 GB pass) are gone.
+template <bool GBF16>
+__global__ void __launch_bounds__(256)
+adamw_vec_kernel(float4 *__restrict__ p, const void *__restrict__ g, float4 *__restrict__ m, float4 *__restrict__ v, size_t n4,
+                 float lr, float b1, float b2, float eps, float wd, float step_size, const float *__restrict__ gscale_ptr,
+                 float gscale_host, uint2 *__restrict__ shadow, size_t n_shadow4) {
+    const float gs = gscale_host * (gscale_ptr ? *gscale_ptr : 1.0f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float gi[4];
+        if (GBF16) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2 *>(g) + i);
+            unpack_bf16x2(u.x, gi[0], gi[1]);
+            unpack_bf16x2(u.y, gi[2], gi[3]);
+        } else {
+            const uint4 u = ld_nc_v4(reinterpret_cast<const float4 *>(g) + i);
+            gi[0] = __uint_as_float(u.x); gi[1] = __uint_as_float(u.y); gi[2] = __uint_as_float(u.z); gi[3] = __uint_as_float(u.w);
+        }
+        const float4 pm = p[i], mm = m[i], vm = v[i];
+        float pi[4] = {pm.x, pm.y, pm.z, pm.w}, mi[4] = {mm.x, mm.y, mm.z, mm.w}, vi[4] = {vm.x, vm.y, vm.z, vm.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = gi[k] * gs;
+            mi[k] = b1 * mi[k] + (1.0f - b1) * gk;
+            vi[k] = b2 * vi[k] + (1.0f - b2) * gk * gk;
+            pi[k] = pi[k] - step_size * mi[k] / (sqrtf(vi[k]) + eps);
+            if (wd != 0.0f) pi[k] -= lr * wd * pi[k];
+        }
+        m[i] = make_float4(mi[0], mi[1], mi[2], mi[3]);
+        v[i] = make_float4(vi[0], vi[1], vi[2], vi[3]);
+        p[i] = make_float4(pi[0], pi[1], pi[2], pi[3]);
+        if (i < n_shadow4) shadow[i] = make_uint2(pack_bf16x2(pi[0], pi[1]), pack_bf16x2(pi[2], pi[3]));
+    }
+}
+
+// fp32 -> bf16 (round to nearest even) of a flat buffer: the gradient arena packed for the NCCL all-reduce, and the first
+// fill of the bf16 shadow arena.  `scale` multiplies first (1.0 for plain conversion).
+__global__ void __launch_bounds__(256)
+pack_bf16_kernel(const float4 *__restrict__ src, uint2 *__restrict__ dst, size_t n4, float scale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 u = ld_nc_v4(src + i);
+        dst[i] = make_uint2(pack_bf16x2(__uint_as_float(u.x) * scale, __uint_as_float(u.y) * scale),
+                            pack_bf16x2(__uint_as_float(u.z) * scale, __uint_as_float(u.w) * scale));
+    }
+}
+
+__global__ void __launch_bounds__(256) sumsq_bf16_kernel(const uint2 *__restrict__ g, size_t n4, float *__restrict__ out) {
+    float acc = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint2 u = __ldg(g + i);
+        float a, b, c, d;
+        unpack_bf16x2(u.x, a, b);
+        unpack_bf16x2(u.y, c, d);
+        acc += (a * a + b * b) + (c * c + d * d);
+    }
+    acc = warp_sum(acc);
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = s[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+}
+
 // clip coefficient on the device: coef = min(1, max_norm / (sqrt(sumsq) * pre + 1e-6))  (torch clip_grad_norm_)
 __global__ void clip_coef_kernel(const float *__restrict__ sumsq, float pre, float max_norm, float *__restrict__ coef) {
     const float nrm = sqrtf(*sumsq) * pre;
@@ -644,18 +713,72 @@ extern "C" int kbner_clip_coef(const float *sumsq, float pre_scale, float max_no
     return KBNER_OK;
 }
 
-extern "C" int kbner_adamw_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
-                                float beta2, float eps, float weight_decay, int step, const float *gscale_dev,
-                                float gscale_host, void *stream) {
-    KBNER_CHECK_ARG(p && g && m && v && step >= 1, "adamw_step: bad arguments");
+extern "C" int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_bf16, float *m, float *v, size_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, int step,
+                                   const float *gscale_dev, float gscale_host, uint16_t *shadow, size_t n_shadow,
+                                   void *stream) {
+    KBNER_CHECK_ARG(p && (g != nullptr) != (g_bf16 != nullptr) && m && v && step >= 1,
+                    "adamw_step: bad arguments (exactly one of g / g_bf16)");
+    KBNER_CHECK_ARG(!shadow || (n_shadow <= n && n_shadow % 4 == 0), "adamw_step: shadow length %zu", n_shadow);
     if (n == 0) return KBNER_OK;
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-    size_t blocks = (n + 255) / 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15u) == 0 &&
+                         ((uintptr_t)g_bf16 & 7u) == 0 && ((uintptr_t)shadow & 7u) == 0;
+    const size_t n4 = aligned ? n / 4 : 0;
+    KBNER_CHECK_ARG(aligned || (!g_bf16 && !shadow), "adamw_step: bf16 gradient / shadow need 16-byte aligned arenas");
+    if (n4) {
+        size_t blocks = (n4 + 255) / 256;
+        if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+        const size_t ns4 = shadow ? n_shadow / 4 : 0;
+        if (g_bf16)
+            adamw_vec_kernel<true><<<(int)blocks, 256, 0, st>>>((float4 *)p, g_bf16, (float4 *)m, (float4 *)v, n4, lr, beta1, beta2, eps,
+                                                              weight_decay, step_size, gscale_dev, gscale_host, (uint2 *)shadow, ns4);
+        else
+            adamw_vec_kernel<false><<<(int)blocks, 256, 0, st>>>((float4 *)p, g, (float4 *)m, (float4 *)v, n4, lr, beta1, beta2, eps,
+                                                               weight_decay, step_size, gscale_dev, gscale_host, (uint2 *)shadow, ns4);
+        KBNER_CHECK_LAUNCH("adamw_step");
+    }
+    const size_t done = n4 * 4;
+    if (done < n) {
+        KBNER_CHECK_ARG(!g_bf16, "adamw_step: a bf16 gradient buffer must have a multiple of 4 elements");
+        size_t blocks = (n - done + 255) / 256;
+        if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+        adamw_kernel<<<(int)blocks, 256, 0, st>>>(p + done, g + done, m + done, v + done, n - done, lr, beta1, beta2, eps,
+                                                  weight_decay, step_size, gscale_dev, gscale_host);
+        KBNER_CHECK_LAUNCH("adamw_step");
+    }
+    return KBNER_OK;
+}
+
+extern "C" int kbner_adamw_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, const float *gscale_dev,
+                                float gscale_host, void *stream) {
+    return kbner_adamw_step_ex(p, g, nullptr, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale_dev, gscale_host,
+                               nullptr, 0, stream);
+}
+
+extern "C" int kbner_pack_bf16(const float *src, uint16_t *dst, size_t n, float scale, void *stream) {
+    KBNER_CHECK_ARG(src && dst, "pack_bf16: null pointer");
+    KBNER_CHECK_ARG(n % 4 == 0 && ((uintptr_t)src & 15u) == 0 && ((uintptr_t)dst & 7u) == 0,
+                    "pack_bf16: n must be a multiple of 4 and the buffers 16- / 8-byte aligned");
+    if (n == 0) return KBNER_OK;
+    size_t blocks = (n / 4 + 255) / 256;
     if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
-    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_size,
-                                                                gscale_dev, gscale_host);
-    KBNER_CHECK_LAUNCH("adamw_step");
+    pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)src, (uint2 *)dst, n / 4, scale);
+    KBNER_CHECK_LAUNCH("pack_bf16");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_sumsq_bf16(const uint16_t *g, size_t n, float *out, void *stream) {
+    KBNER_CHECK_ARG(g && out, "sumsq_bf16: null pointer");
+    KBNER_CHECK_ARG(n % 4 == 0 && ((uintptr_t)g & 7u) == 0, "sumsq_bf16: n must be a multiple of 4, buffer 8-byte aligned");
+    if (n == 0) return KBNER_OK;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 8 * (size_t)kNumSMs) blocks = 8 * kNumSMs;
+    sumsq_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint2 *)g, n / 4, out);
+    KBNER_CHECK_LAUNCH("sumsq_bf16");
     return KBNER_OK;
 }
 

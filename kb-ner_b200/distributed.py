@@ -35,92 +35,89 @@ def allreduce_counts(counts: Iterable[int], device=None) -> List[int]:
     return [int(x) for x in t.tolist()]
 
 
-class GradBucketReducer:
-    """Bucketed gradient all-reduce (sum, then / world) over flat fp32 buckets.
+class GradExchange:
+    """The one collective of the path: the per-optimizer-step gradient exchange of data-parallel fine-tuning.
 
-    Parameters are packed in registration order into buckets of ~bucket_mb; `reduce()` is called on the last
-    gradient-accumulation micro-step only (the reference steps every `gradient_accumulation_steps` micro-batches,
-    finetune_trainer.py:1007-1023).  With NCCL each bucket's all-reduce is launched asynchronously so it overlaps the
-    copy-in of the next bucket; `reduce()` returns after all buckets are written back."""
+    The reference steps every `gradient_accumulation_steps` micro-batches (finetune_trainer.py:1007-1023); here, on that
+    boundary, every rank's flat fp32 gradient arenas are summed over ranks (the caller's FusedAdamW.step(grad_scale =
+    1/world, grads=...) turns the sum into the mean and clips on the post-reduce norm).
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 64.0):
-        self.params = [p for p in params if p.requires_grad]
-        cap = int(bucket_mb * (1 << 20) / 4)
-        self.buckets, cur, size = [], [], 0
-        for p in self.params:
-            if cur and size + p.numel() > cap:
-                self.buckets.append(cur)
-                cur, size = [], 0
-            cur.append(p)
-            size += p.numel()
-        if cur:
-            self.buckets.append(cur)
+    payload  "bf16" (default): each arena is packed fp32 -> bf16 by one kernel into a static buffer, NCCL all-reduces the
+             bf16 buffer (half the 2.24 GB of XLM-R-large's fp32 gradient) and AdamW reads the gradient straight from
+             it -- the fp32 arena is never written back.  "fp32" (KBNER_GRAD_COMM=fp32) all-reduces the arenas in place.
+    overlap  (KBNER_OVERLAP_ALLREDUCE=1) the last backward of the accumulation cycle runs in layer chunks
+             (encoder._backward_chunked) and the pack + all-reduce of every finalised arena slice is started
+             asynchronously under the next chunk.
+    Without an initialised process group (or world size 1) nothing is exchanged and reduce() returns None.
+    `pack` is injectable so the host logic can be exercised with gloo on CPU (tests/test_distributed_cpu.py)."""
 
-    @torch.no_grad()
-    def reduce(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        world = dist.get_world_size()
-        work = []
-        for bucket in self.buckets:
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            flat = torch.cat([g.reshape(-1).float() for g in grads])
-            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-            work.append((h, flat, bucket))
-        for h, flat, bucket in work:
-            h.wait()
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-                p.grad.copy_(flat[off:off + n].view_as(p))
-                off += n
-
-
-def global_grad_norm(params: Iterable[torch.nn.Parameter]) -> torch.Tensor:
-    """L2 norm over all gradients (identical on every rank after GradBucketReducer.reduce)."""
-    sq = [p.grad.float().pow(2).sum() for p in params if p.grad is not None]
-    return torch.sqrt(torch.stack(sq).sum()) if sq else torch.zeros(())
-
-
-class OverlappedGradAllReduce:
-    """All-reduce of the flat gradient arenas that overlaps the backward pass of the LAST accumulation micro-step.
-
-    `with OverlappedGradAllReduce(encoder, arenas) as sync: loss.backward()` makes the encoder run its backward in layer
-    chunks (encoder._backward_chunked) and starts the all-reduce of every finalised arena slice asynchronously while the
-    next chunk computes; on exit the remaining arenas (tag projection, transitions) are reduced and every handle is
-    waited for.  Sum only -- the caller divides by the world size (FusedAdamW.step(grad_scale=1/world)).  Without an
-    initialised process group (or world size 1) it changes nothing.  Enabled with KBNER_OVERLAP_ALLREDUCE=1."""
-
-    def __init__(self, encoder, arenas):
-        self.encoder, self.arenas, self.handles = encoder, list(arenas), []
-        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-
-    @staticmethod
-    def enabled():
+    def __init__(self, encoder, arenas, payload=None, overlap=None, pack=None):
         import os
-        return os.environ.get("KBNER_OVERLAP_ALLREDUCE", "0") == "1"
+        self.encoder, self.arenas = encoder, list(arenas)
+        self.payload = payload or os.environ.get("KBNER_GRAD_COMM", "bf16")
+        if self.payload not in ("bf16", "fp32"):
+            raise ValueError("gradient payload must be 'bf16' or 'fp32'")
+        self.overlap = (os.environ.get("KBNER_OVERLAP_ALLREDUCE", "0") == "1") if overlap is None else bool(overlap)
+        if pack is None:
+            from . import ops
+            pack = ops.pack_bf16
+        self._pack = pack
+        self._bufs = {}
+        self._handles = []
+        self._encoder_done = False
+        self.bytes_per_step = 0
+
+    @property
+    def active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _buf(self, ar):
+        b = self._bufs.get(id(ar))
+        if b is None:
+            b = self._bufs[id(ar)] = torch.empty(ar.grad.numel(), dtype=torch.bfloat16, device=ar.grad.device)
+        return b
+
+    def _launch(self, ar, lo, hi):
+        if hi <= lo:
+            return
+        if self.payload == "bf16":
+            dst = self._buf(ar)[lo:hi]
+            self._pack(ar.grad[lo:hi], dst)
+        else:
+            dst = ar.grad[lo:hi]
+        self.bytes_per_step += dst.numel() * dst.element_size()
+        self._handles.append(dist.all_reduce(dst, op=dist.ReduceOp.SUM, async_op=True))
 
     def _slice_done(self, lo, hi):
-        if hi > lo:
-            self.handles.append(dist.all_reduce(self.encoder.arena.grad[lo:hi], async_op=True))
+        self._launch(self.encoder.arena, lo, hi)
 
-    def __enter__(self):
-        if self.active:
+    def backward(self, loss, boundary):
+        """loss.backward(); on an accumulation boundary with overlap on, the encoder reports finalised arena slices."""
+        if boundary and self.active and self.overlap and self.encoder is not None:
+            self.bytes_per_step = 0
             self.encoder._grad_sync = self._slice_done
-        return self
+            try:
+                loss.backward()
+            finally:
+                self.encoder._grad_sync = None
+            self._encoder_done = True
+        else:
+            loss.backward()
 
-    def __exit__(self, exc_type, exc, tb):
+    def reduce(self):
+        """Exchange whatever has not been started yet, wait for everything, return the per-arena buffers the optimizer
+        must read (bf16 payload: the packed buffers; fp32: the arenas' own .grad), or None when not distributed."""
         if not self.active:
-            return False
-        self.encoder._grad_sync = None
-        if exc_type is None:
-            for ar in self.arenas:
-                if ar is not self.encoder.arena:
-                    self.handles.append(dist.all_reduce(ar.grad, async_op=True))
-            for h in self.handles:
-                h.wait()
-        self.handles = []
-        return False
+            return None
+        if not self._encoder_done:
+            self.bytes_per_step = 0
+        for ar in self.arenas:
+            if self._encoder_done and self.encoder is not None and ar is getattr(self.encoder, "arena", None):
+                continue
+            self._launch(ar, 0, ar.grad.numel())
+        for h in self._handles:
+            h.wait()
+        self._handles, self._encoder_done = [], False
+        if self.payload == "bf16":
+            return [self._buf(ar) for ar in self.arenas]
+        return [ar.grad for ar in self.arenas]

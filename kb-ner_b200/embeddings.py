@@ -136,8 +136,13 @@ class TransformerWordEmbeddings(torch.nn.Module):
                     if tokenizer is None and os.path.exists(os.path.join(name, SyntheticTokenizer.FILE)):
                         tokenizer = SyntheticTokenizer.from_pretrained(name)
                 else:
-                    config = EncoderConfig.xlmr_base() if "base" in name else EncoderConfig.xlmr_large()
-                    config.name = name
+                    # the reference would download `name` from the hub here (AutoModel.from_pretrained, :2951-2953); there is
+                    # nothing to load it from, and a silently random-initialised encoder is exactly the "computing something
+                    # else" this package refuses: random init only happens when the caller passes an explicit `config`
+                    raise FileNotFoundError(
+                        "no local weights for %r: pass a directory written by save_pretrained() (config.json + "
+                        "model.safetensors / pytorch_model.bin, HF or kbner_b200), or config=EncoderConfig(...) for a "
+                        "randomly initialised encoder" % name)
             if not hasattr(self, "model"):
                 with torch.device(self.device_):
                     self.model = XLMRobertaEncoderB200(config)
@@ -363,8 +368,10 @@ class TransformerWordEmbeddings(torch.nn.Module):
             sentences = [sentences]
         if not hasattr(sentences, "features"):
             sentences = BatchedData(sentences)
-        if (not self.fine_tune) and self.name in sentences.features:
-            return sentences
+        # The reference short-circuits here when static embeddings are already stored on the batch (:3030-3037).  Its cache
+        # holds real tensors; an EncodedBatch aliases the encoder's workspace / graph output (valid until the next forward),
+        # so a cached one may describe ANOTHER batch by now: always re-encode (11 ms for 32 x 512 -- the reference's cache
+        # exists because its encoder costs seconds).
         sentences.features[self.name] = self.encode(sentences)
         return sentences
 

@@ -10,10 +10,22 @@ fp32 master parameters; bf16 compute copies of the Linear weights (Q|K|V fused i
 fp32 accumulation, fp32 pre-LayerNorm sums, fp32 LayerNorm / softmax statistics, bf16 activations.
 Only the requested final hidden state is produced (the reference's ``torch.stack`` of all 25 layer
 outputs, embeddings.py:3275, and the unused pooler are not computed -- SURVEY E7/E8).
+
+Inference precision (``encoder.precision`` / ``KBNER_PRECISION``), measured against the fp32 oracle on 24 layers:
+  ``"bf16"``        (default, fastest) bf16 operands and bf16 hidden state between kernels     ~9.7e-3 rel-L2
+  ``"bf16-res32"``  fp32 residual stream, bf16 operands (unfused LayerNorm)                    ~7.4e-3
+  ``"bf16x3"``      fp32 residual stream + every GEMM operand as a bf16 pair hi+lo, one K-concatenated tcgen05 GEMM
+                    per projection (3x the tensor work): the mode that meets BASELINE.json's 1e-3 on logits ~2e-4
 """
+import collections
+import os
+
 import torch
 
 from . import ops
+
+
+PRECISIONS = ("bf16", "bf16-res32", "bf16x3")
 
 
 def _lib_note_launches(n):
@@ -106,25 +118,38 @@ class XLMRobertaEncoderB200(torch.nn.Module):
             lyr.output.LayerNorm = _ln(H)
             self.encoder.layer.append(lyr)
         self._compute = None          # bf16 / fused compute copies, built by sync_compute_weights()
+        self._gen = 0                 # bumped whenever the compute copies are REPLACED (captured graphs die with them)
         self._ws = {}
-        self._graphs = {}
-        self._tgraphs = {}
-        import os
+        # captured CUDA graphs per (R, S) shape, least-recently-used first.  A training graph pins every saved activation
+        # of its shape (~0.9 MB per token for XLM-R-large), so both caches are bounded: a corpus with hundreds of distinct
+        # (R, S) keeps the most recent few and replays the rest eagerly until they come back.
+        self._graphs = collections.OrderedDict()
+        self._tgraphs = collections.OrderedDict()
+        self._graph_cap = max(1, int(os.environ.get("KBNER_GRAPH_CACHE", "8")))
+        self._tgraph_cap = max(1, int(os.environ.get("KBNER_TRAIN_GRAPH_CACHE", "3")))
         self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
         self._fuse_ln = os.environ.get("KBNER_FUSE_LN", "1") != "0"
+        self.precision = os.environ.get("KBNER_PRECISION", "bf16")
+        if self.precision not in PRECISIONS:
+            raise ValueError("KBNER_PRECISION must be one of %s" % (PRECISIONS,))
 
     # ---- checkpointing: only parameters travel; graphs, workspaces, compute copies and the arena are rebuilt ----
     def __getstate__(self):
         state = self.__dict__.copy()
         for k in ("_compute", "arena", "_drop_seed", "_drop_seed_buf"):
             state[k] = None
-        for k in ("_ws", "_graphs", "_tgraphs"):
-            state[k] = {}
+        state["_ws"] = {}
+        state["_graphs"] = collections.OrderedDict()
+        state["_tgraphs"] = collections.OrderedDict()
         state["_compute_static"] = False
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
+        self.__dict__.setdefault("_gen", 0)
+        self.__dict__.setdefault("precision", "bf16")
+        self.__dict__.setdefault("_graph_cap", 8)
+        self.__dict__.setdefault("_tgraph_cap", 3)
         # parameters arrive as views of the saved arena storage: give each its own storage again
         for p in self.parameters():
             p.data = p.data.clone()
@@ -136,44 +161,89 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         missing = [k for k in own if k not in sd]
         if missing:
             raise KeyError("missing encoder parameters: %s" % missing[:4])
-        self.load_state_dict(sd)
+        bad = [(k, tuple(v.shape), tuple(own[k].shape)) for k, v in sd.items() if tuple(v.shape) != tuple(own[k].shape)]
+        if bad:
+            raise ValueError("encoder parameter shapes differ from the config: %s" % bad[:3])
+        self.load_state_dict({k: v.to(torch.float32) for k, v in sd.items()})
         self._compute = None
+
+    def set_precision(self, precision):
+        """Switch the inference arithmetic (module docstring); drops the compute copies and every captured graph."""
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
+        if precision != self.precision:
+            self.precision = precision
+            self._compute = None
+            self._drop_graphs()
+
+    def _drop_graphs(self):
+        self._graphs.clear()
+        self._tgraphs.clear()
+        self._ws = {}
+        self._gen += 1
 
     @torch.no_grad()
     def sync_compute_weights(self):
-        """(Re)build the bf16 compute copies from the fp32 masters (after load / optimizer step)."""
+        """(Re)build the bf16 compute copies from the fp32 masters (after load / optimizer step).  The copies are NEW
+        tensors, so every graph that captured the old addresses is dropped here."""
+        x3 = self.precision == "bf16x3"
+
+        def w(t):
+            t = t.detach().float()
+            hi = t.bfloat16()
+            if not x3:
+                return hi.contiguous()
+            lo = (t - hi.float()).bfloat16()
+            return torch.cat([hi, hi, lo], 1).contiguous()      # [out, 3*in]: pairs with activation rows [ hi | lo | hi ]
         layers = []
         for lyr in self.encoder.layer:
             a = lyr.attention
             layers.append(dict(
-                wqkv=torch.cat([a.self.query.weight, a.self.key.weight, a.self.value.weight], 0).bfloat16().contiguous(),
+                wqkv=w(torch.cat([a.self.query.weight, a.self.key.weight, a.self.value.weight], 0)),
                 bqkv=torch.cat([a.self.query.bias, a.self.key.bias, a.self.value.bias], 0).float().contiguous(),
-                wo=a.output.dense.weight.bfloat16().contiguous(), bo=a.output.dense.bias.float().contiguous(),
+                wo=w(a.output.dense.weight), bo=a.output.dense.bias.float().contiguous(),
                 g1=a.output.LayerNorm.weight.float().contiguous(), b1=a.output.LayerNorm.bias.float().contiguous(),
-                w1=lyr.intermediate.dense.weight.bfloat16().contiguous(), bi=lyr.intermediate.dense.bias.float().contiguous(),
-                w2=lyr.output.dense.weight.bfloat16().contiguous(), b2=lyr.output.dense.bias.float().contiguous(),
+                w1=w(lyr.intermediate.dense.weight), bi=lyr.intermediate.dense.bias.float().contiguous(),
+                w2=w(lyr.output.dense.weight), b2=lyr.output.dense.bias.float().contiguous(),
                 g2=lyr.output.LayerNorm.weight.float().contiguous(), bb2=lyr.output.LayerNorm.bias.float().contiguous()))
         self._compute = layers
+        self._compute_static = False
+        self._drop_graphs()
+
+    def _new_workspace(self, M, dev):
+        H, F = self.config.hidden_size, self.config.intermediate_size
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        if self.precision == "bf16":
+            return dict(x0=e((M, H), bf), x1=e((M, H), bf), qkv=e((M, 3 * H), bf), ctx=e((M, H), bf), y=e((M, H), f32),
+                        h=e((M, F), bf))
+        k = 3 if self.precision == "bf16x3" else 1
+        ws = dict(x=e((M, k * H), bf), r0=e((M, H), f32), r1=e((M, H), f32), qkv=e((M, 3 * H), bf), ctx=e((M, k * H), bf),
+                  y=e((M, H), f32), h=e((M, k * F), bf))
+        if k == 3:
+            ws["yf"] = e((M, F), f32)
+        return ws
 
     def _workspace(self, M, dev):
-        key = (M, str(dev))
+        """Workspace of the EAGER path: one shape resident.  A captured graph owns a workspace of its own (st["ws"]): these
+        buffers go back to the allocator when another shape arrives, and a graph must never write to freed memory."""
+        key = (M, str(dev), self.precision)
         ws = self._ws.get(key)
         if ws is None:
-            H, F = self.config.hidden_size, self.config.intermediate_size
-            bf, f32 = torch.bfloat16, torch.float32
-            ws = dict(x0=torch.empty((M, H), dtype=bf, device=dev), x1=torch.empty((M, H), dtype=bf, device=dev),
-                      qkv=torch.empty((M, 3 * H), dtype=bf, device=dev), ctx=torch.empty((M, H), dtype=bf, device=dev),
-                      y=torch.empty((M, H), dtype=f32, device=dev), h=torch.empty((M, F), dtype=bf, device=dev))
-            self._ws = {key: ws}      # keep one shape resident
+            ws = self._new_workspace(M, dev)
+            self._ws = {key: ws}
         return ws
 
     # ---- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def _forward_hidden_eager(self, ids, key_len):
+    def _forward_hidden_eager(self, ids, key_len, ws=None):
         c = self.config
         R, S = ids.shape
         M = R * S
-        ws = self._workspace(M, ids.device)
+        if ws is None:
+            ws = self._workspace(M, ids.device)
+        if self.precision != "bf16":
+            return self._forward_hidden_precise(ids, key_len, ws)
         e = self.embeddings
         x, xn = ws["x0"], ws["x1"]
         ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight,
@@ -201,39 +271,78 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         return x
 
     @torch.no_grad()
-    def forward_hidden(self, ids, key_len):
-        """ids [R,S] int32 (cuda), key_len [R] int32 -> last hidden state [R*S, H] bf16.
-        The returned tensor aliases an internal workspace buffer (valid until the next call).
-
-        The 1 + 7*layers launches of one shape are captured into a CUDA graph on the second call with that shape and
-        replayed afterwards (static id / length buffers, static workspace): the forward of a batch is one graph launch,
-        which takes ~170 ctypes round trips per batch off the host's critical path.  KBNER_GRAPHS=0 disables it."""
-        if self._compute is None:
-            self.sync_compute_weights()
-            self._graphs = {}
+    def _forward_hidden_precise(self, ids, key_len, ws):
+        """"bf16-res32" / "bf16x3" (module docstring).  Same kernels for the contractions -- the tcgen05 GEMM over
+        K-concatenated operands, the attention kernel writing its output as hi|lo|hi -- plus the fp32-residual LayerNorm
+        and the bias + erf-GELU + split pass.  Q/K/V and the probabilities stay single bf16 (2.0e-4 of the 24-layer hidden
+        state, scripts/bf16_ablation.py).  Returns the fp32 hidden state [R*S, H]."""
+        c = self.config
         R, S = ids.shape
-        key = (R, S, str(ids.device), id(self._compute))
-        st = self._graphs.get(key) if self._use_graphs else None
-        if st is not None and st["graph"] is not None:
+        x3 = self.precision == "bf16x3"
+        e = self.embeddings
+        x, r_in, r_out = ws["x"], ws["r0"], ws["r1"]
+        y, h, ctx, qkv = ws["y"], ws["h"], ws["ctx"], ws["qkv"]
+        ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight,
+                         e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias,
+                         c.layer_norm_eps, c.pad_token_id, out=x, out32=r_in, split=x3)
+        for w in self._compute:
+            ops.gemm_bf16_tn(x, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BIAS, out=qkv)
+            ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, out=ctx, split=x3)
+            ops.gemm_bf16_tn(ctx, w["wo"], None, epilogue=ops.EPI_NONE_F32, out=y)
+            ops.layernorm_fwd_res32(y, w["g1"], w["b1"], c.layer_norm_eps, out=x, out32=r_out, bias=w["bo"], resid=r_in,
+                                    split=x3)
+            r_in, r_out = r_out, r_in
+            if x3:
+                ops.gemm_bf16_tn(x, w["w1"], None, epilogue=ops.EPI_NONE_F32, out=ws["yf"])
+                ops.bias_gelu_split(ws["yf"], w["bi"], h)
+            else:
+                ops.gemm_bf16_tn(x, w["w1"], w["bi"], epilogue=ops.EPI_BIAS_GELU, out=h)
+            ops.gemm_bf16_tn(h, w["w2"], None, epilogue=ops.EPI_NONE_F32, out=y)
+            ops.layernorm_fwd_res32(y, w["g2"], w["bb2"], c.layer_norm_eps, out=x, out32=r_out, bias=w["b2"], resid=r_in,
+                                    split=x3)
+            r_in, r_out = r_out, r_in
+        return r_in
+
+    @torch.no_grad()
+    def forward_hidden(self, ids, key_len):
+        """ids [R,S] int32 (cuda), key_len [R] int32 -> last hidden state [R*S, H] (bf16; fp32 in the precision modes).
+        The returned tensor aliases an internal buffer (valid until the next call).
+
+        The 1 + 5*layers launches of one shape are captured into a CUDA graph on the second call with that shape and
+        replayed afterwards (static id / length buffers, a workspace the graph state owns): the forward of a batch is
+        one graph launch, which takes ~125 ctypes round trips per batch off the host's critical path.  The cache keeps the
+        KBNER_GRAPH_CACHE (8) most recently used shapes; KBNER_GRAPHS=0 disables capture."""
+        if self._compute is None:
+            if getattr(self, "arena", None) is not None and self.precision == "bf16":
+                _sync_compute_weights_arena(self)
+            else:
+                self.sync_compute_weights()
+        if not self._use_graphs:
+            return self._forward_hidden_eager(ids, key_len)
+        R, S = ids.shape
+        key = (R, S, str(ids.device), self._gen, self.precision)
+        st = self._graphs.get(key)
+        if st is None:                                   # first call with this shape: eager (also warms every kernel up)
+            self._graphs[key] = {"graph": None}
+            while len(self._graphs) > self._graph_cap:
+                self._graphs.popitem(last=False)
+            return self._forward_hidden_eager(ids, key_len)
+        self._graphs.move_to_end(key)
+        if st["graph"] is not None:
             st["ids"].copy_(ids, non_blocking=True)
             st["key_len"].copy_(key_len, non_blocking=True)
             st["graph"].replay()
             _lib_note_launches(st["launches"])
             return st["out"]
-        if not self._use_graphs:
-            return self._forward_hidden_eager(ids, key_len)
-        if st is None:                                   # first call with this shape: eager (also warms every kernel up)
-            self._graphs = {k: v for k, v in self._graphs.items() if k[3] == id(self._compute)}
-            self._graphs[key] = {"graph": None, "calls": 1}
-            return self._forward_hidden_eager(ids, key_len)
         # second call: capture
         from . import _lib
         st["ids"], st["key_len"] = ids.clone(), key_len.clone()
+        st["ws"] = self._new_workspace(R * S, ids.device)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
         with torch.cuda.graph(g):
-            st["out"] = self._forward_hidden_eager(st["ids"], st["key_len"])
+            st["out"] = self._forward_hidden_eager(st["ids"], st["key_len"], st["ws"])
         st["launches"] = _lib.launch_count() - l0
         st["graph"] = g
         g.replay()
@@ -252,22 +361,30 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         return (h.float().view(ids.shape[0], ids.shape[1], -1),)
 
     # the HF surface the reference touches: train.py:208-209,260-261; finetune_trainer.py:1297-1298
-    def save_pretrained(self, path):
+    def save_pretrained(self, path, safe_serialization=True):
+        """A directory `transformers.XLMRobertaModel.from_pretrained` can read (and from_pretrained below):
+        config.json in transformers' layout + model.safetensors (safe_serialization=False: pytorch_model.bin, the only
+        format the reference's transformers 3.0.0 knows)."""
         import json
-        import os
+        from .checkpoint_compat import hf_config_dict
         os.makedirs(path, exist_ok=True)
-        torch.save(self.state_dict(), os.path.join(path, "pytorch_model.bin"))
+        sd = {k: v.detach().to("cpu").contiguous().clone() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(path, "pytorch_model.bin"))
         with open(os.path.join(path, "config.json"), "w") as f:
-            json.dump(self.config.to_dict(), f, indent=1)
+            json.dump(hf_config_dict(self.config), f, indent=1)
 
     @classmethod
     def from_pretrained(cls, path, **kw):
-        import json
-        import os
-        with open(os.path.join(path, "config.json")) as f:
-            cfg = json.load(f)
-        m = cls(EncoderConfig(**{**cfg, **kw}))
-        m.load_hf_state_dict(torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu"))
+        """Replaces AutoModel.from_pretrained(model, config=config) for a LOCAL directory (flair/embeddings.py:2951-2953):
+        config.json + model.safetensors / pytorch_model.bin as transformers (any version) or this package wrote them, with or
+        without a task-model prefix (`roberta.`); pooler / LM-head tensors are ignored, a missing encoder tensor raises."""
+        from .checkpoint_compat import config_from_hf_json, normalize_hf_state_dict, read_weight_files
+        m = cls(config_from_hf_json(path, **kw))
+        m.load_hf_state_dict(normalize_hf_state_dict(read_weight_files(path)))
         return m
 
 
@@ -284,10 +401,12 @@ class ParamArena:
     def __init__(self, params):
         params = list(params)
         dev = params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in params]           # keep every view 16-byte aligned
+        sizes = [(p.numel() + 7) // 8 * 8 for p in params]           # every view 16-byte aligned, in fp32 and in bf16
         self.numel = sum(sizes)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.shadow = None            # bf16 copy of flat[:shadow.numel()] (the tensor-core operands), see make_shadow
+        self.shadow_fresh = False     # set by FusedAdamW.step when its launch has just rewritten the shadow
         self.offsets = {}
         off = 0
         for p, n in zip(params, sizes):
@@ -304,6 +423,27 @@ class ParamArena:
         for s in shape:
             n *= s
         return (self.grad if grad else self.flat)[off:off + n].view(shape)
+
+    def make_shadow(self, n):
+        """bf16 shadow of the first n parameters, same offsets as the fp32 arena.  FusedAdamW writes it in the optimizer
+        launch; refresh_shadow() is the explicit fp32 -> bf16 pass for every other way the masters can change."""
+        n = (int(n) + 7) // 8 * 8
+        if self.shadow is None or self.shadow.numel() != n:
+            self.shadow = torch.empty(n, dtype=torch.bfloat16, device=self.flat.device)
+            self.shadow_fresh = False
+        return self.shadow
+
+    def refresh_shadow(self):
+        if self.shadow is not None:
+            ops.pack_bf16(self.flat[:self.shadow.numel()], self.shadow)
+        self.shadow_fresh = False
+
+    def shadow_view(self, p_first, shape):
+        off = self.offsets[id(p_first)]
+        n = 1
+        for s_ in shape:
+            n *= s_
+        return self.shadow[off:off + n].view(shape)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -333,33 +473,34 @@ def _ensure_arena(self):
 
 @torch.no_grad()
 def _sync_compute_weights_arena(self):
-    """bf16 compute copies straight from the arena (Q|K|V are one contiguous [3H,H] region: no concatenation).
-    The copies live in STATIC buffers that are refreshed in place after every optimizer step, so CUDA graphs that
-    captured their addresses stay valid."""
+    """bf16 compute copies as VIEWS of the arena's bf16 shadow (same offsets as the fp32 masters; Q|K|V are one contiguous
+    [3H,H] region: no concatenation).  The shadow is a static buffer: CUDA graphs that captured its addresses stay valid.
+    FusedAdamW.step rewrites it inside the optimizer launch (and marks it fresh), so the call that follows an optimizer
+    step costs nothing; any other change of the masters is picked up by the one fp32 -> bf16 pass here."""
     ar = self.arena
     H = self.config.hidden_size
-    if getattr(self, "_compute_static", False) and self._compute is not None:
-        for lyr, w in zip(self.encoder.layer, self._compute):
-            a = lyr.attention
-            w["wqkv"].copy_(ar.view(a.self.query.weight, (3 * H, H)))
-            w["wo"].copy_(a.output.dense.weight)
-            w["w1"].copy_(lyr.intermediate.dense.weight)
-            w["w2"].copy_(lyr.output.dense.weight)
+    if getattr(self, "_compute_static", False) and self._compute is not None and ar.shadow is not None:
+        if ar.shadow_fresh:
+            ar.shadow_fresh = False
+        else:
+            ar.refresh_shadow()
         return
+    ar.make_shadow(ar.offsets[id(self.embeddings.word_embeddings.weight)])      # the encoder layers (_arena_order)
+    ar.refresh_shadow()
     layers = []
     for lyr in self.encoder.layer:
         a = lyr.attention
         layers.append(dict(
-            wqkv=ar.view(a.self.query.weight, (3 * H, H)).bfloat16(), bqkv=ar.view(a.self.query.bias, (3 * H,)),
-            wo=a.output.dense.weight.bfloat16(), bo=a.output.dense.bias.data,
+            wqkv=ar.shadow_view(a.self.query.weight, (3 * H, H)), bqkv=ar.view(a.self.query.bias, (3 * H,)),
+            wo=ar.shadow_view(a.output.dense.weight, tuple(a.output.dense.weight.shape)), bo=a.output.dense.bias.data,
             g1=a.output.LayerNorm.weight.data, b1=a.output.LayerNorm.bias.data,
-            w1=lyr.intermediate.dense.weight.bfloat16(), bi=lyr.intermediate.dense.bias.data,
-            w2=lyr.output.dense.weight.bfloat16(), b2=lyr.output.dense.bias.data,
+            w1=ar.shadow_view(lyr.intermediate.dense.weight, tuple(lyr.intermediate.dense.weight.shape)),
+            bi=lyr.intermediate.dense.bias.data,
+            w2=ar.shadow_view(lyr.output.dense.weight, tuple(lyr.output.dense.weight.shape)), b2=lyr.output.dense.bias.data,
             g2=lyr.output.LayerNorm.weight.data, bb2=lyr.output.LayerNorm.bias.data))
     self._compute = layers
     self._compute_static = True
-    self._graphs = {}
-    self._tgraphs = {}
+    self._drop_graphs()
 
 
 def _dropout_sites(self, li):
@@ -409,6 +550,8 @@ def _forward_train(self, ids, key_len):
     """Forward that keeps the activations the backward needs.  Returns (hidden [R*S,H] bf16, saved).
     Like forward_hidden, the launches of one (R, S) shape are captured into a CUDA graph on the second call and
     replayed afterwards; the saved activations then live in the graph's private pool (valid until the next replay)."""
+    if self.precision != "bf16":
+        raise NotImplementedError("fine-tuning runs in the bf16 arithmetic; precision=%r is an inference mode" % self.precision)
     _ensure_arena(self)
     if self._compute is None or not getattr(self, "_compute_static", False):
         self._compute = None
@@ -432,7 +575,10 @@ def _forward_train(self, ids, key_len):
     st = self._tgraphs.get(key)
     if st is None:
         self._tgraphs[key] = {"fwd": None, "bwd": None}
+        while len(self._tgraphs) > self._tgraph_cap:          # least recently used shape: its graph pool (saved activations) goes
+            self._tgraphs.popitem(last=False)
         return _forward_train_eager(self, ids, key_len)
+    self._tgraphs.move_to_end(key)
     if st["fwd"] is None:
         from . import _lib
         st["ids"], st["key_len"] = ids.clone(), key_len.clone()

@@ -92,20 +92,57 @@ def crf_nll_bwd(emis, tags, trans, klen, alpha, w, start_idx, stop_idx, pos=None
 
 
 # ---- encoder -----------------------------------------------------------------------------------
-def embed_ln_fwd(ids, word_emb, pos_emb, type_emb, gamma, beta, eps, pad_id, out=None):
+def embed_ln_fwd(ids, word_emb, pos_emb, type_emb, gamma, beta, eps, pad_id, out=None, out32=None, split=False):
+    """out [R*S,H] bf16 (split: [R*S,3H] rows hi|lo|hi); out32 (optional) receives the same values in fp32."""
     _chk(ids, torch.int32, "ids", 2)
+    _chk(out32, torch.float32, "out32", 2)
     for n, t in (("word_emb", word_emb), ("pos_emb", pos_emb), ("type_emb", type_emb), ("gamma", gamma),
                  ("beta", beta)):
         _chk(t, torch.float32, n)
     R, S = ids.shape
     V, H = word_emb.shape
     P = pos_emb.shape[0]
+    width = 3 * H if split else H
     if out is None:
-        out = torch.empty((R * S, H), dtype=torch.bfloat16, device=ids.device)
-    _lib.check(_lib.load().kbner_embed_ln_fwd(_ptr(ids), _ptr(word_emb), _ptr(pos_emb), _ptr(type_emb), _ptr(gamma),
-                                              _ptr(beta), float(eps), int(pad_id), R, S, H, V, P, _ptr(out),
-                                              _stream()), "embed_ln_fwd")
+        out = torch.empty((R * S, width), dtype=torch.bfloat16, device=ids.device)
+    else:
+        _chk(out, torch.bfloat16, "out", 2)
+        if tuple(out.shape) != (R * S, width):
+            raise _lib.KbnerError("embed_ln_fwd: out must be [%d, %d]" % (R * S, width))
+    _lib.check(_lib.load().kbner_embed_ln_fwd_ex(_ptr(ids), _ptr(word_emb), _ptr(pos_emb), _ptr(type_emb), _ptr(gamma),
+                                                 _ptr(beta), float(eps), int(pad_id), R, S, H, V, P, _ptr(out),
+                                                 _ptr(out32), int(bool(split)), _stream()), "embed_ln_fwd")
     return out
+
+
+def layernorm_fwd_res32(x, gamma, beta, eps, out, out32=None, bias=None, resid=None, split=False):
+    """Precision modes: out32 = LayerNorm(x + bias + resid) (fp32 residual stream), out = bf16 / split bf16 copy."""
+    _chk(x, torch.float32, "x", 2)
+    _chk(gamma, torch.float32, "gamma", 1)
+    _chk(beta, torch.float32, "beta", 1)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(resid, torch.float32, "resid", 2)
+    _chk(out32, torch.float32, "out32", 2)
+    _chk(out, torch.bfloat16, "out", 2)
+    M, H = x.shape
+    if tuple(out.shape) != (M, 3 * H if split else H):
+        raise _lib.KbnerError("layernorm_fwd_res32: out must be [%d, %d]" % (M, 3 * H if split else H))
+    _lib.check(_lib.load().kbner_add_layernorm_fwd_res32(_ptr(x), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta), float(eps),
+                                                         M, H, _ptr(out32), _ptr(out), int(bool(split)), _stream()),
+               "layernorm_fwd_res32")
+    return out
+
+
+def bias_gelu_split(x, bias, out3):
+    """out3 [M,3F] bf16 = hi|lo|hi of gelu_erf(x + bias), x fp32 [M,F]."""
+    _chk(x, torch.float32, "x", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    _chk(out3, torch.bfloat16, "out3", 2)
+    M, F = x.shape
+    if tuple(out3.shape) != (M, 3 * F):
+        raise _lib.KbnerError("bias_gelu_split: out3 must be [%d, %d]" % (M, 3 * F))
+    _lib.check(_lib.load().kbner_bias_gelu_split(_ptr(x), _ptr(bias), M, F, _ptr(out3), _stream()), "bias_gelu_split")
+    return out3
 
 
 def _drop_args(drop):
@@ -152,7 +189,8 @@ def dropout_apply(x, drop):
 
 
 def gather_tagproj_fwd(hidden, row_of, first_idx, W, bias, S, drop_keep=None):
-    _chk(hidden, torch.bfloat16, "hidden", 2)
+    f32 = hidden.dtype == torch.float32          # precision modes hand the last LayerNorm's fp32 output over
+    _chk(hidden, torch.float32 if f32 else torch.bfloat16, "hidden", 2)
     _chk(row_of, torch.int32, "row_of", 1)
     _chk(first_idx, torch.int32, "first_idx", 2)
     _chk(W, torch.float32, "W", 2)
@@ -161,9 +199,9 @@ def gather_tagproj_fwd(hidden, row_of, first_idx, W, bias, S, drop_keep=None):
     B, T = first_idx.shape
     L, H = W.shape
     logits = torch.empty((B, T, L), dtype=torch.float32, device=hidden.device)
-    _lib.check(_lib.load().kbner_gather_tagproj_fwd(_ptr(hidden), _ptr(row_of), _ptr(first_idx), _ptr(drop_keep),
-                                                    _ptr(W), _ptr(bias), B, T, int(S), H, L, _ptr(logits),
-                                                    _stream()), "gather_tagproj_fwd")
+    fn = _lib.load().kbner_gather_tagproj_fwd_f32 if f32 else _lib.load().kbner_gather_tagproj_fwd
+    _lib.check(fn(_ptr(hidden), _ptr(row_of), _ptr(first_idx), _ptr(drop_keep),
+                  _ptr(W), _ptr(bias), B, T, int(S), H, L, _ptr(logits), _stream()), "gather_tagproj_fwd")
     return logits
 
 
@@ -210,18 +248,24 @@ def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None):
     return out
 
 
-def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None):
+def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None, split=False):
+    """out [R*S,H] bf16; split=True: out is the [R*S,3H] operand of the attention-output GEMM, rows hi|lo|hi."""
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(key_len, torch.int32, "key_len", 1)
     H = heads * 64
     if qkv.shape != (R * S, 3 * H):
         raise _lib.KbnerError("attention: qkv must be [R*S, 3*H] = [%d, %d], got %s" % (R * S, 3 * H, tuple(qkv.shape)))
+    width = 3 * H if split else H
     if out is None:
-        out = torch.empty((R * S, H), dtype=torch.bfloat16, device=qkv.device)
+        out = torch.empty((R * S, width), dtype=torch.bfloat16, device=qkv.device)
+    else:
+        _chk(out, torch.bfloat16, "out", 2)
+        if tuple(out.shape) != (R * S, width):
+            raise _lib.KbnerError("attention: out must be [%d, %d]" % (R * S, width))
     lse = torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device) if want_lse else None
     sp, site, p = _drop_args(drop)
-    _lib.check(_lib.load().kbner_attention_fwd_dropout(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), _ptr(lse), sp, site, p,
-                                                       _stream()), "attention_fwd")
+    _lib.check(_lib.load().kbner_attention_fwd_ex(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), width, int(bool(split)),
+                                                  _ptr(lse), sp, site, p, _stream()), "attention_fwd")
     return (out, lse) if want_lse else out
 
 
@@ -297,12 +341,41 @@ def clip_coef(sumsq, pre_scale, max_norm, coef):
     return coef
 
 
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale_dev=None, gscale_host=1.0):
-    for n, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, gscale_dev=None, gscale_host=1.0, shadow=None):
+    """Fused AdamW over a flat arena.  g: fp32, or the bf16 buffer an all-reduce of packed gradients left behind.
+    shadow (optional, bf16, numel <= p.numel()): receives the updated leading parameters as bf16 (compute copies)."""
+    for n, t in (("p", p), ("m", m), ("v", v)):
         _chk(t, torch.float32, n, 1)
-    _lib.check(_lib.load().kbner_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1),
-                                            float(beta2), float(eps), float(weight_decay), int(step), _ptr(gscale_dev),
-                                            float(gscale_host), _stream()), "adamw_step")
+    gb = g.dtype == torch.bfloat16
+    _chk(g, torch.bfloat16 if gb else torch.float32, "g", 1)
+    _chk(shadow, torch.bfloat16, "shadow", 1)
+    if g.numel() != p.numel():
+        raise _lib.KbnerError("adamw_step: gradient has %d elements, parameters %d" % (g.numel(), p.numel()))
+    _lib.check(_lib.load().kbner_adamw_step_ex(_ptr(p), None if gb else _ptr(g), _ptr(g) if gb else None, _ptr(m), _ptr(v),
+                                               p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                               float(weight_decay), int(step), _ptr(gscale_dev), float(gscale_host),
+                                               _ptr(shadow), 0 if shadow is None else shadow.numel(), _stream()),
+               "adamw_step")
+
+
+def pack_bf16(src, dst, scale=1.0):
+    """dst (bf16) = src (fp32) * scale, flat buffers with a multiple of 4 elements."""
+    _chk(src, torch.float32, "src", 1)
+    _chk(dst, torch.bfloat16, "dst", 1)
+    if src.numel() != dst.numel():
+        raise _lib.KbnerError("pack_bf16: size mismatch")
+    _lib.check(_lib.load().kbner_pack_bf16(_ptr(src), _ptr(dst), src.numel(), float(scale), _stream()), "pack_bf16")
+    return dst
+
+
+def sumsq(g, out):
+    """out[0] += sum g^2 over a flat fp32 or bf16 buffer."""
+    if g.dtype == torch.bfloat16:
+        _chk(g, torch.bfloat16, "g", 1)
+        _chk(out, torch.float32, "out", 1)
+        _lib.check(_lib.load().kbner_sumsq_bf16(_ptr(g), g.numel(), _ptr(out), _stream()), "sumsq_bf16")
+        return out
+    return sumsq_f32(g, out)
 
 
 EPI_DGELU_BF16, EPI_ACCUM_F32 = 4, 5

@@ -33,28 +33,34 @@ class FusedAdamW:
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
 
-    def grad_norm(self, grad_scale=1.0):
+    def grad_norm(self, grad_scale=1.0, grads=None):
         """Global L2 norm of (grad * grad_scale) over all arenas -- a device tensor, no sync."""
         self._sumsq.zero_()
-        for g in self.groups:
-            ops.sumsq_f32(g["arena"].grad, self._sumsq)
+        for i, g in enumerate(self.groups):
+            ops.sumsq(g["arena"].grad if grads is None else grads[i], self._sumsq)
         return torch.sqrt(self._sumsq) * grad_scale
 
-    def step(self, grad_scale=1.0):
-        """grad_scale multiplies every gradient first (1/accumulation, 1/world after a sum all-reduce)."""
+    def step(self, grad_scale=1.0, grads=None):
+        """grad_scale multiplies every gradient first (1/accumulation, 1/world after a sum all-reduce).
+        grads (optional): one flat buffer per group to read INSTEAD of arena.grad -- the bf16 buffers a data-parallel
+        exchange (distributed.GradExchange) left behind; the clip norm is taken over the same buffers (post-reduce,
+        finetune_trainer.py:1010).  Arenas that carry a bf16 shadow get it rewritten by the same launch."""
         self.steps += 1
         self._sumsq.zero_()
-        for g in self.groups:
-            ops.sumsq_f32(g["arena"].grad, self._sumsq)
+        for i, g in enumerate(self.groups):
+            ops.sumsq(g["arena"].grad if grads is None else grads[i], self._sumsq)
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
             ops.clip_coef(self._sumsq, grad_scale, self.max_grad_norm, self._coef)
             coef = self._coef
         else:
             coef = None
-        for g in self.groups:
+        for i, g in enumerate(self.groups):
             ar = g["arena"]
-            ops.adamw_step(ar.flat, ar.grad, g["m"], g["v"], g["lr"], self.betas[0], self.betas[1], self.eps,
-                           self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale)
+            ops.adamw_step(ar.flat, ar.grad if grads is None else grads[i], g["m"], g["v"], g["lr"], self.betas[0],
+                           self.betas[1], self.eps, self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale,
+                           shadow=ar.shadow)
+            if ar.shadow is not None:
+                ar.shadow_fresh = True
 
     def zero_grad(self):
         for g in self.groups:

@@ -71,8 +71,10 @@ class SequenceTagger(torch.nn.Module):
         bad = [k for k, v in off.items() if v]
         if bad:
             raise NotImplementedError("options outside the hot path (KD / multi-view / ACE variants): %s" % bad)
-        if dropout or (locked_dropout and use_rnn):
-            raise NotImplementedError("dropout / locked_dropout apply to the RNN path only")
+        # dropout / locked_dropout: the reference applies Dropout and LockedDropout to the embedded sentence tensor BEFORE
+        # the use_rnn branch (sequence_tagger_model.py:958-964), i.e. also on this head, in train() mode.  Every KB-NER YAML
+        # sets both to 0.0 and the fused projection kernel carries word dropout only: the values are stored (they are part
+        # of the checkpoint format, :452-454) and a TRAINING forward with either > 0 raises -- see forward().
         # ---- attribute surface read by ModelFinetuner / train.py -----------------------
         self.debug, self.use_language_attention, self.biaf_attention = debug, False, False
         self.token_level_attention, self.use_language_vector, self.use_crf = False, False, True
@@ -96,7 +98,7 @@ class SequenceTagger(torch.nn.Module):
         self.distill_emission = self.crf_attention = self.enhanced_crf = self.predict_posterior = False
         self.posterior_constraint = self.use_transition_attention = self.unlabel_entropy_loss = False
         self.relearn_embeddings = self.map_embeddings = self.embedding_selector = self.use_rl = False
-        self.use_dropout, self.use_word_dropout, self.use_locked_dropout = 0.0, word_dropout, locked_dropout
+        self.use_dropout, self.use_word_dropout, self.use_locked_dropout = dropout, word_dropout, locked_dropout
         self.pickle_module = pickle_module
         self.interpolation = interpolation
         self.time = 0.0
@@ -106,7 +108,6 @@ class SequenceTagger(torch.nn.Module):
         self.linear = torch.nn.Linear(self.embeddings.embedding_length, self.tagset_size)
         self.start_idx = tag_dictionary.get_idx_for_item(START_TAG)
         self.stop_idx = tag_dictionary.get_idx_for_item(STOP_TAG)
-        self.x_idx = tag_dictionary.get_idx_for_item("S-X")
         trans = torch.randn(self.tagset_size, self.tagset_size)
         trans[self.start_idx, :] = -1e12          # nothing transitions INTO <START>   (:402-410; [to, from])
         trans[:, self.stop_idx] = -1e12           # nothing transitions FROM <STOP>
@@ -119,6 +120,16 @@ class SequenceTagger(torch.nn.Module):
     @property
     def device(self):
         return self.transitions.device
+
+    @property
+    def x_idx(self):
+        """Index of 'S-X', looked up at call time like the reference (:1202, :2449): `train.py --parse --remove_x` adds the
+        item to the dictionary AFTER the model was loaded.  Items beyond the L emission columns cannot be decoded."""
+        idx = self.tag_dictionary.get_idx_for_item("S-X")
+        if idx >= self.tagset_size:
+            raise ValueError("'S-X' was added to the tag dictionary after the model was built (index %d, %d emission columns): "
+                             "remove_x needs a model trained with S-X in its tag set" % (idx, self.tagset_size))
+        return idx
 
     def _encoded(self, sentences):
         """The device-side batch left behind by embeddings.embed (one stacked embedding)."""
@@ -142,6 +153,10 @@ class SequenceTagger(torch.nn.Module):
         if self.use_decoder_timer:
             self.time = time.time()
         drop_keep = None
+        if self.training and (self.use_dropout > 0.0 or self.use_locked_dropout > 0.0):
+            raise NotImplementedError("training with dropout=%s / locked_dropout=%s on the tagger head is not built (the KB-NER "
+                                      "configs set both to 0.0; inference with such a checkpoint is unaffected)"
+                                      % (self.use_dropout, self.use_locked_dropout))
         if self.training and self.use_word_dropout > 0.0:
             # WordDropout on [T,B,D]: one Bernoulli(1-p) draw per time step, shared by the batch, no rescale
             # (flair/nn.py:176-183)
@@ -175,7 +190,13 @@ class SequenceTagger(torch.nn.Module):
             if tg.numel() < T:
                 tg = torch.cat([tg, torch.zeros(T - tg.numel(), dtype=torch.int32)])     # pad with 0 = <unk>
             rows.append(tg[:T])
-        return torch.stack(rows, 0).to(self.device, non_blocking=True)
+        tags = torch.stack(rows, 0)
+        # host-side range check (the tensor is still on the host): a gold tag outside the L emission columns -- e.g. an item
+        # added to the dictionary after the model was built -- would index past emis / trans in the CRF kernels
+        if tags.numel() and (int(tags.max()) >= self.tagset_size or int(tags.min()) < 0):
+            raise ValueError("gold tag index outside [0, %d): the tag dictionary has items the model was not built with"
+                             % self.tagset_size)
+        return tags.to(self.device, non_blocking=True)
 
     def _calculate_loss(self, features: torch.Tensor, sentences, mask: torch.Tensor):
         B, T, L = features.shape
@@ -194,12 +215,13 @@ class SequenceTagger(torch.nn.Module):
             pos, klen = ops.crf_compact(keep_u8)                  # (:2474-2488)
         self._keep = (pos, klen)
         nll = _CrfNll.apply(features, self.transitions, tags.contiguous(), pos, klen, self.start_idx, self.stop_idx)
-        labelled = torch.tensor([0.0 if getattr(s, "is_unlabel", False) else 1.0 for s in sentences],
-                                device=nll.device)
-        if float(labelled.sum()) == 0:
-            return nll.sum() * 0.0
-        if float(labelled.min()) == 0:
-            return (nll * labelled).sum() / labelled.sum()        # (:2499-2504)
+        # is_unlabel is a host-side attribute: decided here without touching the device (two device->host syncs per
+        # micro-step sat between the forward and backward graphs in the first version)
+        n_lab = sum(0 if getattr(s, "is_unlabel", False) else 1 for s in sentences)
+        if n_lab == 0:
+            return nll.sum() * 0.0                                 # (:2500-2501)
+        if n_lab < len(sentences):
+            return nll.sum() / n_lab                               # (:2502-2504) the UNMASKED sum over the labelled count
         return nll.mean()                                          # (:2506)
 
     # ---- decode (:1157-1246) ---------------------------------------------------------------------------
@@ -318,6 +340,7 @@ class SequenceTagger(torch.nn.Module):
                 n_sent += len(batch)
                 features = self.forward(batch, prediction_mode=prediction_mode)
                 handle = self._decode_async(features)
+                batch.features = {}            # the EncodedBatch aliases the encoder's buffers: never leave it cached
                 if pending is not None:
                     self._labels_from_handle(*pending)
                 pending = (handle, batch)
@@ -347,8 +370,8 @@ class SequenceTagger(torch.nn.Module):
                     gold_x = [tok.get_tag(self.tag_type).value == "S-X" for tok in s.tokens] if self.remove_x else None
                     span_counts(metric, s.get_spans(self.tag_type), s.get_spans("predicted"), gold_x, self.remove_x)
                 store_embeddings(batch, embeddings_storage_mode)
-                if embeddings_storage_mode == "none" and hasattr(batch, "features"):
-                    batch.features = {}
+                if hasattr(batch, "features"):
+                    batch.features = {}        # the EncodedBatch aliases the encoder's buffers (valid until the next forward)
         finally:
             if outfile is not None:
                 outfile.close()
@@ -383,6 +406,7 @@ class SequenceTagger(torch.nn.Module):
         model = cls(hidden_size=state["hidden_size"], embeddings=state["embeddings"],
                     tag_dictionary=state["tag_dictionary"], tag_type=state["tag_type"], use_crf=state["use_crf"],
                     use_rnn=state["use_rnn"], use_cnn=state.get("use_cnn", False), rnn_layers=state["rnn_layers"],
+                    dropout=state.get("use_dropout", 0.0),
                     word_dropout=state.get("use_word_dropout", 0.05), locked_dropout=state.get("use_locked_dropout", 0.5),
                     remove_x=state.get("remove_x", False), sentence_loss=state.get("sentence_level_loss", False),
                     target_languages=state.get("target_languages", 1), config=state.get("config"), testing=testing)
@@ -393,12 +417,11 @@ class SequenceTagger(torch.nn.Module):
         torch.save(self._get_state_dict(), str(model_file), pickle_protocol=4)
 
     @classmethod
-    def load(cls, model_file, device=None):
-        state = torch.load(str(model_file), map_location="cpu", weights_only=False)
-        model = cls._init_model_with_state_dict(state)
-        model.eval()
-        model.to(device or "cuda")
-        return model
+    def load(cls, model_file, device=None, tokenizer=None):
+        """flair/nn.py:87-108.  Reads checkpoints written by this package AND by the reference (whose pickles name
+        flair / transformers-3.0.0 classes: checkpoint_compat maps them, see there)."""
+        from .checkpoint_compat import load_reference_checkpoint
+        return load_reference_checkpoint(model_file, tokenizer=tokenizer, device=device, tagger_cls=cls)
 
 
 class _TagProjGrad(torch.autograd.Function):

@@ -19,8 +19,9 @@ What is reproduced (file:line of the reference):
     ``model.evaluate`` (:1111), ``best-model.pt`` / ``final-model.pt`` saving (:1280-1312), ``final_test`` tolerating
     the ``eval_train`` keyword ``train.py --test`` passes (Appendix B.11).
 
-What is new: one process per GPU; the only collective is the all-reduce of the flat gradient arenas on accumulation
-boundaries (NCCL), followed by the fused clip + AdamW with ``grad_scale = 1 / world``.
+What is new: one process per GPU; the only collective is the exchange of the flat gradient arenas on accumulation
+boundaries (``distributed.GradExchange``: packed to bf16, NCCL all-reduce), followed by the fused clip + AdamW with
+``grad_scale = 1 / world`` reading the reduced buffers.
 """
 import logging
 import math
@@ -32,7 +33,7 @@ from typing import List, Optional
 import torch
 
 from .data import BatchedData
-from .distributed import OverlappedGradAllReduce, allreduce_counts, shard_indices
+from .distributed import GradExchange, allreduce_counts, shard_indices
 from .optim import build_reference_optimizer
 from .training_utils import Metric
 
@@ -90,7 +91,7 @@ class ModelFinetuner:
         opt = self.optimizer or build_reference_optimizer(model, lr=learning_rate, lr_rate=lr_rate,
                                                           max_grad_norm=max_grad_norm)
         opt.set_linear_schedule(steps_per_epoch * max_epochs)
-        arenas = [g["arena"] for g in opt.groups]
+        exchange = GradExchange(emb.model, [g["arena"] for g in opt.groups])
         rnd = random.Random(seed)
         best, history = -1.0, []
         for epoch in range(self.epoch, max_epochs):
@@ -107,21 +108,13 @@ class ModelFinetuner:
                 denom = tail if (tail and bi >= len(mine) - tail) else gradient_accumulation_steps
                 loss = model.forward_loss(batch) / denom
                 boundary = (bi + 1) % gradient_accumulation_steps == 0 or bi == len(mine) - 1
-                overlap = boundary and world > 1 and OverlappedGradAllReduce.enabled()
-                if overlap:       # the all-reduce of finished layer chunks runs under the rest of this backward
-                    with OverlappedGradAllReduce(emb.model, arenas):
-                        loss.backward()
-                else:
-                    loss.backward()
+                exchange.backward(loss, boundary)        # with overlap on, finished layer chunks are exchanged under the rest
                 seen += len(batch)
                 if boundary:
-                    if world > 1 and not overlap:
-                        for ar in arenas:
-                            torch.distributed.all_reduce(ar.grad)
-                    opt.step(grad_scale=1.0 / world)
+                    opt.step(grad_scale=1.0 / world, grads=exchange.reduce())     # None (local fp32 arenas) when world == 1
                     opt.scheduler_step()
                     opt.zero_grad()
-                    emb.model.sync_compute_weights_arena()
+                    emb.model.sync_compute_weights_arena()       # free: the optimizer launch rewrote the bf16 shadow
                 if (bi + 1) % log_every == 0:
                     run_loss = float(loss.detach()) * denom
                     log.info("epoch %d - iter %d/%d - loss %.6f - samples/sec: %.2f", epoch + 1, bi + 1, len(mine),
@@ -166,7 +159,17 @@ class ModelFinetuner:
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         batches = make_batches(list(sentences), mini_batch_size)
         mine = [batches[i] for i in shard_indices(len(batches), rank, world, pad=False)]
-        result, loss = self.model.evaluate(mine, out_path=out_path, embeddings_storage_mode="none")
+        # every rank writes its own shard's predictions; rank 0 stitches them (in rank order) into out_path afterwards
+        part = out_path if (world == 1 or out_path is None) else "%s.rank%d" % (out_path, rank)
+        result, loss = self.model.evaluate(mine, out_path=part, embeddings_storage_mode="none")
+        if world > 1 and out_path is not None:
+            torch.distributed.barrier()
+            if rank == 0:
+                with open(out_path, "w", encoding="utf-8") as out:
+                    for r in range(world):
+                        with open("%s.rank%d" % (out_path, r), encoding="utf-8") as f:
+                            out.write(f.read())
+                        os.remove("%s.rank%d" % (out_path, r))
         if world > 1:
             # every rank needs the same class order: tag types come from the shared tag dictionary
             classes = sorted({it.split("-", 1)[1] for it in self.model.tag_dictionary.get_items() if "-" in it})

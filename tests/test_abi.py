@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     assert set(_declared()) == set(kbner_b200._lib.SIGNATURES), "ctypes table out of sync with the header"
-    assert kbner_b200._lib.load().kbner_abi_version() == 1
+    assert kbner_b200._lib.load().kbner_abi_version() == 2
 
 
 def test_no_silent_fallback_when_library_missing(monkeypatch):

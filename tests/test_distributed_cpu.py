@@ -15,30 +15,43 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from kbner_b200.distributed import GradBucketReducer, allreduce_counts, global_grad_norm, shard_indices
+    from kbner_b200.distributed import GradExchange, allreduce_counts, shard_indices
+    from kbner_b200.encoder import EncoderConfig, ParamArena, XLMRobertaEncoderB200, _chunk_plan
     n = 11
     mine = shard_indices(n, rank, world)
     allidx = [None] * world
     dist.all_gather_object(allidx, mine)
     counts = allreduce_counts([len(set(mine)), rank + 1, 7])
-    # gradient averaging: each rank holds the gradient of its own shard's mean loss
+    # the host logic of the exchange is exercised with a torch stand-in for the pack kernel (the product binds the CUDA one)
+    pack = lambda src, dst, scale=1.0: dst.copy_(src * scale)
+    # gradient averaging through the PRODUCT's exchange class: each rank holds the gradient of its own shard's mean loss in
+    # a flat arena; sum over ranks / world must equal the global-batch gradient (loss is a per-batch mean,
+    # sequence_tagger_model.py:2506)
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 3))
-    x = torch.randn(4 * world, 8)
-    y = torch.randn(4 * world, 3)
-    loss = ((model(x[rank * 4:(rank + 1) * 4]) - y[rank * 4:(rank + 1) * 4]) ** 2).mean()
-    loss.backward()
-    GradBucketReducer(model.parameters(), bucket_mb=0.0005).reduce()      # tiny buckets: several per model
-    norm = float(global_grad_norm(model.parameters()))
     ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 3))
     ref.load_state_dict(model.state_dict())
+    arena = ParamArena(model.parameters())
+    x = torch.randn(4 * world, 8)
+    y = torch.randn(4 * world, 3)
     ((ref(x) - y) ** 2).mean().backward()
-    err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
-    # overlapped all-reduce of the gradient arenas: a stand-in encoder whose chunked "backward" reports the arena slices
-    # the real one finalises (encoder._chunk_plan); every rank must end with the SUM over ranks in every arena, the hook
-    # must be gone afterwards, and the plan must tile the arena exactly
-    from kbner_b200.distributed import OverlappedGradAllReduce
-    from kbner_b200.encoder import EncoderConfig, XLMRobertaEncoderB200, _chunk_plan
+    ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    errs = {}
+    for payload in ("fp32", "bf16"):
+        arena.zero_grad()
+        ex = GradExchange(None, [arena], payload=payload, overlap=False, pack=pack)
+        loss = ((model(x[rank * 4:(rank + 1) * 4]) - y[rank * 4:(rank + 1) * 4]) ** 2).mean()
+        ex.backward(loss, boundary=True)
+        (g,) = ex.reduce()
+        got = torch.cat([(g[arena.offsets[id(p)]:arena.offsets[id(p)] + p.numel()]).float() for p in model.parameters()]) / world
+        errs[payload] = float((got - ref_flat).abs().max() / ref_flat.abs().max())
+        errs[payload + "_dtype"] = str(g.dtype)
+        errs[payload + "_bytes"] = ex.bytes_per_step
+        if payload == "fp32":
+            norm = float(torch.sqrt((g ** 2).sum()))           # the clip norm is taken post-reduce: same on both ranks
+    # overlapped exchange: a stand-in for the encoder's chunked backward reports the arena slices the real one finalises
+    # (encoder._chunk_plan); every rank must end with the SUM over ranks in every arena, the hook must be gone
+    # afterwards, and the plan must tile the arena exactly
     cfg = EncoderConfig(name="t", vocab_size=50, hidden_size=256, num_hidden_layers=5, num_attention_heads=4,
                         intermediate_size=256, max_position_embeddings=32)
     enc = XLMRobertaEncoderB200(cfg)
@@ -47,21 +60,27 @@ def _worker(rank, world, port, q):
     tiles = sorted([(a, b) for _, _, a, b in plan] + [emb_slice])
     tiled = tiles[0][0] == 0 and tiles[-1][1] == ar.numel and all(tiles[i][1] == tiles[i + 1][0] for i in range(len(tiles) - 1))
     descending = all(plan[i][1] == plan[i + 1][0] + 1 for i in range(len(plan) - 1)) and plan[-1][1] == 0
-
-    class Head:
-        def __init__(self):
-            self.grad = torch.full((7,), float(rank + 1))
-    head = Head()
-    ar.grad.fill_(float(rank + 1))
-    with OverlappedGradAllReduce(enc, [ar, head]) as red:
-        hook_set = enc._grad_sync is not None
-        for _, _, a, b in plan:                   # what encoder._backward_chunked does after each chunk
-            enc._grad_sync(a, b)
-        enc._grad_sync(*emb_slice)
+    head = ParamArena([torch.nn.Parameter(torch.zeros(7))])
     total = float(sum(range(1, world + 1)))
-    overlap_ok = (tiled and descending and hook_set and enc._grad_sync is None and bool((ar.grad == total).all())
-                  and bool((head.grad == total).all()))
-    q.put((rank, allidx, counts, err, norm, overlap_ok))
+    overlap_ok = tiled and descending
+    for payload in ("fp32", "bf16"):
+        ar.grad.fill_(float(rank + 1))
+        head.grad.fill_(float(rank + 1))
+        ex = GradExchange(enc, [ar, head], payload=payload, overlap=True, pack=pack)
+        hook_seen = []
+
+        class FakeLoss:                               # what encoder._backward_chunked does after each chunk
+            def backward(self_inner):
+                hook_seen.append(enc._grad_sync is not None)
+                for _, _, a, b in plan:
+                    enc._grad_sync(a, b)
+                enc._grad_sync(*emb_slice)
+        ex.backward(FakeLoss(), boundary=True)
+        g_enc, g_head = ex.reduce()
+        overlap_ok = (overlap_ok and hook_seen == [True] and enc._grad_sync is None and bool((g_enc.float() == total).all())
+                      and bool((g_head.float() == total).all())
+                      and ex.bytes_per_step == (ar.numel + head.numel) * (2 if payload == "bf16" else 4))
+    q.put((rank, allidx, counts, errs, norm, overlap_ok))
     dist.destroy_process_group()
 
 
@@ -77,11 +96,13 @@ def test_two_rank_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     res.sort()
-    for rank, allidx, counts, err, norm, overlap_ok in res:
+    for rank, allidx, counts, errs, norm, overlap_ok in res:
         assert sorted(set(sum(allidx, []))) == list(range(11))          # every sentence covered
         assert len(allidx[0]) == len(allidx[1]) == 6                    # same number of steps on every rank
         assert counts[1] == 3 and counts[2] == 14
-        assert err < 1e-6                                               # mean of rank grads == global-batch grad
+        assert errs["fp32"] < 1e-6 and errs["fp32_dtype"] == "torch.float32"   # mean of rank grads == global-batch grad
+        assert errs["bf16"] < 1e-2 and errs["bf16_dtype"] == "torch.bfloat16"  # bf16 payload: one rounding per addend
+        assert errs["bf16_bytes"] * 2 == errs["fp32_bytes"]
         assert overlap_ok                                               # chunked all-reduce: arena tiled, sums right, hook removed
     assert abs(res[0][4] - res[1][4]) < 1e-7                            # identical clip norm on both ranks
 
