@@ -324,7 +324,7 @@ class SequenceTagger(torch.nn.Module):
 
     @torch.no_grad()
     def evaluate(self, data_loader, out_path=None, embeddings_storage_mode: str = "none", prediction_mode=False,
-                 speed_test=False):
+                 speed_test=False, materialize_labels=False):
         """-> (Result, eval_loss) like the reference (:2593-2729): per-class span counts in a Metric, the remove-X filter
         (:2653-2672) when self.remove_x, the prediction file "text gold pred score" streamed to out_path."""
         self.eval()
@@ -333,7 +333,11 @@ class SequenceTagger(torch.nn.Module):
         if speed_test:
             # forward + _obtain_labels only (:2611-2612, :2698-2700), software-pipelined: the Label lists of batch i
             # are built on the host while the kernels of batch i+1 run
+            # materialize_labels: build every Label object like the reference's _obtain_labels (:1227-1232) instead of
+            # leaving them to be created on access
             pending = None
+            finish = (lambda h, b: [list(ls) for ls in self._labels_from_handle(h, b)]) if materialize_labels \
+                else self._labels_from_handle
             for batch in data_loader:
                 if not isinstance(batch, BatchedData):
                     batch = BatchedData(batch)
@@ -342,10 +346,10 @@ class SequenceTagger(torch.nn.Module):
                 handle = self._decode_async(features)
                 batch.features = {}            # the EncodedBatch aliases the encoder's buffers: never leave it cached
                 if pending is not None:
-                    self._labels_from_handle(*pending)
+                    finish(*pending)
                 pending = (handle, batch)
             if pending is not None:
-                self.last_labels = self._labels_from_handle(*pending)
+                self.last_labels = finish(*pending)
             dt = time.time() - t0
             log.info("speed_test: %d sentences, %.2f sentences/s", n_sent, n_sent / max(dt, 1e-9))
             return {"sentences_per_sec": n_sent / max(dt, 1e-9), "sentences": n_sent}, 0.0

@@ -9,8 +9,11 @@ Behaviour chosen to exercise the branches of /root/reference/flair/embeddings.py
     zero vector);
   * "</s>" / "<s>" stay single pieces with their special ids (the '<EOS>' separator of the KB-NER inputs becomes "</s>");
   * ids are a stable hash into [4, vocab);
-  * encode_plus() restates transformers-3.0.0 only for inputs that FIT: [<s>] + ids + [</s>].  The overflow semantics of
-    3.0.0 (return_overflowing_tokens with stride) are not restated here -- that branch stays unpinned.
+  * encode_plus(): [<s>] + ids + [</s>] for inputs that fit.  For longer inputs it restates the DOCUMENTED semantics of
+    `truncation=True, stride, return_overflowing_tokens` (transformers tokenization docs: the first max_length - 2 ids are
+    kept, "overflowing_tokens" = the removed ids preceded by `stride` ids of overlap, IN ORDER), which is what
+    transformers >= 3.1 implements.  The 3.0.0 source the reference pins is not available offline, so the reference's
+    window + stitching code (:3203-3227, :3292-3299) is pinned GIVEN this overflow rule, not 3.0.0's own implementation.
 """
 from typing import List
 
@@ -52,6 +55,14 @@ class FakeSentencePieceTokenizer:
         return ids
 
     def encode_plus(self, ids, max_length=None, stride=0, return_overflowing_tokens=False, truncation=True, **_kw):
-        if max_length is not None and len(ids) + 2 > max_length:
-            raise NotImplementedError("inputs longer than max_length - 2 sub-tokens: overflow semantics not restated")
-        return {"input_ids": [self.bos_token_id] + list(ids) + [self.eos_token_id]}
+        ids = list(ids)
+        if max_length is None or len(ids) + 2 <= max_length:
+            return {"input_ids": [self.bos_token_id] + ids + [self.eos_token_id]}
+        if not truncation:
+            raise ValueError("input longer than max_length and truncation is off")
+        n_remove = len(ids) + 2 - max_length
+        kept = ids[:len(ids) - n_remove]
+        out = {"input_ids": [self.bos_token_id] + kept + [self.eos_token_id]}
+        if return_overflowing_tokens:
+            out["overflowing_tokens"] = ids[max(0, len(kept) - stride):]       # `stride` ids of overlap, then the removed ids
+        return out

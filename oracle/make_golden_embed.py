@@ -42,6 +42,12 @@ def cases():
     out.append(("long_fits", [[word(3, 3) for _ in range(254)] + ["<EOS>"] + [word(3, 3) for _ in range(253)]], {}))
     # 7: a sentence whose every word is dropped: no sub-token at all -> removed from the batch, zero vectors
     out.append(("empty_sentence", [["​", "­"]], {}))
+    # 8-10: more than 510 sub-tokens -> overlapping windows (encode_plus overflow, :3203-3227) stitched by dropping
+    # stride // 2 (+ the special token) on each inner edge (:3292-3299): two windows, three windows with multi-piece words
+    # and an <EOS> context, and a batch that mixes a windowed sentence with short ones (row bookkeeping)
+    out.append(("overflow_two_windows", [[word(3, 3) for _ in range(700)]], {}))
+    out.append(("overflow_three_windows", [[word(1, 8) for _ in range(120)] + ["<EOS>"] + [word(1, 8) for _ in range(420)]], {}))
+    out.append(("overflow_in_batch", [[word() for _ in range(5)], [word(2, 3) for _ in range(600)], [word() for _ in range(9)]], {}))
     return out
 
 

@@ -1,14 +1,12 @@
 #!/bin/bash
-# Runs the GPU parity tests group by group (separate processes: a trapped kernel poisons only its group).
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-for grp in crf gemm "layernorm or embed or tagproj" attention; do
-  name=$(echo "$grp" | tr ' ' '_')
-  timeout 600 python -m pytest tests/test_kernels_gpu.py -q -x -m gpu -k "$grp" > "gpurun_out/test_${name}.log" 2>&1
-  echo "== $grp: exit $?" | tee -a gpurun_out/summary.txt
-  tail -n 25 "gpurun_out/test_${name}.log"
-done
-timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "== smoke: exit $?" | tee -a gpurun_out/summary.txt
-tail -n 5 gpurun_out/smoke.log
-timeout 900 python -m pytest tests/test_api_gpu.py -q -x -m gpu -s > gpurun_out/test_api.log 2>&1; echo "== api: exit $?" | tee -a gpurun_out/summary.txt
-tail -n 30 gpurun_out/test_api.log
+# One GPU session: the GPU test suite, the bench line, and the ncu launch list of one bench step.
+#   gpurun --timeout 1500 -- bash scripts/gpu_ci.sh <tag> [pytest-args...]
+# Everything lands under gpurun_out/<tag>/ (copied into profiles/ by hand when it is evidence).
+set -u
+TAG=${1:-ci}; shift || true
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { tail -30 $OUT/build.log; exit 1; }
+timeout 1200 python -m pytest tests -m gpu -x -q -s "$@" > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log
+tail -5 $OUT/pytest.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err

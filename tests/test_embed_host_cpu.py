@@ -64,3 +64,30 @@ def test_golden_covers_the_branches():
     assert all(t is None for row in names["empty_sentence"]["tokens"] for t in row)          # sentence without sub-tokens
     assert max(names["long_fits"]["mask_len"]) > 500                                          # near-full window
     assert 2 in [i for row in names["with_eos_context"]["input_ids"] for i in row[1:-1]]     # '<EOS>' became </s> inside
+
+
+def test_build_batch_accepts_the_references_own_sentence_objects():
+    """Duck typing at the drop-in boundary: the reference's flair.data.Sentence / Token inside its own
+    flair.custom_data_loader.BatchedData (custom_data_loader.py:13-20) go through build_batch / embed's host half unchanged
+    and give the same tensors as this package's data classes.  Needs /root/reference (build container only)."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference is only present in the build container")
+    ref_shim.load_flair()
+    from flair.custom_data_loader import BatchedData as RefBatched
+    from flair.data import Sentence as RefSentence, Token as RefToken
+    from kbner_b200.data import BatchedData, Sentence
+    case = next(c for c in _load()["cases"] if c["name"] == "with_eos_context")
+    emb = _embeddings(case["options"], _load()["tokenizer"])
+    ref_sents = []
+    for words in case["sentences"]:
+        s = RefSentence()
+        for w in words:
+            s.add_token(RefToken(w))
+        ref_sents.append(s)
+    got = emb.build_batch(RefBatched(ref_sents))
+    want = emb.build_batch(BatchedData([Sentence(tokens=list(w)) for w in case["sentences"]]))
+    for a, b in zip(got[:4], want[:4]):
+        assert torch.equal(a, b)
+    assert got[4] == want[4] and got[5] == want[5]
+    assert hasattr(RefBatched(ref_sents), "features")          # what embed() writes its EncodedBatch into
