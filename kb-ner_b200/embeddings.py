@@ -86,11 +86,17 @@ class SyntheticTokenizer:
 
 
 def _strip_markup(piece: str) -> str:
-    """Sub-token -> surface text (the markers the reference strips, embeddings.py:3093-3101)."""
-    piece = re.sub("^Ġ", "", piece)
-    piece = re.sub("^##", "", piece)
-    piece = re.sub("^▁", "", piece)
-    return re.sub("</w>$", "", piece)
+    """Sub-token -> surface text: the four substitutions of the reference (embeddings.py:3093-3101), applied one after the
+    other like its re.sub chain, as plain string tests (130 k regex calls per 32 x 510-word batch were 100 ms of host time)."""
+    if piece[:1] == "Ġ":
+        piece = piece[1:]
+    if piece[:2] == "##":
+        piece = piece[2:]
+    if piece[:1] == "▁":
+        piece = piece[1:]
+    if piece[-4:] == "</w>":
+        piece = piece[:-4]
+    return piece
 
 
 class EncodedBatch:
@@ -181,6 +187,7 @@ class TransformerWordEmbeddings(torch.nn.Module):
         self.embedding_type = "word-level"
         self._tok_cache = {}
         self._plan_cache = {}
+        self._word_cache = {}
         self._stage = None
         self.model.eval()
 
@@ -200,7 +207,14 @@ class TransformerWordEmbeddings(torch.nn.Module):
         return getattr(eos, "content", eos)
 
     def _word_text(self, text: str) -> str:
-        return "".join(_strip_markup(p) for p in self.tokenizer.tokenize(text)).lower()
+        """_get_processed_token_text (:3103-3109): the word re-tokenised on its own, markup stripped, lower-cased.
+        Memoised per word string (the reference recomputes it for every word of every sentence on every call)."""
+        hit = self._word_cache.get(text)
+        if hit is None:
+            hit = "".join(_strip_markup(p) for p in self.tokenizer.tokenize(text)).lower()
+            if len(self._word_cache) < 1000000:
+                self._word_cache[text] = hit
+        return hit
 
     def subtokenize(self, sentence):
         """-> (sub-token ids without specials, n_sub per word).  '<EOS>' words become the tokenizer's EOS
@@ -391,11 +405,13 @@ class TransformerWordEmbeddings(torch.nn.Module):
         state["tokenizer"] = None if not isinstance(self.tokenizer, SyntheticTokenizer) else self.tokenizer
         state["_tok_cache"] = {}
         state["_plan_cache"] = {}
+        state["_word_cache"] = {}
         state["_stage"] = None
         return state
 
     def __setstate__(self, d):
         self.__dict__ = d
+        self.__dict__.setdefault("_word_cache", {})
         if self.tokenizer is None:
             from transformers import AutoTokenizer
             self.tokenizer = AutoTokenizer.from_pretrained(self.name.split("/")[-1])

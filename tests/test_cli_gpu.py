@@ -53,4 +53,4 @@ def test_train_py_pipeline(tmp_path, capsys):
     assert first[0] == "w0_0" and first[1] == "O"                       # keep_order: first sentence of the file first
     # --save_embedding on the loaded checkpoint
     main(["--config", cfg_path, "--save_embedding"])
-    assert (base / "tiny-xlmr" / "pytorch_model.bin").exists()
+    assert (base / "tiny-xlmr" / "model.safetensors").exists()       # HF layout: transformers.XLMRobertaModel.from_pretrained reads it
