@@ -153,10 +153,18 @@ int kbner_add_layernorm_fwd_res32(const float *x, const float *bias, const float
                                   void *stream);
 /* out3 [M,3F] = split(gelu_erf(x + bias)), x fp32 [M,F]: BertIntermediate's activation for the bf16x3 FFN-down GEMM. */
 int kbner_bias_gelu_split(const float *x, const float *bias, int M, int F, uint16_t *out3, void *stream);
-/* kbner_attention_fwd_dropout with an output row stride (elements) and the split layout: with split = 1 `out` is the
- * [R*S, ldo >= 3H] operand buffer of the attention-output GEMM and receives [ hi | lo | hi ]. */
+/* kbner_attention_fwd_dropout with an output row stride `ldo` (elements, shared by the three outputs) and the rounding
+ * residual: out = hi = bf16(o); out_lo (optional) = bf16(o - hi); out_hi2 (optional) = a second copy of hi.  The bf16x3
+ * mode points the three at column offsets 0 / H / 2H of the [R*S, 3H] operand of the attention-output GEMM; fine-tuning
+ * keeps out_lo next to out so that the backward takes D = rowsum(dO * (hi + lo)) (kbner_attention_bwd_ex). */
 int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads, uint16_t *out, int ldo,
-                           int split, float *lse, const uint32_t *drop_seed, uint32_t drop_site, float drop_p,
+                           uint16_t *out_lo, uint16_t *out_hi2, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
+                           float drop_p, void *stream);
+/* kbner_attention_bwd_dropout with the forward's rounding residual out_lo ([R*S,H] bf16 or NULL): dS = P * (dP - D)
+ * cancels catastrophically for near-uniform attention, so D is taken from hi + lo when it is available. */
+int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, const uint16_t *out_lo, const uint16_t *d_out,
+                           const float *lse, const int32_t *key_len, int R, int S, int heads, float *d_scratch,
+                           float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed, uint32_t drop_site, float drop_p,
                            void *stream);
 /* kbner_gather_tagproj_fwd over an fp32 hidden state (the last LayerNorm's y32). */
 int kbner_gather_tagproj_fwd_f32(const float *hidden /*[R*S,H] fp32*/, const int32_t *row_of, const int32_t *first_idx,

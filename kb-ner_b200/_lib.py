@@ -42,8 +42,9 @@ SIGNATURES = {
     "kbner_embed_ln_fwd_ex": ([_c_void_p] * 6 + [_c_float, _c_int] + [_c_int] * 5 + [_c_void_p] * 2 + [_c_int, _c_void_p], _c_int),
     "kbner_add_layernorm_fwd_res32": ([_c_void_p] * 5 + [_c_float, _c_int, _c_int] + [_c_void_p] * 2 + [_c_int, _c_void_p], _c_int),
     "kbner_bias_gelu_split": ([_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 2, _c_int),
-    "kbner_attention_fwd_ex": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p, _c_int, _c_int] + [_c_void_p] * 2 +
+    "kbner_attention_fwd_ex": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p, _c_int] + [_c_void_p] * 4 +
                                [ctypes.c_uint32, _c_float, _c_void_p], _c_int),
+    "kbner_attention_bwd_ex": ([_c_void_p] * 6 + [_c_int] * 3 + [_c_void_p] * 4 + [ctypes.c_uint32, _c_float, _c_void_p], _c_int),
     "kbner_gather_tagproj_fwd_f32": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
     "kbner_colsum_bf16": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
     "kbner_embed_ln_bwd": ([_c_void_p] * 5 + [_c_float] + [_c_int] * 4 + [_c_void_p] * 7, _c_int),

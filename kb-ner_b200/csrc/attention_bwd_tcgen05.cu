@@ -48,9 +48,13 @@ struct AttnBwdSmem {
 };
 
 // D[r][h][s] = sum_d dO[s][h*64+d] * O[s][h*64+d]     (one warp per sub-token row; lane pair = one head)
+// O_lo (optional): the forward's rounding residual bf16(o - O).  dS = P * (dP - D) subtracts two nearly equal numbers when
+// the attention is close to uniform (dP_ij ~ dO_i . mean(V) for every j): D taken from the bf16-rounded O alone is off by
+// 2^-9 |dO||O| there, which measured as 11 % relative error on the top layer's dW_q / dW_k at 24 layers, 8 x 512, against
+// autograd through the fp32 oracle (tests/test_precision_gpu.py); with O = O_hi + O_lo the residual is 2^-17.
 __global__ void __launch_bounds__(256)
-attn_bwd_prep_kernel(const uint16_t *__restrict__ O, const uint16_t *__restrict__ dO, int R, int S, int heads,
-                     float *__restrict__ D) {
+attn_bwd_prep_kernel(const uint16_t *__restrict__ O, const uint16_t *__restrict__ O_lo, const uint16_t *__restrict__ dO, int R,
+                     int S, int heads, float *__restrict__ D) {
     const int H = heads * 64;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -66,6 +70,13 @@ attn_bwd_prep_kernel(const uint16_t *__restrict__ O, const uint16_t *__restrict_
             unpack_bf16x2(a.y, x0, x1); unpack_bf16x2(b.y, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
             unpack_bf16x2(a.z, x0, x1); unpack_bf16x2(b.z, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
             unpack_bf16x2(a.w, x0, x1); unpack_bf16x2(b.w, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+            if (O_lo) {
+                const uint4 l = ld_nc_v4(O_lo + (size_t)row * H + lane * 32 + c * 8);
+                unpack_bf16x2(l.x, x0, x1); unpack_bf16x2(b.x, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+                unpack_bf16x2(l.y, x0, x1); unpack_bf16x2(b.y, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+                unpack_bf16x2(l.z, x0, x1); unpack_bf16x2(b.z, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+                unpack_bf16x2(l.w, x0, x1); unpack_bf16x2(b.w, y0, y1); acc = fmaf(x0, y0, fmaf(x1, y1, acc));
+            }
         }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -337,10 +348,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 using namespace kbner;
 
-extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
-                                           const float *lse, const int32_t *key_len, int R, int S, int heads,
-                                           float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
-                                           uint32_t drop_site, float drop_p, void *stream) {
+extern "C" int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, const uint16_t *out_lo, const uint16_t *d_out,
+                                      const float *lse, const int32_t *key_len, int R, int S, int heads,
+                                      float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
+                                      uint32_t drop_site, float drop_p, void *stream) {
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_bwd: dropout probability %f", (double)drop_p);
     KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * 512 * 256 < (1ull << 32),
                     "attention_bwd: R*heads exceeds the 32-bit dropout counter");
@@ -356,7 +367,7 @@ extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *
         set_error("attention_bwd: memset: %s", cudaGetErrorString(e));
         return KBNER_ECUDA;
     }
-    attn_bwd_prep_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, d_out, R, S, heads, d_scratch);
+    attn_bwd_prep_kernel<<<(M + 7) / 8, 256, 0, st>>>(out, out_lo, d_out, R, S, heads, d_scratch);
     KBNER_CHECK_LAUNCH("attn_bwd_prep");
     CUtensorMap tmQKV, tmDO;
     int rc = make_tmap_bf16_2d(&tmQKV, qkv, (uint64_t)M, (uint64_t)3 * H, (uint64_t)3 * H, 128, 64);
@@ -385,6 +396,14 @@ extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *
     attn_bwd_dq_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq_acc, M, H, dqkv);
     KBNER_CHECK_LAUNCH("attn_bwd_dq");
     return KBNER_OK;
+}
+
+extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
+                                           const float *lse, const int32_t *key_len, int R, int S, int heads,
+                                           float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
+                                           uint32_t drop_site, float drop_p, void *stream) {
+    return kbner_attention_bwd_ex(qkv, out, nullptr, d_out, lse, key_len, R, S, heads, d_scratch, dq_acc, dqkv, drop_seed, drop_site,
+                                  drop_p, stream);
 }
 
 extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,

@@ -96,7 +96,8 @@ template <bool DROP>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const int32_t *__restrict__ key_len, int R, int S, int H, int heads, uint16_t *__restrict__ out,
-                     int ldo, int split, float *__restrict__ lse_out, const Dropout drop) {
+                     int ldo, uint16_t *__restrict__ out_lo, uint16_t *__restrict__ out_hi2, float *__restrict__ lse_out,
+                     const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     AttnSmem &s = *reinterpret_cast<AttnSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,7 +305,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // SWIZZLE_128B pattern P uses (conflict-free) -- and read it back transposed: 8 lanes per row, 4 rows per store
         // instruction = 16 fully written sectors per request.  Only this quarter's rows of the buffer are touched and
         // the next P write to it sits behind the row-max pair barrier of the next key block.
-        auto stage_store = [&](uint8_t *stage, const uint32_t (&pk)[16], uint16_t *gbase, int qrow0, bool again, int again_off) {
+        auto stage_store = [&](uint8_t *stage, const uint32_t (&pk)[16], uint16_t *gbase, int qrow0, uint16_t *gbase2) {
             uint8_t *srow = stage + row * 128;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -317,9 +318,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const int chunk = lane & 7;
                 const uint4 v = *reinterpret_cast<const uint4 *>(stage + rq * 128 + ((chunk ^ (rq & 7)) << 4));
                 if (qrow0 + rq < S) {
-                    uint16_t *gp = gbase + (size_t)rq * ldo + chunk * 8;
-                    *reinterpret_cast<uint4 *>(gp) = v;
-                    if (again) *reinterpret_cast<uint4 *>(gp + again_off) = v;
+                    const size_t go = (size_t)rq * ldo + chunk * 8;
+                    *reinterpret_cast<uint4 *>(gbase + go) = v;
+                    if (gbase2) *reinterpret_cast<uint4 *>(gbase2 + go) = v;
                 }
             }
         };
@@ -352,10 +353,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(o_acc[2 * i], o_acc[2 * i + 1]);
-            uint16_t *gbase = out + (size_t)(row0 + qrow0) * ldo + h * kAttnD;
-            // split (the "bf16x3" precise mode): out row = [ hi | lo | hi ], each H wide, hi + lo = the fp32 value to 2^-17
-            stage_store(stage, pk, gbase, qrow0, split != 0, 2 * H);
-            if (split) {
+            const size_t gofs = (size_t)(row0 + qrow0) * ldo + h * kAttnD;
+            // out_lo: the rounding residual lo = bf16(o - hi), hi + lo = the fp32 value to 2^-17 (the "bf16x3" operand pair of
+            // the attention-output GEMM, and what the backward's D = rowsum(dO * O) is taken from); out_hi2: a second copy of
+            // hi (the K-concatenated operand row is [ hi | lo | hi ])
+            stage_store(stage, pk, out + gofs, qrow0, out_hi2 ? out_hi2 + gofs : nullptr);
+            if (out_lo) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float h0, h1;
@@ -363,7 +366,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     pk[i] = pack_bf16x2(o_acc[2 * i] - h0, o_acc[2 * i + 1] - h1);
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");     // the partner has read the hi tile back
-                stage_store(stage, pk, gbase + H, qrow0, false, 0);
+                stage_store(stage, pk, out_lo + gofs, qrow0, nullptr);
             }
             if (qrow < S && lse_out && half == 0)   // natural-log LSE of the scaled scores (for the backward pass)
                 lse_out[((size_t)r * heads + h) * S + qrow] =
@@ -503,11 +506,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 using namespace kbner;
 
 extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
-                                      uint16_t *out, int ldo, int split, float *lse, const uint32_t *drop_seed,
-                                      uint32_t drop_site, float drop_p, void *stream) {
+                                      uint16_t *out, int ldo, uint16_t *out_lo, uint16_t *out_hi2, float *lse,
+                                      const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream) {
     KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
-    KBNER_CHECK_ARG(ldo >= heads * kAttnD * (split ? 3 : 1) && ldo % 8 == 0 && ((uintptr_t)out & 15u) == 0,
-                    "attention_fwd: output row stride %d (split=%d) / alignment", ldo, split);
+    KBNER_CHECK_ARG(ldo >= heads * kAttnD && ldo % 8 == 0 && (((uintptr_t)out | (uintptr_t)out_lo | (uintptr_t)out_hi2) & 15u) == 0,
+                    "attention_fwd: output row stride %d / 16-byte alignment of out, out_lo, out_hi2", ldo);
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_fwd: dropout probability %f", (double)drop_p);
     KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * kMaxS * (kMaxS / 2) < (1ull << 32),
                     "attention_fwd: R*heads exceeds the 32-bit dropout counter");
@@ -541,10 +544,10 @@ extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_le
     cudaError_t le;
     if (drop.thresh)
         le = launch_kernel(attention_fwd_kernel<true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, R, S, H, heads, out, ldo, split, lse, drop);
+                           key_len, R, S, H, heads, out, ldo, out_lo, out_hi2, lse, drop);
     else
         le = launch_kernel(attention_fwd_kernel<false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
-                           key_len, R, S, H, heads, out, ldo, split, lse, drop);
+                           key_len, R, S, H, heads, out, ldo, out_lo, out_hi2, lse, drop);
     if (le != cudaSuccess) {
         set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
         return KBNER_ECUDA;
@@ -562,10 +565,11 @@ extern "C" int kbner_attention_debug_read(unsigned long long *host, int n) {
 extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                            uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
                                            float drop_p, void *stream) {
-    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, 0, lse, drop_seed, drop_site, drop_p, stream);
+    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, nullptr, nullptr, lse, drop_seed, drop_site, drop_p,
+                                  stream);
 }
 
 extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                    uint16_t *out, float *lse, void *stream) {
-    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, 0, lse, nullptr, 0u, 0.0f, stream);
+    return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, nullptr, nullptr, lse, nullptr, 0u, 0.0f, stream);
 }

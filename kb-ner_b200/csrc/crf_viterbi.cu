@@ -28,6 +28,7 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <utility>
 
 #include "crf_common.cuh"
@@ -38,7 +39,7 @@ namespace {
 
 constexpr float kNegV = -1e12f;   // the reference's sentinel (sequence_tagger_model.py:402-410,1252)
 constexpr int kVitChunk = 16;     // steps per ring stage
-constexpr int kVitStages = 3;
+constexpr int kVitStages = 2;    // chunk c+1 lands while chunk c (16 steps x ~200 cycles) is consumed: one stage ahead is enough
 
 // First index k with cc[k] == m, pre-shifted by SH: a descending chain of "if (cc[k] == m) idx = k << SH".  The move is
 // written as a predicated IMAD (z is an opaque zero) so that it issues on the FMA pipe: FSETP + SEL + FMNMX3 all sit on
@@ -57,7 +58,7 @@ struct VitCfg {
     static constexpr int SPW = 32 / Q;                 // sentences per warp
     static constexpr int BITS = (K <= 16) ? 4 : 8;     // bits per back-pointer
     static constexpr int SPWD = 32 / (JL * BITS);      // steps per back-pointer word
-    static constexpr int FP = (Q < 16) ? Q : 16;       // steps per confidence flush (= unrolled steps)
+    static constexpr int FP = (Q < 8) ? Q : 8;         // steps per confidence flush (= unrolled steps)
     static constexpr int KP = (K + 3) / 4 * 4;         // staging row stride (16-byte rows)
     static_assert(Q * JL >= K && JL <= 2, "every tag needs an owner; a lane stores its JL states with one STS");
     static_assert(kVitChunk % FP == 0 && FP % SPWD == 0, "flush period must tile the chunk and the back-pointer words");
@@ -76,9 +77,15 @@ struct VitCfg {
     static __host__ __device__ size_t bp_bytes(int T) { return (size_t)SPW * bp_stride(T); }
     static __host__ __device__ size_t stg_bytes() { return (size_t)SPW * stg_stride(); }
     static __host__ __device__ size_t path_bytes(int T) { return (size_t)SPW * tpad(T); }
-    static __host__ __device__ size_t smem_bytes(int T, int L) {
-        return ring_bytes(L) + bp_bytes(T) + stg_bytes() + path_bytes(T) + 32 * K + 64;
+    // The decoded path and the back-trace maps reuse the emission ring (dead once the recurrence is over): what a block
+    // keeps resident decides how many blocks share an SM, and 4096 x 512 x 13 must fit in ONE wave (2048 blocks over 148
+    // SMs = 13.8 per SM; the first layout needed 19.6 KB per block = 11 per SM = 1.26 waves, profiles/r01/crf_ncu_r43.txt).
+    static __host__ __device__ size_t tail_bytes(int T) { return path_bytes(T) + 32 * K; }
+    static __host__ __device__ size_t ring_region(int T, int L) {
+        const size_t r = ring_bytes(L), t = tail_bytes(T);
+        return (r > t ? r : t) + 15 & ~(size_t)15;
     }
+    static __host__ __device__ size_t smem_bytes(int T, int L) { return ring_region(T, L) + bp_bytes(T) + stg_bytes() + 64; }
 };
 
 template <int Q, int JL, int K>
@@ -91,11 +98,11 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
     constexpr int SPW = C::SPW, BITS = C::BITS, SPWD = C::SPWD, FP = C::FP, KP = C::KP, CH = kVitChunk, NST = kVitStages;
     extern __shared__ __align__(16) uint8_t smem[];
     float *ring = reinterpret_cast<float *>(smem);
-    uint32_t *bp_all = reinterpret_cast<uint32_t *>(smem + C::ring_bytes(L));
-    float *stg_all = reinterpret_cast<float *>(smem + C::ring_bytes(L) + C::bp_bytes(T));
-    uint8_t *path_all = smem + C::ring_bytes(L) + C::bp_bytes(T) + C::stg_bytes();
+    uint32_t *bp_all = reinterpret_cast<uint32_t *>(smem + C::ring_region(T, L));
+    float *stg_all = reinterpret_cast<float *>(smem + C::ring_region(T, L) + C::bp_bytes(T));
+    uint8_t *path_all = smem;                                         // aliases the ring: used after the recurrence only
     uint8_t *maps_all = path_all + C::path_bytes(T);                  // 32 lanes x K bytes
-    int *s_ctl = reinterpret_cast<int *>(maps_all + 32 * K);          // [0] = nmax, [1..SPW] = klen per sentence
+    int *s_ctl = reinterpret_cast<int *>(smem + C::ring_region(T, L) + C::bp_bytes(T) + C::stg_bytes());   // [0] = nmax, [1..SPW] = klen
 
     const int lane = threadIdx.x;
     const int sub = lane / Q, q = lane % Q;
@@ -275,6 +282,7 @@ crf_viterbi_kernel(const float *__restrict__ emis, const int32_t *__restrict__ p
     }
     conf_flush(prev_s, nchunks * CH - FP);
     cp_async_wait<0>();
+    __syncwarp();              // the ring is dead from here on: path / maps reuse it
 
     // terminal (:1279-1287): first max of v + A[STOP], with STOP / START forced to -1e12
     float term = -CUDART_INF_F;
@@ -356,15 +364,16 @@ int launch_viterbi(const float *emis, const int32_t *pos, const int32_t *klen, c
         set_error("crf_viterbi: T=%d too long for the shared-memory back-pointer table", T);
         return KBNER_EUNSUPPORTED;
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(crf_viterbi_kernel<Q, JL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(200 * 1024));
-        if (e != cudaSuccess) {
-            set_error("crf_viterbi: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return KBNER_ECUDA;
-        }
-        configured = true;
+    static std::once_flag once;
+    static cudaError_t cfg_err = cudaSuccess;
+    std::call_once(once, [] {
+        cfg_err = cudaFuncSetAttribute(crf_viterbi_kernel<Q, JL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        if (cfg_err == cudaSuccess)      // all of the SM's shared memory to the blocks: residency is what bounds this kernel
+            cfg_err = cudaFuncSetAttribute(crf_viterbi_kernel<Q, JL, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    });
+    if (cfg_err != cudaSuccess) {
+        set_error("crf_viterbi: cudaFuncSetAttribute: %s", cudaGetErrorString(cfg_err));
+        return KBNER_ECUDA;
     }
     // 16-byte copies need: no index list, 16-byte aligned rows (T*L % 4 == 0) and base pointer
     const int vec16 = (pos == nullptr && ((size_t)T * L) % 4 == 0 && (reinterpret_cast<uintptr_t>(emis) & 15) == 0) ? 1 : 0;

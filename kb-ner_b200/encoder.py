@@ -129,6 +129,8 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         self._tgraph_cap = max(1, int(os.environ.get("KBNER_TRAIN_GRAPH_CACHE", "3")))
         self._use_graphs = os.environ.get("KBNER_GRAPHS", "1") != "0"
         self._fuse_ln = os.environ.get("KBNER_FUSE_LN", "1") != "0"
+        # fine-tuning keeps the attention output's rounding residual for the backward's D = rowsum(dO * O) (ops.attention_bwd)
+        self._ctx_residual = os.environ.get("KBNER_CTX_RESIDUAL", "1") != "0"
         self.precision = os.environ.get("KBNER_PRECISION", "bf16")
         if self.precision not in PRECISIONS:
             raise ValueError("KBNER_PRECISION must be one of %s" % (PRECISIONS,))
@@ -150,6 +152,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         self.__dict__.setdefault("precision", "bf16")
         self.__dict__.setdefault("_graph_cap", 8)
         self.__dict__.setdefault("_tgraph_cap", 3)
+        self.__dict__.setdefault("_ctx_residual", True)
         # parameters arrive as views of the saved arena storage: give each its own storage again
         for p in self.parameters():
             p.data = p.data.clone()
@@ -531,7 +534,8 @@ def _forward_train_eager(self, ids, key_len):
     for li, w in enumerate(self._compute):
         d_attn, d_h1, d_h2 = _dropout_sites(self, li)
         qkv = ops.gemm_bf16(x, w["wqkv"], M, 3 * H, H, ops.EPI_BIAS, bias=w["bqkv"])
-        ctx, lse = ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, want_lse=True, drop=d_attn)
+        ctx_lo = torch.empty((M, H), dtype=bf, device=dev) if self._ctx_residual else None
+        ctx, lse = ops.attention_fwd(qkv, key_len, R, S, c.num_attention_heads, want_lse=True, drop=d_attn, out_lo=ctx_lo)
         y1 = ops.gemm_bf16(ctx, w["wo"], M, H, H, ops.EPI_NONE_F32)
         x1, mean1, rstd1 = ops.layernorm_fwd(y1, w["g1"], w["b1"], c.layer_norm_eps, save_stats=True, bias=w["bo"], resid=x,
                                              drop=d_h1)
@@ -540,7 +544,7 @@ def _forward_train_eager(self, ids, key_len):
         y2 = ops.gemm_bf16(h, w["w2"], M, H, F, ops.EPI_NONE_F32)
         xo, mean2, rstd2 = ops.layernorm_fwd(y2, w["g2"], w["bb2"], c.layer_norm_eps, save_stats=True, bias=w["b2"], resid=x1,
                                              drop=d_h2)
-        saved["layers"].append((x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2))
+        saved["layers"].append((x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2, ctx_lo))
         x = xo
     return x, saved
 
@@ -621,7 +625,7 @@ def _backward_layers(self, saved, dout, dres, li_hi, li_lo, ws):
         lyr, w = self.encoder.layer[li], self._compute[li]
         a = lyr.attention
         d_attn, d_h1, d_h2 = _dropout_sites(self, li) if saved.get("dropout") else (None, None, None)
-        x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2 = saved["layers"][li]
+        x, qkv, lse, ctx, y1, mean1, rstd1, x1, hpre, h, y2, mean2, rstd2, ctx_lo = saved["layers"][li]
         # ---- FFN block ------------------------------------------------------------------------------
         dz2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad,
                                 dxsum=lyr.output.dense.bias.grad, bias=w["b2"], resid=x1, dres=dres, drop=d_h2)
@@ -637,7 +641,7 @@ def _backward_layers(self, saved, dout, dres, li_hi, li_lo, ws):
         dz1, dy1 = dz1 if isinstance(dz1, tuple) else (dz1, dz1)
         ops.gemm_bf16(dy1, ctx, H, H, M, ops.EPI_ACCUM_F32, out=a.output.dense.weight.grad, a_mn=True, b_mn=True)
         dctx = ops.gemm_bf16(dy1, w["wo"], M, H, H, ops.EPI_BIAS, b_mn=True)
-        dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws, drop=d_attn)
+        dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws, drop=d_attn, out_lo=ctx_lo)
         ops.colsum_bf16(dqkv, ar.view(a.self.query.bias, (3 * H,), grad=True))
         ops.gemm_bf16(dqkv, x, 3 * H, H, M, ops.EPI_ACCUM_F32, out=ar.view(a.self.query.weight, (3 * H, H), grad=True),
                       a_mn=True, b_mn=True)

@@ -248,8 +248,9 @@ def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None):
     return out
 
 
-def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None, split=False):
-    """out [R*S,H] bf16; split=True: out is the [R*S,3H] operand of the attention-output GEMM, rows hi|lo|hi."""
+def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None, split=False, out_lo=None):
+    """out [R*S,H] bf16; split=True: out is the [R*S,3H] operand of the attention-output GEMM, rows hi|lo|hi;
+    out_lo (optional [R*S,H] bf16, not with split): receives the rounding residual bf16(o - out)."""
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(key_len, torch.int32, "key_len", 1)
     H = heads * 64
@@ -264,7 +265,16 @@ def attention_fwd(qkv, key_len, R, S, heads, out=None, want_lse=False, drop=None
             raise _lib.KbnerError("attention: out must be [%d, %d]" % (R * S, width))
     lse = torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device) if want_lse else None
     sp, site, p = _drop_args(drop)
-    _lib.check(_lib.load().kbner_attention_fwd_ex(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), width, int(bool(split)),
+    _chk(out_lo, torch.bfloat16, "out_lo", 2)
+    if split:
+        if out_lo is not None:
+            raise _lib.KbnerError("attention: split already writes the residual")
+        lo_p, hi2_p = out.data_ptr() + 2 * H, out.data_ptr() + 4 * H
+    else:
+        if out_lo is not None and tuple(out_lo.shape) != (R * S, H):
+            raise _lib.KbnerError("attention: out_lo must be [%d, %d]" % (R * S, H))
+        lo_p, hi2_p = _ptr(out_lo), 0
+    _lib.check(_lib.load().kbner_attention_fwd_ex(_ptr(qkv), _ptr(key_len), R, S, heads, _ptr(out), width, lo_p, hi2_p,
                                                   _ptr(lse), sp, site, p, _stream()), "attention_fwd")
     return (out, lse) if want_lse else out
 
@@ -407,8 +417,10 @@ def gemm_bf16(A, B, M, N, K, epilogue, bias=None, aux=None, aux_out=None, out=No
     return out
 
 
-def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None, drop=None):
-    """dQ | dK | dV ([R*S, 3H] bf16) of attention_fwd.  workspace = (d_scratch [R,heads,S] f32, dq_acc [R*S,H] f32)."""
+def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None, drop=None, out_lo=None):
+    """dQ | dK | dV ([R*S, 3H] bf16) of attention_fwd.  workspace = (d_scratch [R,heads,S] f32, dq_acc [R*S,H] f32).
+    out_lo: the forward's rounding residual (attention_fwd(out_lo=...)); D = rowsum(dO * (out + out_lo)) when given."""
+    _chk(out_lo, torch.bfloat16, "out_lo", 2)
     _chk(qkv, torch.bfloat16, "qkv", 2)
     _chk(out, torch.bfloat16, "out", 2)
     _chk(d_out, torch.bfloat16, "d_out", 2)
@@ -421,7 +433,7 @@ def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspa
         workspace = (torch.empty((R, heads, S), dtype=torch.float32, device=qkv.device),
                      torch.empty((R * S, H), dtype=torch.float32, device=qkv.device))
     sp, site, p = _drop_args(drop)
-    _lib.check(_lib.load().kbner_attention_bwd_dropout(_ptr(qkv), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(key_len), R, S, heads,
-                                                       _ptr(workspace[0]), _ptr(workspace[1]), _ptr(dqkv), sp, site, p,
-                                                       _stream()), "attention_bwd")
+    _lib.check(_lib.load().kbner_attention_bwd_ex(_ptr(qkv), _ptr(out), _ptr(out_lo), _ptr(d_out), _ptr(lse), _ptr(key_len), R, S,
+                                                  heads, _ptr(workspace[0]), _ptr(workspace[1]), _ptr(dqkv), sp, site, p,
+                                                  _stream()), "attention_bwd")
     return dqkv

@@ -4,10 +4,10 @@ north_star: "logits and CRF loss within 1e-3 relative in bf16" against the refer
 module called at /root/reference/flair/embeddings.py:3269 + sequence_tagger_model.py:1027, :2499-2506).  What is asserted:
 
   precision "bf16x3"      logits rel-L2 <= 1e-3, CRF loss rel err <= 1e-3          -- the tolerance north_star states
-  precision "bf16-res32"  hidden rel-L2 <= 9e-3 and below the plain bf16 figure     (fp32 residual stream only)
+  precision "bf16-res32"  hidden rel-L2 <= 1e-2 and >= 10 % below the plain bf16 figure (fp32 residual stream only)
   precision "bf16"        hidden rel-L2 <= 1.3e-2 vs fp32 (the number FORMAT: bf16 weights alone cost 6.4e-3,
-                          scripts/bf16_ablation.py) and <= 2.5e-3 vs the bf16-rounding-point restatement of the same
-                          arithmetic (oracle.encoder_forward_bf16_points): the kernels sit ON the format's floor
+                          scripts/bf16_ablation.py) and no further from fp32 than the bf16-rounding-point restatement of
+                          the same arithmetic (oracle.encoder_forward_bf16_points): the kernels sit ON the format's floor
 plus Viterbi tag agreement with the fp32 path in every mode, the kernels the modes add, and the backward pass at
 BASELINE configs[2] shape (24 layers, 8 x 512) against autograd through the fp32 oracle.
 """
@@ -56,27 +56,35 @@ def _rel(a, b):
 
 
 def test_kernels_sit_on_the_bf16_rounding_floor():
-    """24 layers: kernels vs the torch restatement with a bf16 rounding at exactly the kernels' store points."""
+    """Kernels vs the torch restatement that rounds to bf16 at exactly the kernels' store points
+    (oracle.encoder_forward_bf16_points).  ONE layer: the two agree tightly -- same arithmetic, different summation order.
+    24 layers: two bf16 evaluations of the same function decorrelate (a value that rounds the other way moves by one bf16
+    ulp = 4e-3 relative, and 96 GEMMs amplify that), so the meaningful statement is that both sit at the SAME distance from
+    fp32: the kernels add nothing measurable on top of the number format."""
     import encoder_oracle as E
-    tagger, emb, params, ocfg = _large()
-    batch = _batch(1, 1)
-    ids, key_len, row_of, first_idx, lengths, S = emb.build_batch(batch)
-    dp = {k: v.cuda() for k, v in params.items()}
-    with torch.no_grad():
-        hid = emb.model.forward_hidden(ids.cuda(), key_len.cuda()).float().view(2, S, -1).clone()
-        emu = E.encoder_forward_bf16_points(dp, ids.long().cuda(), key_len.long().cuda(), ocfg)
-        ref = E.encoder_forward(dp, ids.long().cuda(), key_len.long().cuda(), ocfg)
+    from test_api_gpu import _models
     out = {}
-    for b in range(2):
-        n = int(key_len[b])
-        out[b] = (_rel(hid[b, :n], emu[b, :n]), _rel(hid[b, :n], ref[b, :n]), _rel(emu[b, :n], ref[b, :n]))
-    print("24 layers (kernels vs bf16-point restatement, kernels vs fp32, restatement vs fp32):", out)
-    for k_emu, k_ref, emu_ref in out.values():
-        # two independent bf16 evaluations of the same 24-layer function differ by rounding-boundary flips (a value that
-        # rounds the other way moves by one bf16 ulp = 4e-3 relative): far below either one's distance to fp32
-        assert k_emu < 4e-3, out
-        assert k_ref < 1.3e-2 and emu_ref < 1.3e-2, out
-        assert k_ref < 1.25 * emu_ref, out        # the kernels add nothing measurable on top of the format
+    for layers in (1, 24):
+        kw = dict(LARGE, vocab_size=5000, num_hidden_layers=layers)
+        tagger, emb, params, ocfg = _models(kw, 13, seed=11)
+        batch = _batch(1, 1)
+        ids, key_len, row_of, first_idx, lengths, S = emb.build_batch(batch)
+        dp = {k: v.cuda() for k, v in params.items()}
+        with torch.no_grad():
+            hid = emb.model.forward_hidden(ids.cuda(), key_len.cuda()).float().view(2, S, -1).clone()
+            emu = E.encoder_forward_bf16_points(dp, ids.long().cuda(), key_len.long().cuda(), ocfg)
+            ref = E.encoder_forward(dp, ids.long().cuda(), key_len.long().cuda(), ocfg)
+        n0, n1 = int(key_len[0]), int(key_len[1])
+        cat = lambda t: torch.cat([t[0, :n0], t[1, :n1]])
+        out[layers] = dict(kernels_vs_restatement=_rel(cat(hid), cat(emu)), kernels_vs_fp32=_rel(cat(hid), cat(ref)),
+                           restatement_vs_fp32=_rel(cat(emu), cat(ref)))
+        del tagger, emb, dp
+    print("kernels / bf16-point restatement / fp32 oracle:", out)
+    one, deep = out[1], out[24]
+    assert one["kernels_vs_restatement"] < 1.5e-3 and one["kernels_vs_fp32"] < 4e-3, out
+    assert one["kernels_vs_restatement"] < 0.6 * one["kernels_vs_fp32"], out        # closer to its restatement than to fp32
+    assert deep["kernels_vs_fp32"] < 1.3e-2 and deep["restatement_vs_fp32"] < 1.3e-2, out
+    assert deep["kernels_vs_fp32"] < 1.1 * deep["restatement_vs_fp32"], out         # the kernels sit on the format's floor
 
 
 def test_precision_modes_meet_the_stated_tolerances():
@@ -127,7 +135,7 @@ def test_precision_modes_meet_the_stated_tolerances():
     x3, r32, fast = res["bf16x3"], res["bf16-res32"], res["bf16"]
     assert x3["logits"] <= NORTH_STAR_TOL and x3["loss_rel"] <= NORTH_STAR_TOL and x3["hidden"] <= NORTH_STAR_TOL, res
     assert x3["tag_agreement"] >= 0.995, res
-    assert r32["hidden"] <= 9e-3 and r32["hidden"] < fast["hidden"], res
+    assert r32["hidden"] <= 1.0e-2 and r32["hidden"] < 0.9 * fast["hidden"], res
     assert fast["hidden"] <= 1.3e-2 and fast["logits"] <= 2e-2 and fast["loss_rel"] <= 5e-3, res
     assert fast["tag_agreement"] >= 0.95 and r32["tag_agreement"] >= 0.95, res
 
@@ -239,7 +247,8 @@ def test_arena_optimizer_kernels():
 
 def test_backward_parity_at_configs2_shape():
     """BASELINE configs[2]: 24 layers, 8 x 512 sub-tokens.  loss.backward() through the hand-written backward (split-K wgrad
-    at M = 4096 included) against torch autograd through the fp32 oracle, fed with the same d(loss)/d(logits)."""
+    at M = 4096 included) against torch autograd through the fp32 oracle, fed with the same d(loss)/d(logits).  Run twice:
+    with and without the attention output's rounding residual in the backward's D = rowsum(dO * O)."""
     import encoder_oracle as E
     from kbner_b200.data import BatchedData, Sentence
     tagger, emb, params, ocfg = _large(seed=21, small_vocab=False)
@@ -258,39 +267,50 @@ def test_backward_parity_at_configs2_shape():
     batch = BatchedData(sents)
     enc = emb.model
     enc.ensure_arena()
-    enc.arena.zero_grad()
-    feats = tagger.forward(batch)
-    feats.retain_grad()
-    loss = tagger._calculate_loss(feats, batch, tagger.mask)
-    loss.backward()
-    d_logits = feats.grad.detach().clone()
     ids, key_len, row_of, first_idx, lengths, S = emb.build_batch(batch)
     assert tuple(ids.shape) == (8, 512)
-    op = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
-    hidden = E.encoder_forward(op, ids.long().cuda(), key_len.long().cuda(), ocfg)
-    flat = hidden.reshape(-1, hidden.shape[-1])
-    idx = row_of.long()[:, None] * S + first_idx.long().clamp(min=0)
-    x = flat[idx.cuda()] * (first_idx >= 0).float().cuda()[..., None]
-    W = tagger.linear.weight.detach().clone()
-    (x @ W.t()).backward(d_logits)
     own = dict(enc.named_parameters())
-    rel, tiny = {}, []
-    for name, ref in op.items():
-        if ref.grad is None:
-            continue
-        denom = ref.grad.norm().item()
-        got = own[name].grad
-        if denom < 1e-7 * max(1.0, ref.numel() ** 0.5):
-            tiny.append(name)                      # e.g. key biases: the exact gradient is 0 (softmax is shift-invariant)
-            continue
-        rel[name] = ((got - ref.grad).norm() / denom).item()
-    vals = sorted(rel.values())
-    worst = sorted(rel.items(), key=lambda kv: -kv[1])[:3]
-    print("configs[2] backward: %d tensors, rel-L2 median %.3e, p90 %.3e, max %.3e; worst %s; %d zero-gradient tensors skipped"
-          % (len(vals), vals[len(vals) // 2], vals[int(len(vals) * 0.9)], vals[-1], worst, len(tiny)))
-    # bf16 operands through 24 layers forward AND backward: the bound is the measured format cost with headroom, written
-    # next to north_star's 1e-3 (which is stated for logits / loss, not for gradients)
-    assert vals[-1] < 8e-2 and vals[len(vals) // 2] < 4e-2, worst
+    report = {}
+    op = None
+    for residual in (False, True):
+        enc._ctx_residual = residual
+        enc.arena.zero_grad()
+        batch.features = {}
+        feats = tagger.forward(batch)
+        feats.retain_grad()
+        loss = tagger._calculate_loss(feats, batch, tagger.mask)
+        loss.backward()
+        if op is None:                     # the oracle's gradients, once (identical d_logits both times: same forward)
+            d_logits = feats.grad.detach().clone()
+            op = {k: v.cuda().clone().requires_grad_(True) for k, v in params.items()}
+            hidden = E.encoder_forward(op, ids.long().cuda(), key_len.long().cuda(), ocfg)
+            flat = hidden.reshape(-1, hidden.shape[-1])
+            idx = row_of.long()[:, None] * S + first_idx.long().clamp(min=0)
+            x = flat[idx.cuda()] * (first_idx >= 0).float().cuda()[..., None]
+            (x @ tagger.linear.weight.detach().t()).backward(d_logits)
+            del hidden, flat, x
+        rel, tiny, num, den = {}, [], 0.0, 0.0
+        for name, ref in op.items():
+            if ref.grad is None:
+                continue
+            denom = ref.grad.norm().item()
+            got = own[name].grad
+            num += float(((got - ref.grad) ** 2).sum())
+            den += denom ** 2
+            if denom < 1e-7 * max(1.0, ref.numel() ** 0.5):
+                tiny.append(name)                  # e.g. key biases: the exact gradient is 0 (softmax is shift-invariant)
+                continue
+            rel[name] = ((got - ref.grad).norm() / denom).item()
+        vals = sorted(rel.values())
+        report[residual] = dict(n=len(vals), median=vals[len(vals) // 2], p90=vals[int(len(vals) * 0.9)], max=vals[-1],
+                                whole_gradient=(num / den) ** 0.5, worst=sorted(rel.items(), key=lambda kv: -kv[1])[:3],
+                                zero_gradient_tensors=len(tiny))
+    print("configs[2] backward vs fp32 autograd, per-tensor rel-L2 {without / with the attention-output residual in D}:", report)
+    r = report[True]
+    # bf16 operands through 24 layers forward AND backward: bounds = the measured format cost with headroom, written next
+    # to north_star's 1e-3 (which is stated for logits / loss, not for gradients)
+    assert r["whole_gradient"] < 2e-2 and r["median"] < 2e-2 and r["p90"] < 3e-2 and r["max"] < 6e-2, report
+    assert r["max"] <= report[False]["max"] * 1.05, report
 
 
 def test_hf_saved_model_hidden_states_match_transformers(tmp_path):
