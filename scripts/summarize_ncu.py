@@ -27,6 +27,21 @@ def main(path):
             if k in hdr:
                 i = hdr.index(k)
                 print("   %-90s %s %s" % (k, r[i], units[i]))
+        # pipe utilisation and the warp-stall breakdown (what an issue-bound kernel is waiting for)
+        for i, k in enumerate(hdr):
+            if k in KEYS:
+                continue
+            if ("inst_executed_pipe_" in k and k.endswith("pct_of_peak_sustained_active")) or \
+                    ("issue_stalled" in k and k.endswith("per_warp_active.pct")) or k in (
+                        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+                        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active",
+                        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "sm__maximum_warps_per_active_cycle_pct"):
+                try:
+                    if float(r[i].replace(",", "")) == 0.0:
+                        continue
+                except ValueError:
+                    pass
+                print("   %-90s %s %s" % (k, r[i], units[i]))
 
 
 if __name__ == "__main__":
