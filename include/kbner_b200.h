@@ -45,6 +45,10 @@ int kbner_device_check(int dev);
 uint64_t kbner_launch_count(void);
 /* Account for kernels launched through a replayed CUDA graph (the host captured them once). */
 void kbner_add_launches(uint64_t n);
+/* SMs the persistent tensor-core grids (GEMM CTA pairs, attention forward) size themselves for; 0 = all of the device.
+ * Data-parallel fine-tuning lowers it around the backward pass that overlaps the NCCL gradient exchange, so that NCCL's
+ * channel CTAs get SMs of their own instead of displacing a persistent grid's CTAs into a second wave. */
+int kbner_set_sm_budget(int n_sms);
 
 /* ---- CRF ---------------------------------------------------------------------------- */
 /* remove-X compaction: pos[b][i] = original index of the i-th kept token, klen[b] = #kept,

@@ -18,6 +18,7 @@ SIGNATURES = {
     "kbner_device_check": ([_c_int], _c_int),
     "kbner_launch_count": ([], ctypes.c_uint64),
     "kbner_add_launches": ([ctypes.c_uint64], None),
+    "kbner_set_sm_budget": ([_c_int], _c_int),
     "kbner_crf_compact": ([_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "kbner_crf_viterbi": ([_c_void_p] * 5 + [_c_int] * 6 + [_c_void_p] * 3, _c_int),
     "kbner_crf_nll_fwd": ([_c_void_p] * 5 + [_c_int] * 5 + [_c_void_p] * 5, _c_int),

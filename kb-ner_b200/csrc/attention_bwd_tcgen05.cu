@@ -352,6 +352,7 @@ extern "C" int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, 
                                       const float *lse, const int32_t *key_len, int R, int S, int heads,
                                       float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
                                       uint32_t drop_site, float drop_p, void *stream) {
+    KBNER_NVTX("kbner/attention_bwd");
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "attention_bwd: dropout probability %f", (double)drop_p);
     KBNER_CHECK_ARG(!(drop_seed && drop_p > 0.0f) || (uint64_t)R * heads * 512 * 256 < (1ull << 32),
                     "attention_bwd: R*heads exceeds the 32-bit dropout counter");
@@ -402,6 +403,7 @@ extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *
                                            const float *lse, const int32_t *key_len, int R, int S, int heads,
                                            float *d_scratch, float *dq_acc, uint16_t *dqkv, const uint32_t *drop_seed,
                                            uint32_t drop_site, float drop_p, void *stream) {
+    KBNER_NVTX("kbner/attention_bwd");
     return kbner_attention_bwd_ex(qkv, out, nullptr, d_out, lse, key_len, R, S, heads, d_scratch, dq_acc, dqkv, drop_seed, drop_site,
                                   drop_p, stream);
 }
@@ -409,6 +411,7 @@ extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *
 extern "C" int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
                                    const float *lse, const int32_t *key_len, int R, int S, int heads,
                                    float *d_scratch, float *dq_acc, uint16_t *dqkv, void *stream) {
+    KBNER_NVTX("kbner/attention_bwd");
     return kbner_attention_bwd_dropout(qkv, out, d_out, lse, key_len, R, S, heads, d_scratch, dq_acc, dqkv, nullptr, 0u, 0.0f,
                                        stream);
 }

@@ -508,6 +508,7 @@ using namespace kbner;
 extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                       uint16_t *out, int ldo, uint16_t *out_lo, uint16_t *out_hi2, float *lse,
                                       const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream) {
+    KBNER_NVTX("kbner/attention");
     KBNER_CHECK_ARG(qkv && key_len && out, "attention_fwd: null pointer");
     KBNER_CHECK_ARG(ldo >= heads * kAttnD && ldo % 8 == 0 && (((uintptr_t)out | (uintptr_t)out_lo | (uintptr_t)out_hi2) & 15u) == 0,
                     "attention_fwd: output row stride %d / 16-byte alignment of out, out_lo, out_hi2", ldo);
@@ -540,7 +541,8 @@ extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_le
     // for the last P.V, the read-out, teardown and the next launch) -- measured with clock64 stamps, see profiles/README.md.
     const long long total = (long long)R * heads * ((S + kBQ - 1) / kBQ);
     KBNER_CHECK_ARG(total < (1ll << 30), "attention_fwd: too many work items");
-    dim3 grid((unsigned)(total < 2 * kNumSMs ? total : 2 * kNumSMs));
+    const long long resident = 2ll * sm_budget();
+    dim3 grid((unsigned)(total < resident ? total : resident));
     cudaError_t le;
     if (drop.thresh)
         le = launch_kernel(attention_fwd_kernel<true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 0, true, tmQ, tmKV,
@@ -558,6 +560,7 @@ extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_le
 
 #ifdef KBNER_ATTN_DEBUG
 extern "C" int kbner_attention_debug_read(unsigned long long *host, int n) {
+    KBNER_NVTX("kbner/attention");
     return (int)cudaMemcpyFromSymbol(host, g_attn_dbg, sizeof(unsigned long long) * (size_t)n);
 }
 #endif
@@ -565,11 +568,13 @@ extern "C" int kbner_attention_debug_read(unsigned long long *host, int n) {
 extern "C" int kbner_attention_fwd_dropout(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                            uint16_t *out, float *lse, const uint32_t *drop_seed, uint32_t drop_site,
                                            float drop_p, void *stream) {
+    KBNER_NVTX("kbner/attention");
     return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, nullptr, nullptr, lse, drop_seed, drop_site, drop_p,
                                   stream);
 }
 
 extern "C" int kbner_attention_fwd(const uint16_t *qkv, const int32_t *key_len, int R, int S, int heads,
                                    uint16_t *out, float *lse, void *stream) {
+    KBNER_NVTX("kbner/attention");
     return kbner_attention_fwd_ex(qkv, key_len, R, S, heads, out, heads * kAttnD, nullptr, nullptr, lse, nullptr, 0u, 0.0f, stream);
 }

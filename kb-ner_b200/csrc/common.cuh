@@ -18,6 +18,20 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 bool pdl_enabled();   // programmatic dependent launch between the hot kernels (KBNER_PDL=0 turns it off)
+int num_sms();        // SM count of the current device (148 on B200), queried once per device
+int sm_budget();      // SMs the persistent tensor-core grids may occupy: num_sms() unless kbner_set_sm_budget() lowered it
+// NVTX range around every C-ABI entry point, named after the kernel family ("kbner/gemm", "kbner/attention", ...), so
+// that a timeline or `ncu --nvtx --nvtx-include "kbner/crf/"` groups launches by family.  Off unless KBNER_NVTX=1
+// (one relaxed load per call otherwise).
+void nvtx_push(const char *name);
+void nvtx_pop();
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtx_push(name); }
+    ~NvtxRange() { nvtx_pop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define KBNER_NVTX(name) ::kbner::NvtxRange nvtx_range__(name)
 
 #define KBNER_CHECK_ARG(cond, ...)                       \
     do {                                                 \

@@ -496,6 +496,7 @@ using namespace kbner;
 
 extern "C" int kbner_crf_compact(const uint8_t *keep, int B, int T, int32_t *pos, int32_t *klen,
                                  void *stream) {
+    KBNER_NVTX("kbner/crf");
     KBNER_CHECK_ARG(keep && pos && klen && B >= 0 && T > 0, "crf_compact: bad arguments");
     if (B == 0) return KBNER_OK;
     const int threads = 128;
@@ -509,6 +510,7 @@ extern "C" int kbner_crf_nll_fwd(const float *emis, const int32_t *tags, const i
                                  const int32_t *klen, const float *trans, int B, int T, int L,
                                  int start_idx, int stop_idx, float *logz, float *gold, float *alpha,
                                  double *alpha_scale, void *stream) {
+    KBNER_NVTX("kbner/crf");
     KBNER_CHECK_ARG(emis && tags && klen && trans && logz && gold, "crf_nll_fwd: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_fwd: need L in [2,32], got %d", L);
     KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,
@@ -534,6 +536,7 @@ extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const i
                                  const double *alpha_scale, const float *w, int B, int T, int L,
                                  int start_idx, int stop_idx, float *d_emis, float *d_trans,
                                  void *stream) {
+    KBNER_NVTX("kbner/crf");
     KBNER_CHECK_ARG(emis && tags && klen && trans && alpha && alpha_scale && w && d_emis && d_trans,
                     "crf_nll_bwd: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_nll_bwd: need L in [2,32], got %d", L);
@@ -548,7 +551,18 @@ extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const i
     do {                                                                                                      \
         using C = NllBwdCfg<Q, K>;                                                                            \
         int blocks = (B + C::SPW - 1) / C::SPW;                                                               \
-        if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;   /* persistent over sentences beyond that */         \
+        /* One block per sentence group while a single wave holds them all; persistent over sentences beyond that.   \
+           (The first version capped the grid at 8 blocks per SM: 4096 sentences = 2048 groups then ran as 1184 blocks \
+           of which 864 walked two groups back to back -- twice the chain -- with 6.7 warps per SM resident: 528 us,   \
+           issue slots 32 % busy, profiles/r02/crf_ncu_p1.txt.) */                                                  \
+        static int per_sm = 0;                                                                                \
+        if (per_sm == 0) {                                                                                    \
+            cudaFuncSetAttribute(crf_nll_bwd_kernel<Q, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   \
+            int n_ = 0;                                                                                       \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_, crf_nll_bwd_kernel<Q, K>, 32, C::smem_bytes(L)) != cudaSuccess || n_ < 1) n_ = 8; \
+            per_sm = n_;                                                                                      \
+        }                                                                                                     \
+        if (blocks > per_sm * num_sms()) blocks = per_sm * num_sms();                                         \
         crf_nll_bwd_kernel<Q, K><<<blocks, 32, C::smem_bytes(L), st>>>(emis, tags, pos, klen, trans, alpha,    \
                                                                       alpha_scale, w, B, T, L, start_idx,     \
                                                                       stop_idx, d_emis, d_trans);             \

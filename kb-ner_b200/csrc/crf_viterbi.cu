@@ -58,7 +58,10 @@ struct VitCfg {
     static constexpr int SPW = 32 / Q;                 // sentences per warp
     static constexpr int BITS = (K <= 16) ? 4 : 8;     // bits per back-pointer
     static constexpr int SPWD = 32 / (JL * BITS);      // steps per back-pointer word
-    static constexpr int FP = (Q < 8) ? Q : 8;         // steps per confidence flush (= unrolled steps)
+    // steps per confidence flush (= unrolled steps).  What a block keeps live decides how many blocks share an SM: with 16
+    // unrolled steps the L = 13 kernel needed 168 registers and the L = 29 kernel 254 (8 blocks per SM: 4096 sentences =
+    // 3.5 waves); 8 steps (4 for L > 16) bring them to 67 / 86.
+    static constexpr int FP = (K > 16) ? 4 : ((Q < 8) ? Q : 8);
     static constexpr int KP = (K + 3) / 4 * 4;         // staging row stride (16-byte rows)
     static_assert(Q * JL >= K && JL <= 2, "every tag needs an owner; a lane stores its JL states with one STS");
     static_assert(kVitChunk % FP == 0 && FP % SPWD == 0, "flush period must tile the chunk and the back-pointer words");
@@ -393,6 +396,7 @@ extern "C" int kbner_crf_viterbi(const float *emis, const int32_t *pos, const in
                                  const int32_t *slen, const float *trans, int B, int T, int L,
                                  int start_idx, int stop_idx, int x_idx, int32_t *tags_out,
                                  float *conf_out, void *stream) {
+    KBNER_NVTX("kbner/crf");
     KBNER_CHECK_ARG(emis && klen && slen && trans && tags_out && conf_out, "crf_viterbi: null pointer");
     KBNER_CHECK_ARG(B >= 0 && T > 0 && L >= 2 && L <= 32, "crf_viterbi: need L in [2,32], got L=%d T=%d", L, T);
     KBNER_CHECK_ARG(start_idx >= 0 && start_idx < L && stop_idx >= 0 && stop_idx < L,

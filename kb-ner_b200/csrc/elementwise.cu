@@ -368,6 +368,7 @@ using namespace kbner;
 extern "C" int kbner_add_layernorm_fwd(const float *x, const float *bias, const uint16_t *resid, const float *gamma,
                                        const float *beta, float eps, int M, int H, uint16_t *y, float *mean, float *rstd,
                                        const uint32_t *drop_seed, uint32_t drop_site, float drop_p, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     KBNER_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 128 == 0, "layernorm_fwd: H=%d must be a multiple of 128", H);
     KBNER_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
@@ -390,6 +391,7 @@ extern "C" int kbner_add_layernorm_fwd(const float *x, const float *bias, const 
 
 extern "C" int kbner_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int M, int H,
                                    uint16_t *y, float *mean, float *rstd, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     return kbner_add_layernorm_fwd(x, nullptr, nullptr, gamma, beta, eps, M, H, y, mean, rstd, nullptr, 0u, 0.0f, stream);
 }
 
@@ -397,6 +399,7 @@ extern "C" int kbner_embed_ln_fwd_ex(const int32_t *ids, const float *word_emb, 
                                      const float *type_emb, const float *gamma, const float *beta, float eps,
                                      int pad_id, int R, int S, int H, int V, int P, uint16_t *out, float *out32, int split,
                                      void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     KBNER_CHECK_ARG(ids && word_emb && pos_emb && type_emb && gamma && beta && out, "embed_ln_fwd: null pointer");
     KBNER_CHECK_ARG(R >= 0 && S > 0 && H % 128 == 0 && V > 0 && P > 0, "embed_ln_fwd: bad shape");
     if (R == 0) return KBNER_OK;
@@ -411,6 +414,7 @@ extern "C" int kbner_embed_ln_fwd_ex(const int32_t *ids, const float *word_emb, 
 extern "C" int kbner_embed_ln_fwd(const int32_t *ids, const float *word_emb, const float *pos_emb,
                                   const float *type_emb, const float *gamma, const float *beta, float eps,
                                   int pad_id, int R, int S, int H, int V, int P, uint16_t *out, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     return kbner_embed_ln_fwd_ex(ids, word_emb, pos_emb, type_emb, gamma, beta, eps, pad_id, R, S, H, V, P, out, nullptr, 0,
                                  stream);
 }
@@ -418,6 +422,7 @@ extern "C" int kbner_embed_ln_fwd(const int32_t *ids, const float *word_emb, con
 extern "C" int kbner_add_layernorm_fwd_res32(const float *x, const float *bias, const float *resid, const float *gamma,
                                              const float *beta, float eps, int M, int H, float *y32, uint16_t *y,
                                              int split, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     KBNER_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd_res32: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 128 == 0, "layernorm_fwd_res32: H=%d must be a multiple of 128", H);
     if (M == 0) return KBNER_OK;
@@ -430,12 +435,13 @@ extern "C" int kbner_add_layernorm_fwd_res32(const float *x, const float *bias, 
 }
 
 extern "C" int kbner_bias_gelu_split(const float *x, const float *bias, int M, int F, uint16_t *out3, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     KBNER_CHECK_ARG(x && bias && out3, "bias_gelu_split: null pointer");
     KBNER_CHECK_ARG(M >= 0 && F > 0 && F % 4 == 0, "bias_gelu_split: F=%d must be a multiple of 4", F);
     if (M == 0) return KBNER_OK;
     const size_t total = (size_t)M * (F / 4);
     size_t blocks = (total + 255) / 256;
-    if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     bias_gelu_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, (size_t)M, F, out3);
     KBNER_CHECK_LAUNCH("bias_gelu_split");
     return KBNER_OK;
@@ -458,7 +464,7 @@ static int launch_tagproj(const void *hidden, const int32_t *row_of, const int32
     }
     const int pairs = (B * T + 1) / 2;
     int blocks = (pairs + kTagprojWarps - 1) / kTagprojWarps;
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
     gather_tagproj_fwd_kernel<CPL, F32><<<blocks, kTagprojWarps * 32, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, L,
                                                               logits);
     KBNER_CHECK_LAUNCH("gather_tagproj_fwd");
@@ -487,11 +493,13 @@ static int tagproj_dispatch(const void *hidden, const int32_t *row_of, const int
 extern "C" int kbner_gather_tagproj_fwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
                                         const uint8_t *drop_keep, const float *W, const float *bias, int B, int T,
                                         int S, int H, int L, float *logits, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     return tagproj_dispatch<false>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, H, L, logits, stream);
 }
 
 extern "C" int kbner_gather_tagproj_fwd_f32(const float *hidden, const int32_t *row_of, const int32_t *first_idx,
                                             const uint8_t *drop_keep, const float *W, const float *bias, int B, int T,
                                             int S, int H, int L, float *logits, void *stream) {
+    KBNER_NVTX("kbner/elementwise");
     return tagproj_dispatch<true>(hidden, row_of, first_idx, drop_keep, W, bias, B, T, S, H, L, logits, stream);
 }

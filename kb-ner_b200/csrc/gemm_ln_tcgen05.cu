@@ -407,6 +407,7 @@ static int g_max_clusters[2 * kMaxPairs + 1] = {0};   // resident clusters per c
 extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t *W, const float *bias,
                                                const uint16_t *resid, const float *gamma, const float *beta, float eps,
                                                uint16_t *Y, int M, int N, int K, int lda, int ldw, void *stream) {
+    KBNER_NVTX("kbner/gemm_ln");
     KBNER_CHECK_ARG(A && W && gamma && beta && Y, "gemm_ln: null pointer");
     KBNER_CHECK_ARG(M > 0 && K > 0, "gemm_ln: empty problem M=%d K=%d", M, K);
     KBNER_CHECK_ARG(N % 256 == 0 && N >= 256 && N <= 256 * kMaxPairs,
@@ -446,7 +447,7 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
             return KBNER_ECUDA;
         }
         // how many clusters of this size can be co-resident (GPC granularity): the kernel is persistent over row panels
-        cfg.gridDim = dim3((unsigned)(csize * (kNumSMs / csize)));
+        cfg.gridDim = dim3((unsigned)(csize * (num_sms() / csize)));
         int n = 0;
         e = cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel, &cfg);
         if (e != cudaSuccess || n <= 0) {
@@ -471,6 +472,7 @@ extern "C" int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t
 
 // Resident clusters the fused kernel gets for hidden size N (0 before its first launch): reported by bench.py.
 extern "C" int kbner_gemm_ln_resident_clusters(int N) {
+    KBNER_NVTX("kbner/gemm_ln");
     if (N % 256 != 0 || N < 256 || N > 256 * kMaxPairs) return 0;
     const int ntiles = N / 256;
     return g_max_clusters[2 * (ntiles / ((ntiles % 2 == 0) ? 2 : 1))];

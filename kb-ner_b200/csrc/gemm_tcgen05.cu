@@ -404,7 +404,8 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int num_kb = (g.K + BK - 1) / BK;
     const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
-    const int clusters = num_work < kNumSMs / 2 ? num_work : kNumSMs / 2;
+    const int pairs = sm_budget() / 2;               // persistent: one CTA pair per two SMs of the budget
+    const int clusters = num_work < pairs ? num_work : pairs;
     cudaError_t le = launch_kernel(gemm_bf16_kernel<EPI>, dim3(clusters * 2), dim3(kGemmThreads), smem, st, 0, true, tmA, tmB, tmC,
                                    tmAux, g);
     if (le != cudaSuccess) {
@@ -422,6 +423,7 @@ using namespace kbner;
 extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float *bias, const uint16_t *aux,
                                uint16_t *aux_out, void *C, int M, int N, int K, int lda, int ldb, int ldc,
                                int a_mn_major, int b_mn_major, int epilogue, void *stream) {
+    KBNER_NVTX("kbner/gemm");
     KBNER_CHECK_ARG(A && B && C, "gemm: null pointer");
     KBNER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     // TMA needs 16-byte row pitches; extents are free (ragged tile edges are zero-filled on load, clipped on store)
@@ -455,7 +457,7 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     if (epilogue == KBNER_EPI_ACCUM_F32) {
         // fill ~2 work items per cluster, but keep >= 4 k-blocks per item so the pipeline prologue stays amortised
         const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-        int splits = (2 * (kNumSMs / 2)) / tiles;
+        int splits = (2 * (sm_budget() / 2)) / tiles;
         if (splits > num_kb_h / 4) splits = num_kb_h / 4;
         if (splits < 1) splits = 1;
         kb_per = (num_kb_h + splits - 1) / splits;
@@ -477,6 +479,7 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
 extern "C" int kbner_gemm_bf16_tn(const uint16_t *A, const uint16_t *B, const float *bias,
                                   const uint16_t *residual, void *C, int M, int N, int K, int lda, int ldb,
                                   int ldc, int epilogue, void *stream) {
+    KBNER_NVTX("kbner/gemm");
     KBNER_CHECK_ARG(epilogue == KBNER_EPI_NONE_F32 || bias, "gemm: epilogue %d needs a bias", epilogue);
     return kbner_gemm_bf16(A, B, bias, residual, nullptr, C, M, N, K, lda, ldb, ldc, 0, 0, epilogue, stream);
 }

@@ -7,6 +7,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -22,6 +24,38 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int num_sms() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+static std::atomic<int> g_sm_budget{0};
+int sm_budget() {
+    const int n = num_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
+    return (b > 0 && b < n) ? b : n;
+}
+
+static bool nvtx_on() {
+    static const bool on = [] {
+        const char *e = getenv("KBNER_NVTX");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+void nvtx_push(const char *name) {
+    if (nvtx_on()) nvtxRangePushA(name);
+}
+void nvtx_pop() {
+    if (nvtx_on()) nvtxRangePop();
+}
+
 bool pdl_enabled() {
     static const bool on = [] {
         const char *e = getenv("KBNER_PDL");
@@ -110,6 +144,15 @@ int make_tmap_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t col
 }  // namespace kbner
 
 extern "C" int kbner_abi_version(void) { return 2; }
+
+extern "C" int kbner_set_sm_budget(int n_sms) {
+    if (n_sms < 0) {
+        kbner::set_error("set_sm_budget: %d", n_sms);
+        return KBNER_EINVAL;
+    }
+    kbner::g_sm_budget.store(n_sms & ~1, std::memory_order_relaxed);      // CTA pairs: an even number of SMs
+    return KBNER_OK;
+}
 extern "C" const char *kbner_last_error(void) { return kbner::g_err; }
 extern "C" uint64_t kbner_launch_count(void) { return kbner::g_launches.load(); }
 extern "C" void kbner_add_launches(uint64_t n) { kbner::count_launch((int)n); }

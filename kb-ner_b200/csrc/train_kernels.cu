@@ -599,6 +599,7 @@ extern "C" int kbner_add_layernorm_bwd(const float *x, const float *bias, const 
                                        int M, int H, uint16_t *dx, uint16_t *dx_masked, float *dgamma, float *dbeta,
                                        float *dxsum, const uint32_t *drop_seed, uint32_t drop_site, float drop_p,
                                        void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(x && dout && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H % 128 == 0, "layernorm_bwd: bad shape");
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "layernorm_bwd: dropout probability %f", (double)drop_p);
@@ -608,7 +609,7 @@ extern "C" int kbner_add_layernorm_bwd(const float *x, const float *bias, const 
     if (M == 0) return KBNER_OK;
     KBNER_CHECK_ARG(H % 256 == 0, "layernorm_bwd: hidden size %d must be a multiple of 256", H);
     int blocks = (M + 1) / 2;                     // two rows per block pass
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;   // <= 128 registers x 256 threads: two blocks per SM, one row prefetched each
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();   // <= 128 registers x 256 threads: two blocks per SM, one row prefetched each
     cudaStream_t st = (cudaStream_t)stream;
     if (bias || resid || dres || drop.thresh) {
         DISPATCH_VPL_T(H, (layernorm_bwd_kernel<VPL / 2, true><<<blocks, VPL * 32, 0, st>>>(x, bias, resid, dout, dres, gamma, mean, rstd, M,
@@ -624,15 +625,17 @@ extern "C" int kbner_add_layernorm_bwd(const float *x, const float *bias, const 
 extern "C" int kbner_layernorm_bwd(const float *x, const float *dout, const float *gamma, const float *mean,
                                    const float *rstd, int M, int H, uint16_t *dx, float *dgamma, float *dbeta,
                                    float *dxsum, void *stream) {
+    KBNER_NVTX("kbner/train");
     return kbner_add_layernorm_bwd(x, nullptr, nullptr, dout, nullptr, gamma, mean, rstd, M, H, dx, nullptr, dgamma, dbeta,
                                    dxsum, nullptr, 0u, 0.0f, stream);
 }
 
 extern "C" int kbner_colsum_bf16(const uint16_t *dY, int M, int N, float *db, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(dY && db && M >= 0 && N > 0 && N % 8 == 0, "colsum_bf16: bad arguments");
     if (M == 0) return KBNER_OK;
     dim3 grid((N + 255) / 256, 1);
-    grid.y = (4 * kNumSMs + grid.x - 1) / grid.x;             // ~4 blocks per SM in total, 8 loads in flight per thread
+    grid.y = (4 * num_sms() + grid.x - 1) / grid.x;             // ~4 blocks per SM in total, 8 loads in flight per thread
     if ((int)grid.y * 8 > M) grid.y = (M + 7) / 8;
     colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, M, N, db);
     KBNER_CHECK_LAUNCH("colsum_bf16");
@@ -643,6 +646,7 @@ extern "C" int kbner_embed_ln_bwd(const int32_t *ids, const float *word_emb, con
                                   const float *type_emb, const float *gamma, float eps, int pad_id, int R, int S,
                                   int H, const float *dout, float *d_word, float *d_pos, float *d_type,
                                   float *dgamma, float *dbeta, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(ids && word_emb && pos_emb && type_emb && gamma && dout && d_word && d_pos && d_type && dgamma && dbeta,
                     "embed_ln_bwd: null pointer");
     if (R == 0) return KBNER_OK;
@@ -670,7 +674,7 @@ static int launch_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, con
         configured = smem;
     }
     int blocks = B * T;
-    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
     gather_tagproj_bwd_kernel<CPL, LG><<<blocks, CPL * 32, smem, st>>>(hidden, row_of, first_idx, drop_keep, W, dlogits, B, T, S, L,
                                                                       d_hidden, dW, db);
     KBNER_CHECK_LAUNCH("gather_tagproj_bwd");
@@ -680,6 +684,7 @@ static int launch_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, con
 extern "C" int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, const int32_t *first_idx,
                                         const uint8_t *drop_keep, const float *W, const float *dlogits, int B, int T,
                                         int S, int H, int L, float *d_hidden, float *dW, float *db, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(hidden && row_of && first_idx && W && dlogits && d_hidden && dW && db, "gather_tagproj_bwd: null pointer");
     KBNER_CHECK_ARG(L >= 1 && L <= 32 && H % 256 == 0 && (size_t)L * H * 4 <= 200 * 1024,
                     "gather_tagproj_bwd: needs L <= 32 and L*H*4 <= 200 KB (L=%d H=%d)", L, H);
@@ -695,11 +700,12 @@ extern "C" int kbner_gather_tagproj_bwd(const uint16_t *hidden, const int32_t *r
 }
 
 extern "C" int kbner_sumsq_f32(const float *g, size_t n, float *out, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(g && out, "sumsq: null pointer");
     KBNER_CHECK_ARG(((uintptr_t)g & 15u) == 0, "sumsq: buffer must be 16-byte aligned");
     if (n == 0) return KBNER_OK;
     size_t blocks = (n / 4 + 255) / 256;
-    if (blocks > 8 * (size_t)kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks > 8 * (size_t)num_sms()) blocks = 8 * num_sms();
     if (blocks == 0) blocks = 1;
     sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
     KBNER_CHECK_LAUNCH("sumsq");
@@ -707,6 +713,7 @@ extern "C" int kbner_sumsq_f32(const float *g, size_t n, float *out, void *strea
 }
 
 extern "C" int kbner_clip_coef(const float *sumsq, float pre_scale, float max_norm, float *coef, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(sumsq && coef, "clip_coef: null pointer");
     clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, pre_scale, max_norm, coef);
     KBNER_CHECK_LAUNCH("clip_coef");
@@ -717,6 +724,7 @@ extern "C" int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_b
                                    float beta1, float beta2, float eps, float weight_decay, int step,
                                    const float *gscale_dev, float gscale_host, uint16_t *shadow, size_t n_shadow,
                                    void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(p && (g != nullptr) != (g_bf16 != nullptr) && m && v && step >= 1,
                     "adamw_step: bad arguments (exactly one of g / g_bf16)");
     KBNER_CHECK_ARG(!shadow || (n_shadow <= n && n_shadow % 4 == 0), "adamw_step: shadow length %zu", n_shadow);
@@ -730,7 +738,7 @@ extern "C" int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_b
     KBNER_CHECK_ARG(aligned || (!g_bf16 && !shadow), "adamw_step: bf16 gradient / shadow need 16-byte aligned arenas");
     if (n4) {
         size_t blocks = (n4 + 255) / 256;
-        if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+        if (blocks > 16 * (size_t)num_sms()) blocks = 16 * num_sms();
         const size_t ns4 = shadow ? n_shadow / 4 : 0;
         if (g_bf16)
             adamw_vec_kernel<true><<<(int)blocks, 256, 0, st>>>((float4 *)p, g_bf16, (float4 *)m, (float4 *)v, n4, lr, beta1, beta2, eps,
@@ -744,7 +752,7 @@ extern "C" int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_b
     if (done < n) {
         KBNER_CHECK_ARG(!g_bf16, "adamw_step: a bf16 gradient buffer must have a multiple of 4 elements");
         size_t blocks = (n - done + 255) / 256;
-        if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+        if (blocks > 16 * (size_t)num_sms()) blocks = 16 * num_sms();
         adamw_kernel<<<(int)blocks, 256, 0, st>>>(p + done, g + done, m + done, v + done, n - done, lr, beta1, beta2, eps,
                                                   weight_decay, step_size, gscale_dev, gscale_host);
         KBNER_CHECK_LAUNCH("adamw_step");
@@ -755,28 +763,31 @@ extern "C" int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_b
 extern "C" int kbner_adamw_step(float *p, const float *g, float *m, float *v, size_t n, float lr, float beta1,
                                 float beta2, float eps, float weight_decay, int step, const float *gscale_dev,
                                 float gscale_host, void *stream) {
+    KBNER_NVTX("kbner/train");
     return kbner_adamw_step_ex(p, g, nullptr, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gscale_dev, gscale_host,
                                nullptr, 0, stream);
 }
 
 extern "C" int kbner_pack_bf16(const float *src, uint16_t *dst, size_t n, float scale, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(src && dst, "pack_bf16: null pointer");
     KBNER_CHECK_ARG(n % 4 == 0 && ((uintptr_t)src & 15u) == 0 && ((uintptr_t)dst & 7u) == 0,
                     "pack_bf16: n must be a multiple of 4 and the buffers 16- / 8-byte aligned");
     if (n == 0) return KBNER_OK;
     size_t blocks = (n / 4 + 255) / 256;
-    if (blocks > 16 * (size_t)kNumSMs) blocks = 16 * kNumSMs;
+    if (blocks > 16 * (size_t)num_sms()) blocks = 16 * num_sms();
     pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)src, (uint2 *)dst, n / 4, scale);
     KBNER_CHECK_LAUNCH("pack_bf16");
     return KBNER_OK;
 }
 
 extern "C" int kbner_sumsq_bf16(const uint16_t *g, size_t n, float *out, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(g && out, "sumsq_bf16: null pointer");
     KBNER_CHECK_ARG(n % 4 == 0 && ((uintptr_t)g & 7u) == 0, "sumsq_bf16: n must be a multiple of 4, buffer 8-byte aligned");
     if (n == 0) return KBNER_OK;
     size_t blocks = (n / 4 + 255) / 256;
-    if (blocks > 8 * (size_t)kNumSMs) blocks = 8 * kNumSMs;
+    if (blocks > 8 * (size_t)num_sms()) blocks = 8 * num_sms();
     sumsq_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint2 *)g, n / 4, out);
     KBNER_CHECK_LAUNCH("sumsq_bf16");
     return KBNER_OK;
@@ -784,6 +795,7 @@ extern "C" int kbner_sumsq_bf16(const uint16_t *g, size_t n, float *out, void *s
 
 extern "C" int kbner_dropout_apply(void *x, int is_f32, int M, int H, const uint32_t *drop_seed, uint32_t drop_site,
                                    float drop_p, void *stream) {
+    KBNER_NVTX("kbner/train");
     KBNER_CHECK_ARG(x && drop_seed, "dropout_apply: null pointer");
     KBNER_CHECK_ARG(M >= 0 && H > 0 && H % 8 == 0, "dropout_apply: H=%d must be a multiple of 8", H);
     KBNER_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "dropout_apply: dropout probability %f", (double)drop_p);
@@ -792,7 +804,7 @@ extern "C" int kbner_dropout_apply(void *x, int is_f32, int M, int H, const uint
     if (M == 0 || !drop.thresh) return KBNER_OK;
     const size_t n_pairs = (size_t)M * H / 2;
     size_t blocks = (n_pairs / 4 + 255) / 256;
-    if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+    if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
     cudaStream_t st = (cudaStream_t)stream;
     if (is_f32) dropout_apply_kernel<true><<<(int)blocks, 256, 0, st>>>(x, n_pairs, drop);
     else dropout_apply_kernel<false><<<(int)blocks, 256, 0, st>>>(x, n_pairs, drop);

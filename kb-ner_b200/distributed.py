@@ -47,7 +47,9 @@ class GradExchange:
              it -- the fp32 arena is never written back.  "fp32" (KBNER_GRAD_COMM=fp32) all-reduces the arenas in place.
     overlap  (KBNER_OVERLAP_ALLREDUCE=1) the last backward of the accumulation cycle runs in layer chunks
              (encoder._backward_chunked) and the pack + all-reduce of every finalised arena slice is started
-             asynchronously under the next chunk.
+             asynchronously under the next chunk.  While that backward runs the persistent GEMM / attention grids are
+             sized for num_sms - KBNER_OVERLAP_SM_CARVEOUT (default 16) SMs (kbner_set_sm_budget): NCCL's channel CTAs
+             then have SMs of their own instead of pushing a persistent grid's CTAs into a second wave.
     Without an initialised process group (or world size 1) nothing is exchanged and reduce() returns None.
     `pack` is injectable so the host logic can be exercised with gloo on CPU (tests/test_distributed_cpu.py)."""
 
@@ -58,6 +60,7 @@ class GradExchange:
         if self.payload not in ("bf16", "fp32"):
             raise ValueError("gradient payload must be 'bf16' or 'fp32'")
         self.overlap = (os.environ.get("KBNER_OVERLAP_ALLREDUCE", "0") == "1") if overlap is None else bool(overlap)
+        self.carveout = int(os.environ.get("KBNER_OVERLAP_SM_CARVEOUT", "16"))
         if pack is None:
             from . import ops
             pack = ops.pack_bf16
@@ -88,6 +91,13 @@ class GradExchange:
         self.bytes_per_step += dst.numel() * dst.element_size()
         self._handles.append(dist.all_reduce(dst, op=dist.ReduceOp.SUM, async_op=True))
 
+    def _set_budget(self, on):
+        if self.carveout > 0 and self.arenas and self.arenas[0].grad.is_cuda:
+            from . import _lib
+            lib = _lib.load()
+            sms = torch.cuda.get_device_properties(self.arenas[0].grad.device).multi_processor_count
+            _lib.check(lib.kbner_set_sm_budget(max(2, sms - self.carveout) if on else 0), "set_sm_budget")
+
     def _slice_done(self, lo, hi):
         self._launch(self.encoder.arena, lo, hi)
 
@@ -96,10 +106,12 @@ class GradExchange:
         if boundary and self.active and self.overlap and self.encoder is not None:
             self.bytes_per_step = 0
             self.encoder._grad_sync = self._slice_done
+            self._set_budget(True)
             try:
                 loss.backward()
             finally:
                 self.encoder._grad_sync = None
+                self._set_budget(False)
             self._encoder_done = True
         else:
             loss.backward()
