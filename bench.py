@@ -586,6 +586,7 @@ def train_leg(args, ctx, tagger, emb, headline):
     opt = build_reference_optimizer(tagger, lr=5e-6, lr_rate=10000.0)
     opt.set_linear_schedule(1000)
     exchange = GradExchange(emb.model, [g["arena"] for g in opt.groups])
+    sparse = exchange.enable_sparse_rows(emb.model.ensure_arena(), emb.model.embeddings.word_embeddings.weight, ACC * MB * S_LEN)
     ex_events = []
 
     def step(i, probe=False):
@@ -652,6 +653,8 @@ def train_leg(args, ctx, tagger, emb, headline):
            "gpu_launches": int(launches), "final_loss": lossv,
            "grad_exchange": {"collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce (sum) of the packed gradient arenas",
                              "payload": exchange.payload if world > 1 else None,
+                             "word_embedding_rows": ("sparse: all-gather of the touched rows (<= %d per rank) + ids, added back in rank "
+                                                     "order" % (ACC * MB * S_LEN)) if sparse else "dense (inside the all-reduce)",
                              "bytes_per_optimizer_step": int(exchange.bytes_per_step) if world > 1 else 0,
                              "overlapped_with_backward": bool(exchange.overlap and world > 1),
                              "exposed_ms_per_optimizer_step": round(ex_ms, 3) if world > 1 else 0.0,

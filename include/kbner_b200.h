@@ -298,6 +298,17 @@ int kbner_adamw_step_ex(float *p, const float *g, const uint16_t *g_bf16, float 
 int kbner_pack_bf16(const float *src, uint16_t *dst, size_t n, float scale, void *stream);
 /* out[0] += sum_i g[i]^2 over a bf16 buffer (the norm of the all-reduced gradient, finetune_trainer.py:1010). */
 int kbner_sumsq_bf16(const uint16_t *g, size_t n, float *out, void *stream);
+/* Sparse exchange of an embedding-table gradient between data-parallel ranks (distributed.GradExchange): rows[i] =
+ * bf16(src[ids[i]]) for ids[i] >= 0 (zeros otherwise; zero_src clears the source row), and dst[ids[i]] += rows[i].  ids are
+ * unique within a call (or -1): the kernels use no atomics and the caller adds the ranks' rows in rank order. */
+int kbner_rows_gather_bf16(float *src /*[V,H]*/, const int32_t *ids /*[n]*/, int n, int V, int H, uint16_t *rows /*[n,H]*/,
+                           int zero_src, void *stream);
+int kbner_rows_scatter_add_bf16(const uint16_t *rows /*[n,H]*/, const int32_t *ids /*[n]*/, int n, int V, int H,
+                                float *dst /*[V,H]*/, void *stream);
+/* The same sum with a FIXED summation order (block partials in caller-owned slots, added in index order in fp64): the
+ * clip coefficient is then bit-identical on every data-parallel rank and from run to run.  g fp32 or bf16 (is_bf16). */
+int kbner_sumsq_det(const void *g, size_t n, int is_bf16, float *partials /*[n_partials >= 32]*/, int n_partials,
+                    float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -499,6 +499,85 @@ adamw_vec_kernel(float4 *__restrict__ p, const void *__restrict__ g, float4 *__r
     }
 }
 
+// Sparse exchange of the word-embedding gradient (data-parallel fine-tuning): an optimizer step touches at most
+// tokens-per-step rows of the [250002, 1024] table, so the ranks exchange the touched ROWS (all-gather of bf16 rows + ids)
+// instead of all-reducing 0.5 GB of mostly zeros.  rows_gather: rows[i] = bf16(src[ids[i]]) (zeros for ids[i] < 0) and,
+// with zero_src, the source row is cleared so that rows_scatter_add can rebuild it as the sum over ranks IN RANK ORDER --
+// the same association on every rank, replicas stay bit-identical.  ids are unique within a call (sorted, duplicates
+// replaced by -1 by the caller): no atomics.  One warp per row, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+rows_gather_bf16_kernel(float *__restrict__ src, const int32_t *__restrict__ ids, int n, int H, uint16_t *__restrict__ rows,
+                        int zero_src) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int id = __ldg(ids + i);
+    uint2 *out = reinterpret_cast<uint2 *>(rows + (size_t)i * H);
+    float4 *row = (id >= 0) ? reinterpret_cast<float4 *>(src + (size_t)id * H) : nullptr;
+    for (int c = lane; c < H / 4; c += 32) {
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (row) {
+            v = row[c];
+            if (zero_src) row[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        out[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rows_scatter_add_bf16_kernel(const uint16_t *__restrict__ rows, const int32_t *__restrict__ ids, int n, int H,
+                             float *__restrict__ dst) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int id = __ldg(ids + i);
+    if (id < 0) return;
+    const uint2 *in = reinterpret_cast<const uint2 *>(rows + (size_t)i * H);
+    float4 *row = reinterpret_cast<float4 *>(dst + (size_t)id * H);
+    for (int c = lane; c < H / 4; c += 32) {
+        const uint2 u = __ldg(in + c);
+        float a, b, e, f;
+        unpack_bf16x2(u.x, a, b);
+        unpack_bf16x2(u.y, e, f);
+        float4 v = row[c];
+        v.x += a; v.y += b; v.z += e; v.w += f;
+        row[c] = v;
+    }
+}
+
+// Deterministic sum of squares.  The atomicAdd version above adds the block partials in arrival order: the clip
+// coefficient then differs in its last bits from run to run AND from rank to rank -- with data-parallel fine-tuning every
+// rank clips the same all-reduced gradient, and replicas whose coefficients differ by an ulp drift apart
+// (tests/test_ddp_gpu.py caught it: `replicas diverged at transitions`).  Here every block writes its partial to a
+// caller-owned slot and one warp adds the slots in index order, in fp64.
+template <bool GBF16>
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const void *__restrict__ g, size_t n4, float *__restrict__ partials) {
+    float acc = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float a, b, c, d;
+        if (GBF16) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2 *>(g) + i);
+            unpack_bf16x2(u.x, a, b);
+            unpack_bf16x2(u.y, c, d);
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+            a = v.x; b = v.y; c = v.z; d = v.w;
+        }
+        acc += (a * a + b * b) + (c * c + d * d);
+    }
+    acc = warp_sum(acc);                       // xor-shuffle tree: a fixed order
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) partials[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+__global__ void __launch_bounds__(32) sumsq_final_kernel(const float *__restrict__ partials, int n, float *__restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) acc += (double)partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[0] = (float)((double)out[0] + acc);
+}
+
 // fp32 -> bf16 (round to nearest even) of a flat buffer: the gradient arena packed for the NCCL all-reduce, and the first
 // fill of the bf16 shadow arena.  `scale` multiplies first (1.0 for plain conversion).
 __global__ void __launch_bounds__(256)
@@ -778,6 +857,47 @@ extern "C" int kbner_pack_bf16(const float *src, uint16_t *dst, size_t n, float 
     if (blocks > 16 * (size_t)num_sms()) blocks = 16 * num_sms();
     pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)src, (uint2 *)dst, n / 4, scale);
     KBNER_CHECK_LAUNCH("pack_bf16");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_rows_gather_bf16(float *src, const int32_t *ids, int n, int V, int H, uint16_t *rows, int zero_src,
+                                      void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(src && ids && rows, "rows_gather: null pointer");
+    KBNER_CHECK_ARG(n >= 0 && V > 0 && H > 0 && H % 4 == 0 && (((uintptr_t)src | (uintptr_t)rows) & 15u) == 0,
+                    "rows_gather: H=%d must be a multiple of 4 and the buffers 16-byte aligned", H);
+    if (n == 0) return KBNER_OK;
+    rows_gather_bf16_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(src, ids, n, H, rows, zero_src);
+    KBNER_CHECK_LAUNCH("rows_gather");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_rows_scatter_add_bf16(const uint16_t *rows, const int32_t *ids, int n, int V, int H, float *dst,
+                                           void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(rows && ids && dst, "rows_scatter_add: null pointer");
+    KBNER_CHECK_ARG(n >= 0 && V > 0 && H > 0 && H % 4 == 0 && (((uintptr_t)dst | (uintptr_t)rows) & 15u) == 0,
+                    "rows_scatter_add: H=%d must be a multiple of 4 and the buffers 16-byte aligned", H);
+    if (n == 0) return KBNER_OK;
+    rows_scatter_add_bf16_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rows, ids, n, H, dst);
+    KBNER_CHECK_LAUNCH("rows_scatter_add");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_sumsq_det(const void *g, size_t n, int is_bf16, float *partials, int n_partials, float *out, void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(g && partials && out && n_partials >= 32, "sumsq_det: null pointer / fewer than 32 partial slots");
+    KBNER_CHECK_ARG(n % 4 == 0 && ((uintptr_t)g & (is_bf16 ? 7u : 15u)) == 0, "sumsq_det: n must be a multiple of 4, buffer aligned");
+    if (n == 0) return KBNER_OK;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 8 * (size_t)num_sms()) blocks = 8 * num_sms();
+    if (blocks > (size_t)n_partials) blocks = (size_t)n_partials;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16) sumsq_partial_kernel<true><<<(int)blocks, 256, 0, st>>>(g, n / 4, partials);
+    else sumsq_partial_kernel<false><<<(int)blocks, 256, 0, st>>>(g, n / 4, partials);
+    KBNER_CHECK_LAUNCH("sumsq_partial");
+    sumsq_final_kernel<<<1, 32, 0, st>>>(partials, (int)blocks, out);
+    KBNER_CHECK_LAUNCH("sumsq_final");
     return KBNER_OK;
 }
 

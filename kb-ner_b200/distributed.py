@@ -45,15 +45,20 @@ class GradExchange:
     payload  "bf16" (default): each arena is packed fp32 -> bf16 by one kernel into a static buffer, NCCL all-reduces the
              bf16 buffer (half the 2.24 GB of XLM-R-large's fp32 gradient) and AdamW reads the gradient straight from
              it -- the fp32 arena is never written back.  "fp32" (KBNER_GRAD_COMM=fp32) all-reduces the arenas in place.
+    sparse   (enable_sparse_rows; bf16 payload) the word-embedding gradient -- 1.02 GB of the 2.24, with at most
+             tokens-per-optimizer-step touched rows -- is not all-reduced: every rank all-gathers the ids it touched and
+             those rows (bf16), clears them locally and adds all ranks' rows back in RANK ORDER (the same sum on every
+             rank: replicas stay bit-identical); AdamW reads that region from the fp32 arena.
     overlap  (KBNER_OVERLAP_ALLREDUCE=1) the last backward of the accumulation cycle runs in layer chunks
              (encoder._backward_chunked) and the pack + all-reduce of every finalised arena slice is started
              asynchronously under the next chunk.  While that backward runs the persistent GEMM / attention grids are
              sized for num_sms - KBNER_OVERLAP_SM_CARVEOUT (default 16) SMs (kbner_set_sm_budget): NCCL's channel CTAs
              then have SMs of their own instead of pushing a persistent grid's CTAs into a second wave.
     Without an initialised process group (or world size 1) nothing is exchanged and reduce() returns None.
-    `pack` is injectable so the host logic can be exercised with gloo on CPU (tests/test_distributed_cpu.py)."""
+    `kernels` (pack / rows_gather / rows_scatter_add) are injectable so the host logic can be exercised with gloo on CPU
+    (tests/test_distributed_cpu.py); the product binds the CUDA ones."""
 
-    def __init__(self, encoder, arenas, payload=None, overlap=None, pack=None):
+    def __init__(self, encoder, arenas, payload=None, overlap=None, pack=None, kernels=None):
         import os
         self.encoder, self.arenas = encoder, list(arenas)
         self.payload = payload or os.environ.get("KBNER_GRAD_COMM", "bf16")
@@ -61,19 +66,90 @@ class GradExchange:
             raise ValueError("gradient payload must be 'bf16' or 'fp32'")
         self.overlap = (os.environ.get("KBNER_OVERLAP_ALLREDUCE", "0") == "1") if overlap is None else bool(overlap)
         self.carveout = int(os.environ.get("KBNER_OVERLAP_SM_CARVEOUT", "16"))
-        if pack is None:
+        self.sparse_wanted = os.environ.get("KBNER_SPARSE_EMB_GRAD", "1") != "0"
+        k = dict(kernels or {})
+        if pack is not None:
+            k["pack"] = pack
+        if not all(n in k for n in ("pack", "rows_gather", "rows_scatter_add")):
             from . import ops
-            pack = ops.pack_bf16
-        self._pack = pack
+            k.setdefault("pack", ops.pack_bf16)
+            k.setdefault("rows_gather", ops.rows_gather_bf16)
+            k.setdefault("rows_scatter_add", ops.rows_scatter_add_bf16)
+        self._k = k
         self._bufs = {}
         self._handles = []
         self._encoder_done = False
+        self._sparse = None
         self.bytes_per_step = 0
 
     @property
     def active(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
+    # ---- sparse rows -----------------------------------------------------------------------------------------------
+    def enable_sparse_rows(self, arena, table, cap_tokens):
+        """Exchange `table`'s gradient ([V,H] parameter living in `arena`) as touched rows.  cap_tokens: the largest number of
+        sub-tokens ANY rank embeds within one optimizer step (the same value on every rank: buffers are all-gathered)."""
+        if not (self.active and self.sparse_wanted and self.payload == "bf16"):
+            return False
+        world = dist.get_world_size()
+        V, H = table.shape
+        lo = arena.offsets[id(table)]
+        dev = arena.grad.device
+        cap = (int(cap_tokens) + 7) // 8 * 8
+        if world * cap >= V:                      # nothing to gain: the union could be the whole table
+            return False
+        self._sparse = dict(arena=arena, lo=lo, hi=lo + (V * H + 7) // 8 * 8, V=V, H=H, cap=cap, n=0, done=False,
+                            ids=torch.full((cap,), -1, dtype=torch.int32, device=dev),
+                            rows=torch.empty((cap, H), dtype=torch.bfloat16, device=dev),
+                            all_ids=torch.empty((world, cap), dtype=torch.int32, device=dev),
+                            all_rows=torch.empty((world, cap, H), dtype=torch.bfloat16, device=dev))
+        if self.encoder is not None:
+            self.encoder._ids_hook = self.note_ids
+        return True
+
+    def note_ids(self, ids):
+        """Called by the encoder's training forward with the [R,S] id tensor of every micro-batch."""
+        sp = self._sparse
+        if sp is None:
+            return
+        n = ids.numel()
+        if sp["n"] + n > sp["cap"]:
+            raise RuntimeError("GradExchange: %d sub-tokens in one optimizer step exceed the agreed capacity %d"
+                               % (sp["n"] + n, sp["cap"]))
+        sp["ids"][sp["n"]:sp["n"] + n].copy_(ids.reshape(-1), non_blocking=True)
+        sp["n"] += n
+
+    def _launch_sparse(self):
+        sp = self._sparse
+        if sp["done"]:
+            return
+        sp["done"] = True
+        ids, _ = torch.sort(sp["ids"])                                  # -1 (unused slots) first, duplicates adjacent
+        dup = torch.zeros_like(ids, dtype=torch.bool)
+        dup[1:] = ids[1:] == ids[:-1]
+        ids = torch.where(dup, torch.full_like(ids, -1), ids)           # keep the first of every run (no host sync)
+        table_grad = sp["arena"].grad[sp["lo"]:sp["lo"] + sp["V"] * sp["H"]].view(sp["V"], sp["H"])
+        self._k["rows_gather"](table_grad, ids, sp["rows"], True)       # touched rows -> bf16, cleared in the table
+        sp["sorted"] = ids
+        world = dist.get_world_size()
+        if dist.get_backend() == "nccl":
+            self._handles.append(dist.all_gather_into_tensor(sp["all_ids"].view(-1), ids, async_op=True))
+            self._handles.append(dist.all_gather_into_tensor(sp["all_rows"].view(-1, sp["H"]), sp["rows"], async_op=True))
+        else:
+            self._handles.append(dist.all_gather(list(sp["all_ids"].unbind(0)), ids, async_op=True))
+            self._handles.append(dist.all_gather(list(sp["all_rows"].unbind(0)), sp["rows"], async_op=True))
+        self.bytes_per_step += world * (ids.numel() * 4 + sp["rows"].numel() * 2)
+
+    def _finish_sparse(self):
+        sp = self._sparse
+        table_grad = sp["arena"].grad[sp["lo"]:sp["lo"] + sp["V"] * sp["H"]].view(sp["V"], sp["H"])
+        for r in range(dist.get_world_size()):                          # rank order: the same sum on every rank
+            self._k["rows_scatter_add"](sp["all_rows"][r], sp["all_ids"][r], table_grad)
+        sp["ids"].fill_(-1)
+        sp["n"], sp["done"] = 0, False
+
+    # ---- dense slices ----------------------------------------------------------------------------------------------
     def _buf(self, ar):
         b = self._bufs.get(id(ar))
         if b is None:
@@ -83,9 +159,15 @@ class GradExchange:
     def _launch(self, ar, lo, hi):
         if hi <= lo:
             return
+        sp = self._sparse
+        if sp is not None and ar is sp["arena"] and lo < sp["hi"] and hi > sp["lo"]:
+            self._launch(ar, lo, min(hi, sp["lo"]))                    # dense part below the table
+            self._launch_sparse()
+            self._launch(ar, max(lo, sp["hi"]), hi)                    # dense part above it
+            return
         if self.payload == "bf16":
             dst = self._buf(ar)[lo:hi]
-            self._pack(ar.grad[lo:hi], dst)
+            self._k["pack"](ar.grad[lo:hi], dst)
         else:
             dst = ar.grad[lo:hi]
         self.bytes_per_step += dst.numel() * dst.element_size()
@@ -117,8 +199,9 @@ class GradExchange:
             loss.backward()
 
     def reduce(self):
-        """Exchange whatever has not been started yet, wait for everything, return the per-arena buffers the optimizer
-        must read (bf16 payload: the packed buffers; fp32: the arenas' own .grad), or None when not distributed."""
+        """Exchange whatever has not been started yet, wait for everything, return per arena what the optimizer must read:
+        a flat buffer (bf16 payload: the packed buffer; fp32: the arena's own .grad) or -- for the arena whose embedding
+        table went the sparse way -- a list of (lo, hi, buffer) segments; None when not distributed."""
         if not self.active:
             return None
         if not self._encoder_done:
@@ -130,6 +213,16 @@ class GradExchange:
         for h in self._handles:
             h.wait()
         self._handles, self._encoder_done = [], False
-        if self.payload == "bf16":
-            return [self._buf(ar) for ar in self.arenas]
-        return [ar.grad for ar in self.arenas]
+        sp = self._sparse
+        if sp is not None:
+            self._finish_sparse()
+        out = []
+        for ar in self.arenas:
+            if self.payload != "bf16":
+                out.append(ar.grad)
+            elif sp is not None and ar is sp["arena"]:
+                b, n = self._buf(ar), ar.grad.numel()
+                out.append([(0, sp["lo"], b[:sp["lo"]]), (sp["lo"], sp["hi"], ar.grad[sp["lo"]:sp["hi"]]), (sp["hi"], n, b[sp["hi"]:n])])
+            else:
+                out.append(self._buf(ar))
+        return out

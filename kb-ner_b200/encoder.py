@@ -138,7 +138,7 @@ class XLMRobertaEncoderB200(torch.nn.Module):
     # ---- checkpointing: only parameters travel; graphs, workspaces, compute copies and the arena are rebuilt ----
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ("_compute", "arena", "_drop_seed", "_drop_seed_buf"):
+        for k in ("_compute", "arena", "_drop_seed", "_drop_seed_buf", "_ids_hook", "_grad_sync"):
             state[k] = None
         state["_ws"] = {}
         state["_graphs"] = collections.OrderedDict()
@@ -572,6 +572,9 @@ def _forward_train(self, ids, key_len):
         self._drop_seed = self._drop_seed_buf
     else:
         self._drop_seed = None
+    hook = getattr(self, "_ids_hook", None)
+    if hook is not None:              # the data-parallel exchange records which embedding rows this step touches
+        hook(ids)
     if not self._use_graphs:
         return _forward_train_eager(self, ids, key_len)
     R, S = ids.shape

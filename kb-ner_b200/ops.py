@@ -378,8 +378,44 @@ def pack_bf16(src, dst, scale=1.0):
     return dst
 
 
-def sumsq(g, out):
-    """out[0] += sum g^2 over a flat fp32 or bf16 buffer."""
+def rows_gather_bf16(src, ids, rows, zero_src=False):
+    """rows[i] = bf16(src[ids[i]]) (zeros where ids[i] < 0); zero_src clears the gathered source rows.  src fp32 [V,H]."""
+    _chk(src, torch.float32, "src", 2)
+    _chk(ids, torch.int32, "ids", 1)
+    _chk(rows, torch.bfloat16, "rows", 2)
+    V, H = src.shape
+    if tuple(rows.shape) != (ids.numel(), H):
+        raise _lib.KbnerError("rows_gather: rows must be [%d, %d]" % (ids.numel(), H))
+    _lib.check(_lib.load().kbner_rows_gather_bf16(_ptr(src), _ptr(ids), ids.numel(), V, H, _ptr(rows), int(bool(zero_src)),
+                                                  _stream()), "rows_gather_bf16")
+    return rows
+
+
+def rows_scatter_add_bf16(rows, ids, dst):
+    """dst[ids[i]] += rows[i] for ids[i] >= 0; ids unique within the call.  dst fp32 [V,H]."""
+    _chk(dst, torch.float32, "dst", 2)
+    _chk(ids, torch.int32, "ids", 1)
+    _chk(rows, torch.bfloat16, "rows", 2)
+    V, H = dst.shape
+    if tuple(rows.shape) != (ids.numel(), H):
+        raise _lib.KbnerError("rows_scatter_add: rows must be [%d, %d]" % (ids.numel(), H))
+    _lib.check(_lib.load().kbner_rows_scatter_add_bf16(_ptr(rows), _ptr(ids), ids.numel(), V, H, _ptr(dst), _stream()),
+               "rows_scatter_add_bf16")
+    return dst
+
+
+def sumsq(g, out, partials=None):
+    """out[0] += sum g^2 over a flat fp32 or bf16 buffer.  With `partials` (fp32 scratch, >= 32 slots) the summation order
+    is fixed: bit-identical across runs and across data-parallel ranks (what the clip coefficient needs)."""
+    if partials is not None:
+        _chk(g, g.dtype, "g", 1)
+        if g.dtype not in (torch.bfloat16, torch.float32):
+            raise _lib.KbnerError("sumsq: fp32 or bf16 expected")
+        _chk(partials, torch.float32, "partials", 1)
+        _chk(out, torch.float32, "out", 1)
+        _lib.check(_lib.load().kbner_sumsq_det(_ptr(g), g.numel(), 1 if g.dtype == torch.bfloat16 else 0, _ptr(partials),
+                                               partials.numel(), _ptr(out), _stream()), "sumsq_det")
+        return out
     if g.dtype == torch.bfloat16:
         _chk(g, torch.bfloat16, "g", 1)
         _chk(out, torch.float32, "out", 1)

@@ -31,24 +31,37 @@ class FusedAdamW:
         self.steps = 0
         dev = self.groups[0]["arena"].flat.device
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._partials = torch.zeros(2048, dtype=torch.float32, device=dev)    # fixed-order norm: same bits on every rank
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+
+    @staticmethod
+    def _segments(arena, grads, i):
+        """The gradient of group i as (lo, hi, buffer) segments of its arena: the arena's own fp32 .grad, one exchanged
+        buffer, or the segment list GradExchange returns when the embedding table's rows went the sparse way."""
+        n = arena.grad.numel()
+        if grads is None:
+            return [(0, n, arena.grad)]
+        g = grads[i]
+        return [(lo, hi, t) for lo, hi, t in g if hi > lo] if isinstance(g, (list, tuple)) else [(0, n, g)]
+
+    def _norm_into_sumsq(self, grads):
+        self._sumsq.zero_()
+        for i, g in enumerate(self.groups):
+            for _, _, t in self._segments(g["arena"], grads, i):
+                ops.sumsq(t, self._sumsq, self._partials)
 
     def grad_norm(self, grad_scale=1.0, grads=None):
         """Global L2 norm of (grad * grad_scale) over all arenas -- a device tensor, no sync."""
-        self._sumsq.zero_()
-        for i, g in enumerate(self.groups):
-            ops.sumsq(g["arena"].grad if grads is None else grads[i], self._sumsq)
+        self._norm_into_sumsq(grads)
         return torch.sqrt(self._sumsq) * grad_scale
 
     def step(self, grad_scale=1.0, grads=None):
         """grad_scale multiplies every gradient first (1/accumulation, 1/world after a sum all-reduce).
-        grads (optional): one flat buffer per group to read INSTEAD of arena.grad -- the bf16 buffers a data-parallel
-        exchange (distributed.GradExchange) left behind; the clip norm is taken over the same buffers (post-reduce,
+        grads (optional): per group what to read INSTEAD of arena.grad -- the buffers a data-parallel exchange
+        (distributed.GradExchange.reduce) left behind; the clip norm is taken over the same buffers (post-reduce,
         finetune_trainer.py:1010).  Arenas that carry a bf16 shadow get it rewritten by the same launch."""
         self.steps += 1
-        self._sumsq.zero_()
-        for i, g in enumerate(self.groups):
-            ops.sumsq(g["arena"].grad if grads is None else grads[i], self._sumsq)
+        self._norm_into_sumsq(grads)
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
             ops.clip_coef(self._sumsq, grad_scale, self.max_grad_norm, self._coef)
             coef = self._coef
@@ -56,9 +69,11 @@ class FusedAdamW:
             coef = None
         for i, g in enumerate(self.groups):
             ar = g["arena"]
-            ops.adamw_step(ar.flat, ar.grad if grads is None else grads[i], g["m"], g["v"], g["lr"], self.betas[0],
-                           self.betas[1], self.eps, self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale,
-                           shadow=ar.shadow)
+            ns = 0 if ar.shadow is None else ar.shadow.numel()
+            for lo, hi, t in self._segments(ar, grads, i):
+                ops.adamw_step(ar.flat[lo:hi], t, g["m"][lo:hi], g["v"][lo:hi], g["lr"], self.betas[0], self.betas[1], self.eps,
+                               self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale,
+                               shadow=ar.shadow[lo:min(hi, ns)] if lo < ns else None)
             if ar.shadow is not None:
                 ar.shadow_fresh = True
 

@@ -92,6 +92,14 @@ class ModelFinetuner:
                                                           max_grad_norm=max_grad_norm)
         opt.set_linear_schedule(steps_per_epoch * max_epochs)
         exchange = GradExchange(emb.model, [g["arena"] for g in opt.groups])
+        if world > 1:
+            # sparse exchange of the word-embedding gradient: capacity = the most sub-tokens any rank embeds within one
+            # optimizer step (counted from the batches' own index tensors, which also warms the tokenisation cache)
+            toks = [int(emb.build_batch(b)[0].numel()) for b in batches]
+            cap = max(sum(sorted(toks, reverse=True)[:gradient_accumulation_steps]), 1) if toks else 1
+            t = torch.tensor([cap], dtype=torch.int64, device=emb.device_)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            exchange.enable_sparse_rows(emb.model.ensure_arena(), emb.model.embeddings.word_embeddings.weight, int(t[0]))
         rnd = random.Random(seed)
         best, history = -1.0, []
         for epoch in range(self.epoch, max_epochs):

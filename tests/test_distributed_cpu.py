@@ -80,7 +80,53 @@ def _worker(rank, world, port, q):
         overlap_ok = (overlap_ok and hook_seen == [True] and enc._grad_sync is None and bool((g_enc.float() == total).all())
                       and bool((g_head.float() == total).all())
                       and ex.bytes_per_step == (ar.numel + head.numel) * (2 if payload == "bf16" else 4))
-    q.put((rank, allidx, counts, errs, norm, overlap_ok))
+    # sparse exchange of an embedding table's gradient: touched rows + ids are all-gathered and added back in rank order;
+    # the dense rest of the arena goes through the all-reduce; the optimizer receives (lo, hi, buffer) segments
+    def rows_gather(src, ids, rows, zero_src):
+        ok = ids >= 0
+        rows.zero_()
+        rows[ok] = src[ids[ok].long()].bfloat16()
+        if zero_src:
+            src[ids[ok].long()] = 0.0
+
+    def rows_scatter_add(rows, ids, dst):
+        ok = ids >= 0
+        dst[ids[ok].long()] += rows[ok].float()
+    V, Hd = 40, 8
+    table = torch.nn.Parameter(torch.zeros(V, Hd))
+    other = torch.nn.Parameter(torch.zeros(24))
+    sar = ParamArena([other, table, torch.nn.Parameter(torch.zeros(8))])
+    g = torch.Generator().manual_seed(100 + rank)
+    my_ids = torch.randint(0, V, (6,), generator=g, dtype=torch.int32)
+    sar.grad.zero_()
+    dense_table = torch.zeros(V, Hd)
+    for t in my_ids.tolist():                                  # what embed_ln_bwd does: scatter-add per token
+        dense_table[t] += float(rank + 1) * 0.5
+    tl = sar.offsets[id(table)]
+    sar.grad[tl:tl + V * Hd] = dense_table.reshape(-1)
+    sar.grad[:24] = float(rank + 1)
+    sar.grad[tl + V * Hd:] = float(10 * (rank + 1))
+    ex = GradExchange(None, [sar], payload="bf16", overlap=False,
+                      kernels=dict(pack=pack, rows_gather=rows_gather, rows_scatter_add=rows_scatter_add))
+    sparse_on = ex.enable_sparse_rows(sar, table, cap_tokens=8)
+    ex.note_ids(my_ids[:4].view(2, 2))
+    ex.note_ids(my_ids[4:].view(1, 2))
+    (segs,) = ex.reduce()
+    all_tables = [torch.zeros(V, Hd) for _ in range(world)]
+    for r in range(world):
+        gg = torch.Generator().manual_seed(100 + r)
+        for t in torch.randint(0, V, (6,), generator=gg, dtype=torch.int32).tolist():
+            all_tables[r][t] += float(r + 1) * 0.5
+    want_table = sum(all_tables)
+    got = torch.zeros(sar.numel)
+    for lo, hi, buf in segs:
+        got[lo:hi] = buf.float()
+    sparse_ok = (sparse_on and isinstance(segs, list) and len(segs) == 3 and segs[1][2].dtype == torch.float32
+                 and segs[0][2].dtype == torch.bfloat16
+                 and torch.allclose(got[tl:tl + V * Hd].view(V, Hd), want_table)
+                 and bool((got[:24] == total).all()) and bool((got[tl + V * Hd:] == 10 * total).all())
+                 and ex._sparse["n"] == 0 and bool((ex._sparse["ids"] == -1).all()))
+    q.put((rank, allidx, counts, errs, norm, overlap_ok and sparse_ok))
     dist.destroy_process_group()
 
 
