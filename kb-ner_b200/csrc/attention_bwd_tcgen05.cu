@@ -21,6 +21,8 @@
 // the fp32 accumulator by `attn_bwd_dq_kernel`.  D is produced by `attn_bwd_prep_kernel`.
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
@@ -376,7 +378,7 @@ extern "C" int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, 
     rc = make_tmap_bf16_2d(&tmDO, d_out, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
     if (rc) return rc;
     const size_t smem = sizeof(AttnBwdSmem);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)

@@ -23,6 +23,8 @@
 // tensor pipe is ~21 % busy.
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
@@ -525,7 +527,7 @@ extern "C" int kbner_attention_fwd_ex(const uint16_t *qkv, const int32_t *key_le
     if (rc) return rc;
     const size_t smem = sizeof(AttnSmem);
     const Dropout drop = make_dropout(drop_seed, drop_site, drop_p);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)

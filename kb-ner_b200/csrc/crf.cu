@@ -11,6 +11,8 @@
 // chain, not by HBM: their traffic is the emissions (and, for the gradient, the stored alpha) read once ("CRF").
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "crf_common.cuh"
 
 namespace kbner {
@@ -555,7 +557,7 @@ extern "C" int kbner_crf_nll_bwd(const float *emis, const int32_t *tags, const i
            (The first version capped the grid at 8 blocks per SM: 4096 sentences = 2048 groups then ran as 1184 blocks \
            of which 864 walked two groups back to back -- twice the chain -- with 6.7 warps per SM resident: 528 us,   \
            issue slots 32 % busy, profiles/r02/crf_ncu_p1.txt.) */                                                  \
-        static int per_sm = 0;                                                                                \
+        static std::atomic<int> per_sm{0};                                                                    \
         if (per_sm == 0) {                                                                                    \
             cudaFuncSetAttribute(crf_nll_bwd_kernel<Q, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   \
             int n_ = 0;                                                                                       \

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the encoder / tagger head: embedding gather + LayerNorm, LayerNorm,
 // first-sub-token gather + word dropout + tag projection.  One warp per row, 16-byte loads,
 // fp32 statistics (two-pass, from registers), bf16 activations out.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace kbner {
@@ -452,7 +454,7 @@ static int launch_tagproj(const void *hidden, const int32_t *row_of, const int32
                           const uint8_t *drop_keep, const float *W, const float *bias, int B, int T, int S, int L,
                           float *logits, cudaStream_t st) {
     const size_t smem = ((size_t)L * CPL * 256 + (size_t)kTagprojWarps * 2 * L * 33) * sizeof(float);
-    static size_t configured = 0;
+    static std::atomic<size_t> configured{0};     // idempotent set-up: a race only repeats it
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gather_tagproj_fwd_kernel<CPL, F32>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -24,6 +24,8 @@
 //               the accumulator is ready, bias loads overlapped with tcgen05.ld, TMEM double-buffered (2 x 256 cols)
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "cluster_ptx.cuh"
 #include "tc_ptx.cuh"
@@ -392,7 +394,7 @@ template <int EPI>
 static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmAux,
                        const GemmArgs &g, cudaStream_t st) {
     const size_t smem = sizeof(GemmSmem);
-    static bool configured = false;
+    static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {

@@ -2,6 +2,8 @@
 // gradient norm, fused AdamW).  The reference gets all of these from autograd + transformers.AdamW
 // (/root/reference/flair/trainers/finetune_trainer.py:939-957 backward, :1007-1023 clip / step / zero_grad);
 // here each is one coalesced pass.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace kbner {
@@ -743,7 +745,7 @@ static int launch_tagproj_bwd(const uint16_t *hidden, const int32_t *row_of, con
                               float *d_hidden, float *dW, float *db, cudaStream_t st) {
     constexpr int LG = 16;
     const size_t smem = ((size_t)L * CPL * 256 + (size_t)kTpbWords * L) * sizeof(float);
-    static size_t configured = 0;
+    static std::atomic<size_t> configured{0};     // idempotent set-up: a race only repeats it
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gather_tagproj_bwd_kernel<CPL, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
