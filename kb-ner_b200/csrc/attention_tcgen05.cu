@@ -212,6 +212,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             ++t;
         }
+        // Drain: every tcgen05.commit of the stream's tail arrives on a k_free / v_free / q_free barrier that no refill waits
+        // for any more.  Wait for them here, so that no asynchronous arrive is still in flight towards this CTA's shared
+        // memory when it exits (compute-sanitizer synccheck: "Missing wait", profiles/r02/sanitizer_san1.txt).
+        for (uint32_t sl = 0; sl < (uint32_t)kKVStages; ++sl) {
+            const uint32_t kf = kuse + (sl < kslot ? 1u : 0u), vf = vuse + (sl < vslot ? 1u : 0u);   // fills of slot sl
+            if (kf > 0) ptx::mbar_wait(&s.k_free[sl], (kf - 1) & 1);
+            if (vf > 0) ptx::mbar_wait(&s.v_free[sl], (vf - 1) & 1);
+        }
+        if (nq > 0) ptx::mbar_wait(&s.q_free, (nq - 1) & 1);
     } else if (warp == 8) {
         // ===================== MMA issuer: WARP-UNIFORM, only the issuing instructions sit under elect.sync ===============
         // (Under `if (lane == 0)` ptxas wraps every UTCHMMA / UTCBAR in an ELECT / PLOP3 / BRA.U.ANY loop.)  This warp's
