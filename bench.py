@@ -348,15 +348,13 @@ def infer_leg(args, ctx, tagger, emb):
                    "encoder": cfg.name, "precision": emb.model.precision},
         "e2e": {"value": round(n_sent / wall_e2e, 2), "unit": "sentences/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(wall_e2e * 1e3 / K, 3),
-                "api": "FastSequenceTagger.evaluate(loader, speed_test=True): per batch build_batch (sentence plans cached from "
-                       "the warm-up pass) -> one pinned H2D -> forward graph -> tag projection -> Viterbi -> tags + confidences "
-                       "D2H into per-sentence LabelSeq (Label objects are created on access)",
+                "api": "FastSequenceTagger.evaluate(loader, speed_test=True): build_batch (plans cached by the warm-up pass) -> one "
+                       "pinned H2D -> forward graph -> tag projection -> Viterbi -> tags + confidences D2H into LabelSeq (Label "
+                       "objects on access)",
                 "strict": {"value": round(BATCH * ks * world / wall_strict, 2), "unit": "sentences/s", "steps": ks,
                            "ms_per_step": round(wall_strict * 1e3 / ks, 3),
-                           "what": "same call on never-seen sentences (Zipf-distributed words; sub-tokenisation of 16 320 words + window "
-                                   "plan per batch inside the timed region, through the pure-Python SyntheticTokenizer stand-in) with "
-                                   "all 16 320 Label objects per batch built -- the host work the reference's --test_speed also pays; "
-                                   "host-bound, not kernel-bound"}},
+                           "what": "same call on never-seen sentences (sub-tokenisation + window plan of 16 320 words per batch inside the "
+                                   "region, pure-Python SyntheticTokenizer stand-in) with every Label object built: host-bound"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels (gemm_bf16_kernel + gemm_ln_kernel, %d launches/step; the fused "
                                "LayerNorm epilogues are charged to the GEMM time, their FLOPs are not counted)" % len(gemm_events),
@@ -444,8 +442,7 @@ def parity_leg(ctx, tagger, emb, batch):
                               "viterbi_tag_agreement": round(agree, 6), "span_f1_vs_fp32_path": round(float(span_f1(tags_np)), 4)}
     emb.model.set_precision(before)
     out["crf_loss_fp32_oracle"] = round(ref_loss, 4)
-    out["note"] = ("random-init head: emission margins are ~0.6 wide against N(0,1) transitions, the hardest case for tag "
-                   "agreement; identical emissions give bit-identical tags (tests/test_kernels_gpu.py)")
+    out["note"] = "random-init head (emission margins ~0.6 vs N(0,1) transitions); identical emissions give bit-identical tags"
     return out
 
 
@@ -460,8 +457,9 @@ def crf_sweep_leg(ctx):
     sm_clock_ghz = 1.965
     issue_per_s = 148 * 4 * sm_clock_ghz * 1e9          # warp-instructions per second: 4 schedulers per SM, 1 per clock
     out = {"T": T, "hbm_peak_gbs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % how, "l2": "256 MB written between iterations",
-           "alu_ceiling": "exact first-arg-max Viterbi needs >= L^2 * (0.5 FADD2 + 0.5 FMNMX3 + 1.5 arg-max) lane-instructions per "
-                          "sentence-step; ceiling = that / 32 lanes / (148 SMs x 4 schedulers x %.3f GHz)" % sm_clock_ghz,
+           "bytes": "algorithmic (SURVEY 8d): viterbi T*L*4+T*8, nll_fwd T*L*4+T*4+8, nll_bwd 3*T*L*4+T*12 per sentence",
+           "alu_floor_ms": "issue floor of the exact first-arg-max recurrence: L^2 * 2.5 lane-instructions per sentence-step / 32 "
+                           "lanes / (148 SMs x 4 schedulers x %.3f GHz) -- DESIGN.md section 4 (CRF)" % sm_clock_ghz,
            "rows": []}
     for L, sweep in ((13, (64, 256, 1024, 4096)), (29, (64, 1024, 4096))):
         rng = np.random.RandomState(0)
@@ -493,11 +491,9 @@ def crf_sweep_leg(ctx):
                     ts.append(s_.elapsed_time(e_))
                 ms = sorted(ts)[len(ts) // 2]
                 gbs = B * bytes_per / (ms / 1e3) / 1e9
-                row[name] = {"ms": round(ms, 4), "sent_per_s": round(B / (ms / 1e3), 1), "GBps": round(gbs, 1),
-                             "frac_hbm": round(gbs / hbm, 4)}
+                row[name] = {"ms": round(ms, 4), "GBps": round(gbs), "frac_hbm": round(gbs / hbm, 4)}
             alu_ms = B * T * L * L * 2.5 / 32 / issue_per_s * 1e3
-            row["viterbi"]["alu_issue_floor_ms"] = round(alu_ms, 4)
-            row["viterbi"]["frac_of_alu_ceiling"] = round(alu_ms / row["viterbi"]["ms"], 4)
+            row["viterbi"]["alu_floor_ms"] = round(alu_ms, 4)
             out["rows"].append(row)
     return out
 
@@ -644,17 +640,16 @@ def train_leg(args, ctx, tagger, emb, headline):
                                   % ("" if world == 1 else " / [3]: DDP, NCCL gradient all-reduce"),
                       "micro_batch_per_gpu": MB, "grad_accum": ACC, "seq_len": S_LEN, "tags": N_TAGS,
                       "parallelism": "dp%d" % world,
-                      "dropout": "hidden %.2f / attention %.2f as in transformers (stateless counter-hash masks, regenerated in "
-                                 "the backward)" % (cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob),
-                      "l2": "working set (2.2 GB fp32 masters + 0.6 GB bf16 + activations) exceeds the 126 MB L2"},
+                      "dropout": "hidden %.2f / attention %.2f" % (cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob),
+                      "l2": "working set (2.8 GB of weights + activations) exceeds the 126 MB L2"},
            "e2e": {"value": round(n_sent / (wall_ms / 1e3), 2), "unit": "sentences/s", "h2d_bytes_per_step": MB * S_LEN * 4 * 2,
                    "d2h_bytes_per_step": 4, "api": "FastSequenceTagger.forward_loss + loss.backward + GradExchange.reduce + "
                                                   "FusedAdamW.step (the body of ModelFinetuner.train)"},
            "gpu_launches": int(launches), "final_loss": lossv,
            "grad_exchange": {"collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce (sum) of the packed gradient arenas",
                              "payload": exchange.payload if world > 1 else None,
-                             "word_embedding_rows": ("sparse: all-gather of the touched rows (<= %d per rank) + ids, added back in rank "
-                                                     "order" % (ACC * MB * S_LEN)) if sparse else "dense (inside the all-reduce)",
+                             "word_embedding_rows": ("sparse: all-gather of <= %d touched rows per rank" % (ACC * MB * S_LEN))
+                             if sparse else "dense (inside the all-reduce)",
                              "bytes_per_optimizer_step": int(exchange.bytes_per_step) if world > 1 else 0,
                              "overlapped_with_backward": bool(exchange.overlap and world > 1),
                              "exposed_ms_per_optimizer_step": round(ex_ms, 3) if world > 1 else 0.0,
@@ -663,6 +658,9 @@ def train_leg(args, ctx, tagger, emb, headline):
                         "note": "whole-step model FLOPs (3 x forward) / step time, not a single kernel", "traffic": None}}
     if headline:
         rec["_t0"], rec["_t1"] = tw0, tw1
+    else:
+        for k in ("unit", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "n_gpus"):
+            rec.pop(k, None)
     return rec
 
 

@@ -269,7 +269,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             ptx::mbar_wait(&s.v_full[vslot], vuse & 1);
             ATTN_STAMP(0, g, 1);
             const uint32_t f = s.blk_flags[g & 7];
-            if ((f & 1u) && g > 0) obuf ^= 1u;       // a new item accumulates into the other O buffer
+            if ((f & 1u) && g > 0) ++obuf;           // a new item accumulates into the other O buffer (obuf = item index)
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 const uint32_t v_addr = v_addr0 + vslot * kKVBytes;
@@ -279,9 +279,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     const uint64_t da = ptx::make_sw128_desc(p_addr + kk * 32, 16, 1024);
                     // V tile [key][d]: 16 keys per MMA = two 8-row swizzle atoms, 1024 B apart (SBO)
                     const uint64_t db = ptx::make_sw128_desc(v_addr + kk * 16 * 128, 16, 1024);
-                    ptx::mma_f16_ss(tmem_o + obuf * 64, da, db, idesc_o, !(f & 1u) || (kk != 0));   // O accumulates in TMEM
+                    ptx::mma_f16_ss(tmem_o + (obuf & 1u) * 64, da, db, idesc_o, !(f & 1u) || (kk != 0));   // O accumulates in TMEM
                 }
-                ptx::mma_commit(&s.bar_o[g & 1]);
+                // bar_o[item & 1] completes ONCE per item, with its last P.V: every phase of it is waited for by the
+                // read-out (a per-block commit left phases nobody observed -- compute-sanitizer synccheck "Missing wait");
+                // the lazy rescale of the running O synchronises on v_free instead, which covers the same MMAs
+                if (f & 2u) ptx::mma_commit(&s.bar_o[obuf & 1u]);
                 ptx::mma_commit(&s.v_free[vslot]);
             }
             __syncwarp();
@@ -335,12 +338,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
             }
         };
-        auto read_out = [&](bool from_tmem, uint32_t o_addr, uint32_t g_last, uint8_t *stage, float m_run, float l_run, int qrow,
+        auto read_out = [&](bool from_tmem, uint32_t o_addr, uint32_t item, uint8_t *stage, float m_run, float l_run, int qrow,
                             int row0, int h, int r) {
             const int qrow0 = qrow - row;                       // first query row of the item's 128-row block
             float o_acc[32];
             if (from_tmem) {
-                ptx::mbar_wait(&s.bar_o[g_last & 1], (g_last >> 1) & 1);
+                ptx::mbar_wait(&s.bar_o[item & 1], (item >> 1) & 1);       // the item's last P.V has retired
                 ptx::tc_fence_after();
                 uint32_t ro[32];
                 ptx::tmem_ld_32x32b_x32(o_addr, ro);
@@ -439,7 +442,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     const float alpha = ex2_approx(m_run - m_new);
                     m_run = m_new;
                     l_run *= alpha;
-                    ptx::mbar_wait(&s.bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);    // P.V of the previous block has retired
+                    ptx::mbar_wait(&s.v_free[(g - 1) % kKVStages], ((g - 1) / kKVStages) & 1);    // P.V of the previous block has retired
                     ptx::tc_fence_after();
                     uint32_t ro[32];
                     ptx::tmem_ld_32x32b_x32(o_addr, ro);
@@ -485,7 +488,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::mbar_arrive(&s.bar_p[g & 1]);
                 ATTN_STAMP((warp == 0 ? 1 : (warp == 7 ? 2 : -1)), g, 3);
                 if (j == 0 && pend) {            // the previous item's read-out, now that this item's first block is under way
-                    read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    read_out(true, pend_o, n_item - 1, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
                     pend = false;
                 }
             }
@@ -496,13 +499,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ++n_item;
             } else {                             // window without a valid key: zeros (flush the outstanding read-out first)
                 if (pend) {
-                    read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+                    read_out(true, pend_o, n_item - 1, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
                     pend = false;
                 }
                 read_out(false, 0u, 0u, s.p[g & 1], m_run, l_run, qrow, row0, h, r);   // every earlier P.V has retired
             }
         }
-        if (pend) read_out(true, pend_o, pend_g, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
+        if (pend) read_out(true, pend_o, n_item - 1, s.p[pend_g & 1], pend_m, pend_l, pend_qrow, pend_row0, pend_h, pend_r);
     }
     ptx::tc_fence_before();
     __syncthreads();
