@@ -58,6 +58,10 @@ SIGNATURES = {
                                                                           ctypes.c_size_t, _c_void_p], _c_int),
     "kbner_pack_bf16": ([_c_void_p, _c_void_p, ctypes.c_size_t, _c_float, _c_void_p], _c_int),
     "kbner_sumsq_bf16": ([_c_void_p, ctypes.c_size_t, _c_void_p, _c_void_p], _c_int),
+    "kbner_mark_rows": ([_c_void_p, ctypes.c_size_t, _c_int, _c_void_p, _c_void_p], _c_int),
+    "kbner_adamw_rows": ([_c_void_p] * 5 + [_c_int, _c_int] + [_c_float] * 5 + [_c_int, _c_void_p, _c_float, _c_void_p], _c_int),
+    "kbner_sumsq_rows_det": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p], _c_int),
+    "kbner_zero_rows": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
     "kbner_rows_gather_bf16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p], _c_int),
     "kbner_rows_scatter_add_bf16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
     "kbner_sumsq_det": ([_c_void_p, ctypes.c_size_t, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p], _c_int),

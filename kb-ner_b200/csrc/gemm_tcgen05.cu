@@ -275,7 +275,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (col0 < N) {
                             const uint32_t b = (nb + c) & 1;
                             ptx::mbar_expect_tx(&s.aux_full[ew][b], 4096);
-                            ptx::tma_load_2d(stage_base + b * 4096, &tmAux, &s.aux_full[ew][b], col0, row_base);
+                            ptx::tma_load_2d_cta(stage_base + b * 4096, &tmAux, &s.aux_full[ew][b], col0, row_base);
                         }
                     }
                 }

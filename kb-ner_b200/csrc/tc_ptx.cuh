@@ -84,6 +84,17 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// The same copy with the destination and the mbarrier named in the EXECUTING CTA's window (.shared::cta, PTX 8.6+): inside a
+// thread-block cluster this leaves no room for reading the operands as rank-0 cluster addresses (compute-sanitizer synccheck
+// reported "Missing init" for a barrier of the odd CTA of a pair that the .shared::cluster form completed on).
+__device__ __forceinline__ void tma_load_2d_cta(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                                int32_t c0 /*inner*/, int32_t c1 /*outer*/) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -545,6 +545,77 @@ rows_scatter_add_bf16_kernel(const uint16_t *__restrict__ rows, const int32_t *_
     }
 }
 
+// Row-sparse optimizer work on the word-embedding table (250 002 x 1024 = 46 % of XLM-R-large's parameters): a row no
+// sentence has ever touched has g = m = v = 0, so AdamW leaves it where it is (p -= step * 0 / (0 + eps); weight decay is 0
+// in the reference's groups, finetune_trainer.py:552-571) -- reading and rewriting it (28 B per parameter) every optimizer
+// step is pure HBM traffic.  `touched[row]` is set the first time a sub-token id is embedded (mark_rows) and never cleared:
+// rows with momentum keep being updated.  The three passes over the table (clip norm, AdamW, zero_grad) visit flagged rows
+// only; per element the arithmetic is the dense kernels', so the parameters are bit-identical to the dense path.
+__global__ void __launch_bounds__(256) mark_rows_kernel(const int32_t *__restrict__ ids, size_t n, int V, uint8_t *__restrict__ touched) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int id = ids[i];
+        if (id >= 0 && id < V) touched[id] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_rows_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                  const uint8_t *__restrict__ touched, int V, int H, float lr, float b1, float b2, float eps, float wd,
+                  float step_size, const float *__restrict__ gscale_ptr, float gscale_host) {
+    const float gs = gscale_host * (gscale_ptr ? *gscale_ptr : 1.0f);
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < V; row += gridDim.x * 8) {
+        if (!touched[row]) continue;
+        const size_t base = (size_t)row * H / 4;
+        for (int c = lane; c < H / 4; c += 32) {
+            const float4 gq = reinterpret_cast<const float4 *>(g)[base + c];
+            float4 pq = reinterpret_cast<float4 *>(p)[base + c], mq = reinterpret_cast<float4 *>(m)[base + c],
+                   vq = reinterpret_cast<float4 *>(v)[base + c];
+            float gi[4] = {gq.x, gq.y, gq.z, gq.w}, pi[4] = {pq.x, pq.y, pq.z, pq.w}, mi[4] = {mq.x, mq.y, mq.z, mq.w},
+                  vi[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = gi[k] * gs;
+                mi[k] = b1 * mi[k] + (1.0f - b1) * gk;
+                vi[k] = b2 * vi[k] + (1.0f - b2) * gk * gk;
+                pi[k] = pi[k] - step_size * mi[k] / (sqrtf(vi[k]) + eps);
+                if (wd != 0.0f) pi[k] -= lr * wd * pi[k];
+            }
+            reinterpret_cast<float4 *>(m)[base + c] = make_float4(mi[0], mi[1], mi[2], mi[3]);
+            reinterpret_cast<float4 *>(v)[base + c] = make_float4(vi[0], vi[1], vi[2], vi[3]);
+            reinterpret_cast<float4 *>(p)[base + c] = make_float4(pi[0], pi[1], pi[2], pi[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_rows_partial_kernel(const float *__restrict__ g, const uint8_t *__restrict__ touched, int V, int H, float *__restrict__ partials) {
+    float acc = 0.0f;
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < V; row += gridDim.x * 8) {
+        if (!touched[row]) continue;
+        const size_t base = (size_t)row * H / 4;
+        for (int c = lane; c < H / 4; c += 32) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(g) + base + c);
+            acc += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+        }
+    }
+    acc = warp_sum(acc);
+    __shared__ float s[8];
+    if (lane == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) partials[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+__global__ void __launch_bounds__(256) zero_rows_kernel(float *__restrict__ g, const uint8_t *__restrict__ touched, int V, int H) {
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < V; row += gridDim.x * 8) {
+        if (!touched[row]) continue;
+        float4 *r = reinterpret_cast<float4 *>(g) + (size_t)row * H / 4;
+        for (int c = lane; c < H / 4; c += 32) r[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
 // Deterministic sum of squares.  The atomicAdd version above adds the block partials in arrival order: the clip
 // coefficient then differs in its last bits from run to run AND from rank to rank -- with data-parallel fine-tuning every
 // rank clips the same all-reduced gradient, and replicas whose coefficients differ by an ulp drift apart
@@ -859,6 +930,61 @@ extern "C" int kbner_pack_bf16(const float *src, uint16_t *dst, size_t n, float 
     if (blocks > 16 * (size_t)num_sms()) blocks = 16 * num_sms();
     pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)src, (uint2 *)dst, n / 4, scale);
     KBNER_CHECK_LAUNCH("pack_bf16");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_mark_rows(const int32_t *ids, size_t n, int V, uint8_t *touched, void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(ids && touched && V > 0, "mark_rows: null pointer");
+    if (n == 0) return KBNER_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 4 * (size_t)num_sms()) blocks = 4 * num_sms();
+    mark_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(ids, n, V, touched);
+    KBNER_CHECK_LAUNCH("mark_rows");
+    return KBNER_OK;
+}
+
+static int rows_grid(int V) {
+    int blocks = (V + 7) / 8;
+    const int cap = 16 * num_sms();
+    return blocks < cap ? blocks : cap;
+}
+
+extern "C" int kbner_adamw_rows(float *p, const float *g, float *m, float *v, const uint8_t *touched, int V, int H, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int step, const float *gscale_dev,
+                                float gscale_host, void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(p && g && m && v && touched && step >= 1, "adamw_rows: bad arguments");
+    KBNER_CHECK_ARG(V > 0 && H > 0 && H % 4 == 0 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15u) == 0,
+                    "adamw_rows: H=%d must be a multiple of 4 and the buffers 16-byte aligned", H);
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+    adamw_rows_kernel<<<rows_grid(V), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, touched, V, H, lr, beta1, beta2, eps, weight_decay,
+                                                                      step_size, gscale_dev, gscale_host);
+    KBNER_CHECK_LAUNCH("adamw_rows");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_sumsq_rows_det(const float *g, const uint8_t *touched, int V, int H, float *partials, int n_partials,
+                                    float *out, void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(g && touched && partials && out && n_partials >= 32, "sumsq_rows_det: null pointer / fewer than 32 partial slots");
+    KBNER_CHECK_ARG(V > 0 && H > 0 && H % 4 == 0 && ((uintptr_t)g & 15u) == 0, "sumsq_rows_det: H=%d / alignment", H);
+    int blocks = rows_grid(V);
+    if (blocks > n_partials) blocks = n_partials;
+    cudaStream_t st = (cudaStream_t)stream;
+    sumsq_rows_partial_kernel<<<blocks, 256, 0, st>>>(g, touched, V, H, partials);
+    KBNER_CHECK_LAUNCH("sumsq_rows_partial");
+    sumsq_final_kernel<<<1, 32, 0, st>>>(partials, blocks, out);
+    KBNER_CHECK_LAUNCH("sumsq_final");
+    return KBNER_OK;
+}
+
+extern "C" int kbner_zero_rows(float *g, const uint8_t *touched, int V, int H, void *stream) {
+    KBNER_NVTX("kbner/train");
+    KBNER_CHECK_ARG(g && touched && V > 0 && H > 0 && H % 4 == 0 && ((uintptr_t)g & 15u) == 0, "zero_rows: bad arguments");
+    zero_rows_kernel<<<rows_grid(V), 256, 0, (cudaStream_t)stream>>>(g, touched, V, H);
+    KBNER_CHECK_LAUNCH("zero_rows");
     return KBNER_OK;
 }
 

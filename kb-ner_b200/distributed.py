@@ -55,7 +55,7 @@ class GradExchange:
              sized for num_sms - KBNER_OVERLAP_SM_CARVEOUT (default 16) SMs (kbner_set_sm_budget): NCCL's channel CTAs
              then have SMs of their own instead of pushing a persistent grid's CTAs into a second wave.
     Without an initialised process group (or world size 1) nothing is exchanged and reduce() returns None.
-    `kernels` (pack / rows_gather / rows_scatter_add) are injectable so the host logic can be exercised with gloo on CPU
+    `kernels` (pack / rows_gather / rows_scatter_add / mark_rows) are injectable so the host logic can be exercised with gloo on CPU
     (tests/test_distributed_cpu.py); the product binds the CUDA ones."""
 
     def __init__(self, encoder, arenas, payload=None, overlap=None, pack=None, kernels=None):
@@ -70,11 +70,12 @@ class GradExchange:
         k = dict(kernels or {})
         if pack is not None:
             k["pack"] = pack
-        if not all(n in k for n in ("pack", "rows_gather", "rows_scatter_add")):
+        if not all(n in k for n in ("pack", "rows_gather", "rows_scatter_add", "mark_rows")):
             from . import ops
             k.setdefault("pack", ops.pack_bf16)
             k.setdefault("rows_gather", ops.rows_gather_bf16)
             k.setdefault("rows_scatter_add", ops.rows_scatter_add_bf16)
+            k.setdefault("mark_rows", ops.mark_rows)
         self._k = k
         self._bufs = {}
         self._handles = []
@@ -106,6 +107,10 @@ class GradExchange:
                             all_rows=torch.empty((world, cap, H), dtype=torch.bfloat16, device=dev))
         if self.encoder is not None:
             self.encoder._ids_hook = self.note_ids
+        # every gradient that reaches the table now arrives with its ids: the optimizer may skip never-touched rows
+        import os
+        if os.environ.get("KBNER_ROW_SKIPPING", "1") != "0" and arena.row_table is None and hasattr(arena, "enable_row_skipping"):
+            arena.enable_row_skipping(table)
         return True
 
     def note_ids(self, ids):
@@ -146,6 +151,9 @@ class GradExchange:
         table_grad = sp["arena"].grad[sp["lo"]:sp["lo"] + sp["V"] * sp["H"]].view(sp["V"], sp["H"])
         for r in range(dist.get_world_size()):                          # rank order: the same sum on every rank
             self._k["rows_scatter_add"](sp["all_rows"][r], sp["all_ids"][r], table_grad)
+        rt = getattr(sp["arena"], "row_table", None)
+        if rt is not None:                                              # rows other ranks touched carry gradient here too
+            self._k["mark_rows"](sp["all_ids"].view(-1), rt["touched"])
         sp["ids"].fill_(-1)
         sp["n"], sp["done"] = 0, False
 

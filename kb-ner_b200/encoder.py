@@ -410,6 +410,7 @@ class ParamArena:
         self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.shadow = None            # bf16 copy of flat[:shadow.numel()] (the tensor-core operands), see make_shadow
         self.shadow_fresh = False     # set by FusedAdamW.step when its launch has just rewritten the shadow
+        self.row_table = None         # row-sparse optimizer passes over one [V,H] table, see enable_row_skipping
         self.offsets = {}
         off = 0
         for p, n in zip(params, sizes):
@@ -448,8 +449,33 @@ class ParamArena:
             n *= s_
         return self.shadow[off:off + n].view(shape)
 
+    def enable_row_skipping(self, table):
+        """The optimizer passes (clip norm, AdamW, zero_grad) over `table` ([V,H] parameter of this arena) visit only rows
+        marked in `touched` -- rows some sentence has embedded since training began (mark_touched).  Unmarked rows have
+        g = m = v = 0 and AdamW (weight decay 0) leaves them unchanged, so the result is bit-identical to the dense passes.
+        Valid while every gradient that reaches the table comes with its ids: single GPU, or the sparse row exchange."""
+        V, H = table.shape
+        lo = self.offsets[id(table)]
+        self.row_table = dict(lo=lo, hi=lo + (V * H + 7) // 8 * 8, V=V, H=H,
+                              touched=torch.zeros(V, dtype=torch.uint8, device=self.flat.device))
+        return self.row_table
+
+    def mark_touched(self, ids):
+        if self.row_table is not None:
+            ops.mark_rows(ids, self.row_table["touched"])
+
+    def table_view(self, buf):
+        rt = self.row_table
+        return buf[rt["lo"]:rt["lo"] + rt["V"] * rt["H"]].view(rt["V"], rt["H"])
+
     def zero_grad(self):
-        self.grad.zero_()
+        rt = self.row_table
+        if rt is None:
+            self.grad.zero_()
+            return
+        self.grad[:rt["lo"]].zero_()
+        ops.zero_rows(self.table_view(self.grad), rt["touched"])
+        self.grad[rt["hi"]:].zero_()
 
 
 def _arena_order(enc):
@@ -575,6 +601,7 @@ def _forward_train(self, ids, key_len):
     hook = getattr(self, "_ids_hook", None)
     if hook is not None:              # the data-parallel exchange records which embedding rows this step touches
         hook(ids)
+    self.arena.mark_touched(ids)      # row-sparse optimizer passes over the word-embedding table (no-op unless enabled)
     if not self._use_graphs:
         return _forward_train_eager(self, ids, key_len)
     R, S = ids.shape

@@ -378,6 +378,40 @@ def pack_bf16(src, dst, scale=1.0):
     return dst
 
 
+def mark_rows(ids, touched):
+    """touched[id] = 1 for every id in ids (int32, any shape; ids outside [0, V) are ignored)."""
+    _chk(ids, torch.int32, "ids")
+    _chk(touched, torch.uint8, "touched", 1)
+    _lib.check(_lib.load().kbner_mark_rows(_ptr(ids), ids.numel(), touched.numel(), _ptr(touched), _stream()), "mark_rows")
+
+
+def adamw_rows(p, g, m, v, touched, lr, beta1, beta2, eps, weight_decay, step, gscale_dev=None, gscale_host=1.0):
+    """AdamW over the marked rows of a [V,H] table (all fp32, same arithmetic as adamw_step)."""
+    for n, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+        _chk(t, torch.float32, n, 2)
+    _chk(touched, torch.uint8, "touched", 1)
+    V, H = p.shape
+    _lib.check(_lib.load().kbner_adamw_rows(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(touched), V, H, float(lr), float(beta1),
+                                            float(beta2), float(eps), float(weight_decay), int(step), _ptr(gscale_dev),
+                                            float(gscale_host), _stream()), "adamw_rows")
+
+
+def sumsq_rows(g, touched, out, partials):
+    """out[0] += sum of squares over the marked rows of g [V,H] fp32, fixed summation order."""
+    _chk(g, torch.float32, "g", 2)
+    _chk(touched, torch.uint8, "touched", 1)
+    _chk(partials, torch.float32, "partials", 1)
+    _lib.check(_lib.load().kbner_sumsq_rows_det(_ptr(g), _ptr(touched), g.shape[0], g.shape[1], _ptr(partials), partials.numel(),
+                                                _ptr(out), _stream()), "sumsq_rows")
+    return out
+
+
+def zero_rows(g, touched):
+    _chk(g, torch.float32, "g", 2)
+    _chk(touched, torch.uint8, "touched", 1)
+    _lib.check(_lib.load().kbner_zero_rows(_ptr(g), _ptr(touched), g.shape[0], g.shape[1], _stream()), "zero_rows")
+
+
 def rows_gather_bf16(src, ids, rows, zero_src=False):
     """rows[i] = bf16(src[ids[i]]) (zeros where ids[i] < 0); zero_src clears the gathered source rows.  src fp32 [V,H]."""
     _chk(src, torch.float32, "src", 2)

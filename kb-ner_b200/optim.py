@@ -34,21 +34,35 @@ class FusedAdamW:
         self._partials = torch.zeros(2048, dtype=torch.float32, device=dev)    # fixed-order norm: same bits on every rank
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
 
-    @staticmethod
-    def _segments(arena, grads, i):
+    def _segments(self, arena, grads, i):
         """The gradient of group i as (lo, hi, buffer) segments of its arena: the arena's own fp32 .grad, one exchanged
-        buffer, or the segment list GradExchange returns when the embedding table's rows went the sparse way."""
+        buffer, or the segment list GradExchange returns when the embedding table's rows went the sparse way.  With row
+        skipping enabled on the arena (ParamArena.enable_row_skipping) the local fp32 gradient is split around the table."""
         n = arena.grad.numel()
+        rt = arena.row_table
         if grads is None:
-            return [(0, n, arena.grad)]
+            if rt is None or self.weight_decay != 0.0:
+                return [(0, n, arena.grad)]
+            segs = [(0, rt["lo"], arena.grad[:rt["lo"]]), (rt["lo"], rt["hi"], arena.grad[rt["lo"]:rt["hi"]]),
+                    (rt["hi"], n, arena.grad[rt["hi"]:])]
+            return [sg for sg in segs if sg[1] > sg[0]]
         g = grads[i]
         return [(lo, hi, t) for lo, hi, t in g if hi > lo] if isinstance(g, (list, tuple)) else [(0, n, g)]
+
+    def _is_table(self, arena, lo, hi, t):
+        rt = arena.row_table
+        return (rt is not None and self.weight_decay == 0.0 and lo == rt["lo"] and hi == rt["hi"] and t.dtype == torch.float32)
 
     def _norm_into_sumsq(self, grads):
         self._sumsq.zero_()
         for i, g in enumerate(self.groups):
-            for _, _, t in self._segments(g["arena"], grads, i):
-                ops.sumsq(t, self._sumsq, self._partials)
+            ar = g["arena"]
+            for lo, hi, t in self._segments(ar, grads, i):
+                if self._is_table(ar, lo, hi, t):
+                    rt = ar.row_table
+                    ops.sumsq_rows(t[:rt["V"] * rt["H"]].view(rt["V"], rt["H"]), rt["touched"], self._sumsq, self._partials)
+                else:
+                    ops.sumsq(t, self._sumsq, self._partials)
 
     def grad_norm(self, grad_scale=1.0, grads=None):
         """Global L2 norm of (grad * grad_scale) over all arenas -- a device tensor, no sync."""
@@ -71,6 +85,13 @@ class FusedAdamW:
             ar = g["arena"]
             ns = 0 if ar.shadow is None else ar.shadow.numel()
             for lo, hi, t in self._segments(ar, grads, i):
+                if self._is_table(ar, lo, hi, t):         # marked rows only: the rest of the table has g = m = v = 0
+                    rt = ar.row_table
+                    tv = lambda b: b[lo:lo + rt["V"] * rt["H"]].view(rt["V"], rt["H"])
+                    ops.adamw_rows(tv(ar.flat), t[:rt["V"] * rt["H"]].view(rt["V"], rt["H"]), tv(g["m"]), tv(g["v"]), rt["touched"],
+                                   g["lr"], self.betas[0], self.betas[1], self.eps, self.weight_decay, self.steps,
+                                   gscale_dev=coef, gscale_host=grad_scale)
+                    continue
                 ops.adamw_step(ar.flat[lo:hi], t, g["m"][lo:hi], g["v"][lo:hi], g["lr"], self.betas[0], self.betas[1], self.eps,
                                self.weight_decay, self.steps, gscale_dev=coef, gscale_host=grad_scale,
                                shadow=ar.shadow[lo:min(hi, ns)] if lo < ns else None)
@@ -91,10 +112,19 @@ class FusedAdamW:
             g["lr"] = g["base_lr"] * f
 
 
-def build_reference_optimizer(tagger, lr=5e-6, lr_rate=10000.0, **kw):
-    """The reference's two groups for a FastSequenceTagger on TransformerWordEmbeddings (finetune_trainer.py:552-571)."""
+def build_reference_optimizer(tagger, lr=5e-6, lr_rate=10000.0, row_skipping=None, **kw):
+    """The reference's two groups for a FastSequenceTagger on TransformerWordEmbeddings (finetune_trainer.py:552-571).
+    row_skipping (default: on for a single process, KBNER_ROW_SKIPPING=0 turns it off): the optimizer passes over the
+    word-embedding table visit only rows that were ever embedded (ParamArena.enable_row_skipping); data-parallel runs
+    switch it on when their gradient exchange sends that table as rows (GradExchange.enable_sparse_rows)."""
+    import os
     enc = tagger.embeddings.embeddings[0].model
     enc_arena = enc.ensure_arena()
+    if row_skipping is None:
+        distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        row_skipping = os.environ.get("KBNER_ROW_SKIPPING", "1") != "0" and not distributed
+    if row_skipping and kw.get("weight_decay", 0.0) == 0.0 and enc_arena.row_table is None:
+        enc_arena.enable_row_skipping(enc.embeddings.word_embeddings.weight)
     head_arena = ParamArena([tagger.linear.weight, tagger.linear.bias])
     crf_arena = ParamArena([tagger.transitions])
     tagger._head_arena, tagger._crf_arena = head_arena, crf_arena

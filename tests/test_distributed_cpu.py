@@ -106,8 +106,10 @@ def _worker(rank, world, port, q):
     sar.grad[tl:tl + V * Hd] = dense_table.reshape(-1)
     sar.grad[:24] = float(rank + 1)
     sar.grad[tl + V * Hd:] = float(10 * (rank + 1))
+    def mark_rows(ids, touched):
+        touched[ids[ids >= 0].long()] = 1
     ex = GradExchange(None, [sar], payload="bf16", overlap=False,
-                      kernels=dict(pack=pack, rows_gather=rows_gather, rows_scatter_add=rows_scatter_add))
+                      kernels=dict(pack=pack, rows_gather=rows_gather, rows_scatter_add=rows_scatter_add, mark_rows=mark_rows))
     sparse_on = ex.enable_sparse_rows(sar, table, cap_tokens=8)
     ex.note_ids(my_ids[:4].view(2, 2))
     ex.note_ids(my_ids[4:].view(1, 2))
@@ -125,7 +127,10 @@ def _worker(rank, world, port, q):
                  and segs[0][2].dtype == torch.bfloat16
                  and torch.allclose(got[tl:tl + V * Hd].view(V, Hd), want_table)
                  and bool((got[:24] == total).all()) and bool((got[tl + V * Hd:] == 10 * total).all())
-                 and ex._sparse["n"] == 0 and bool((ex._sparse["ids"] == -1).all()))
+                 and ex._sparse["n"] == 0 and bool((ex._sparse["ids"] == -1).all())
+                 # the exchange switched the arena's row skipping on and marked the rows ANY rank touched
+                 and sar.row_table is not None
+                 and bool((sar.row_table["touched"].bool() == (want_table.abs().sum(1) > 0)).all()))
     q.put((rank, allidx, counts, errs, norm, overlap_ok and sparse_ok))
     dist.destroy_process_group()
 

@@ -351,3 +351,51 @@ def test_hf_saved_model_hidden_states_match_transformers(tmp_path):
             res[mode] = max(_rel(got[r, :n], want[r, :n]) for r, n in enumerate(lens))
     print("vs transformers.XLMRobertaModel:", res)
     assert res["bf16"] < 1e-2 and res["bf16x3"] < NORTH_STAR_TOL, res
+
+
+@pytest.mark.parametrize("clip", [None, 1.0])
+def test_row_skipping_optimizer_matches_the_dense_passes(clip):
+    """ParamArena.enable_row_skipping: clip norm / AdamW / zero_grad over the marked rows of an embedding table only.  Without
+    clipping the parameters are BIT-identical to the dense passes (same arithmetic per element; untouched rows have g = m = v =
+    0); with clipping the two norms differ in summation order only (<= 1 ulp of the coefficient)."""
+    from kbner_b200 import ops
+    from kbner_b200.encoder import ParamArena
+    from kbner_b200.optim import FusedAdamW
+    torch.manual_seed(4)
+    V, H = 500, 256
+
+    def make():
+        g = torch.Generator(device="cuda").manual_seed(9)
+        ps = [torch.nn.Parameter(torch.randn(40, 8, device="cuda", generator=g)),
+              torch.nn.Parameter(torch.randn(V, H, device="cuda", generator=g) * 0.02),
+              torch.nn.Parameter(torch.randn(16, device="cuda", generator=g))]
+        ar = ParamArena(ps)
+        return ps, ar, FusedAdamW([{"arena": ar, "lr": 1e-3}], max_grad_norm=clip)
+    (pd, ad, od), (ps_, as_, os_) = make(), make()
+    as_.enable_row_skipping(ps_[1])
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(6):
+        ids = torch.randint(0, V, (3, 11), device="cuda", generator=gen).to(torch.int32)
+        rows = torch.randn(33, H, device="cuda", generator=gen)
+        g0, g2 = torch.randn(40, 8, device="cuda", generator=gen), torch.randn(16, device="cuda", generator=gen)
+        for ps, ar in ((pd, ad), (ps_, as_)):
+            ps[0].grad.copy_(g0)
+            ps[2].grad.copy_(g2)
+            ps[1].grad.index_add_(0, ids.view(-1).long(), rows)           # what embed_ln_bwd does: scatter-add per token
+        as_.mark_touched(ids)
+        if step == 4:                                                    # a step in which the table receives no gradient at all:
+            for ps in (pd, ps_):                                         # rows touched earlier keep moving on their momentum
+                ps[1].grad.zero_()
+        od.step(grad_scale=0.5)
+        os_.step(grad_scale=0.5)
+        if clip is None:
+            assert torch.equal(ad.flat, as_.flat), step
+        else:
+            assert torch.allclose(ad.flat, as_.flat, rtol=2e-6, atol=1e-9), step
+        od.zero_grad()
+        os_.zero_grad()
+        assert float(as_.grad.abs().max()) == 0.0 and float(ad.grad.abs().max()) == 0.0
+    touched = as_.row_table["touched"]
+    assert 0 < int(touched.sum()) < V                                    # some rows were never embedded: they never moved
+    never = ~touched.bool()
+    assert torch.equal(ps_[1].detach()[never], pd[1].detach()[never])
