@@ -37,8 +37,10 @@ def main():
         for tok in s.tokens:
             tok.add_tag("ner", "S-T0" if tok.text[0] in "abcde" else "O")
     trainer = ModelFinetuner(tagger, corpus=ListCorpus(sents, [], []))
+    # two epochs = two optimizer steps: the second replays the captured forward / backward (chunk) graphs and steps rows of
+    # the embedding table that carry momentum from the first
     trainer.train(os.path.join(out_dir, "run-%d-%d" % (n_ranks, rank)), learning_rate=1e-3, lr_rate=10.0,
-                  mini_batch_size=B if not single else B * single, max_epochs=1, gradient_accumulation_steps=1,
+                  mini_batch_size=B if not single else B * single, max_epochs=2, gradient_accumulation_steps=1,
                   shuffle=False, save_final_model=False, train_with_dev=True)
     sd = {k: v.detach().float().cpu().clone() for k, v in tagger.state_dict().items()}
     torch.save(sd, os.path.join(out_dir, "params-%s-rank%d.pt" % ("single" if single else "ddp", rank)))

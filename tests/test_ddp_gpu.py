@@ -20,14 +20,16 @@ def _run(cmd, env=None):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("payload", ["bf16", "fp32"])
-def test_two_ranks_equal_one_rank_with_the_doubled_batch(tmp_path, payload):
+@pytest.mark.parametrize("payload,overlap", [("bf16", "0"), ("fp32", "0"), ("bf16", "1")])
+def test_two_ranks_equal_one_rank_with_the_doubled_batch(tmp_path, payload, overlap):
+    """payload bf16 = packed buffers + sparse embedding rows + row-skipping optimizer; fp32 = dense in-place all-reduce;
+    overlap 1 = the chunked backward with the exchange of finished layer chunks started under the next one."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     worker = os.path.join(HERE, "ddp_worker.py")
     port = str(29700 + os.getpid() % 200)
     _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-          "--master-port", port, worker, str(tmp_path)], env={"KBNER_GRAD_COMM": payload})
+          "--master-port", port, worker, str(tmp_path)], env={"KBNER_GRAD_COMM": payload, "KBNER_OVERLAP_ALLREDUCE": overlap})
     _run([sys.executable, worker, str(tmp_path), "--single", "2"], env={"CUDA_VISIBLE_DEVICES": "0"})
     r0 = torch.load(tmp_path / "params-ddp-rank0.pt")
     r1 = torch.load(tmp_path / "params-ddp-rank1.pt")
@@ -43,4 +45,5 @@ def test_two_ranks_equal_one_rank_with_the_doubled_batch(tmp_path, payload):
         worst = max(worst, frac_off)
         assert frac_off < (0.02 if payload == "bf16" else 0.01), (k, frac_off)
         assert float(diff.mean()) < 0.05, (k, float(diff.mean()))
-    print("DDP vs single (%s payload): worst fraction of elements whose update differs by > lr/4: %.4f" % (payload, worst))
+    print("DDP vs single (%s payload, overlap %s): worst fraction of elements whose update differs by > lr/4: %.4f"
+          % (payload, overlap, worst))
