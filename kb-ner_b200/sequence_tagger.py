@@ -302,6 +302,15 @@ class SequenceTagger(torch.nn.Module):
         return logz
 
     def _score_sentence(self, feats, tags, lens_, mask=None):
+        """Gold-path score (:2544-2591).  The reference multiplies by `mask` ([B,T], 1 on real tokens); its masks are
+        left-packed prefix masks, for which that equals scoring the first mask.sum(1) tokens -- a mask that is not a prefix
+        mask (remove-X before compaction) has to go through _calculate_loss, which compacts first like the reference."""
+        if mask is not None:
+            m = torch.as_tensor(mask).to(self.device) != 0
+            n = m.sum(1)
+            if bool((m != (torch.arange(m.shape[1], device=m.device)[None, :] < n[:, None])).any()):
+                raise ValueError("_score_sentence: mask must be a prefix mask (compact with _calculate_loss / crf_compact first)")
+            lens_ = n
         lens_ = torch.as_tensor(lens_).to(torch.int32).to(self.device)
         _, gold, _ = ops.crf_nll_fwd(feats.detach().float().contiguous(), tags.to(torch.int32).contiguous(),
                                      self.transitions.detach().contiguous(), lens_, self.start_idx, self.stop_idx)
