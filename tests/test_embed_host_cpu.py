@@ -91,3 +91,37 @@ def test_build_batch_accepts_the_references_own_sentence_objects():
         assert torch.equal(a, b)
     assert got[4] == want[4] and got[5] == want[5]
     assert hasattr(RefBatched(ref_sents), "features")          # what embed() writes its EncodedBatch into
+
+
+def test_per_word_piece_cache_agrees_with_the_sentence_level_algorithm():
+    """The per-word fast path of subtokenize is only used after it has agreed with the reference's sentence-level matching on
+    the first sentences; here: on every golden case (dropped words, <EOS>, truncation to maximum_subtoken_length, windows) the
+    two paths give the same ids / n_sub, a verified instance answers from the per-word cache, and a tokenizer whose pieces
+    DO depend on the neighbouring word switches the fast path off."""
+    from fake_tokenizer import FakeSentencePieceTokenizer
+    from kbner_b200.data import Sentence
+    g = _load()
+    for case in g["cases"]:
+        emb = _embeddings(case["options"], g["tokenizer"])
+        for w in case["sentences"]:
+            words = [emb._eos_text() if x == "<EOS>" else x for x in w]
+            assert emb._subtokenize_by_word(words) == emb._subtokenize_words(words), case["name"]
+        assert emb._by_word is None
+    emb = _embeddings({}, g["tokenizer"])
+    emb._verify_left = 2
+    s1, s2, s3 = (Sentence(tokens=["alpha", "beta%d" % i, "gamma"]) for i in range(3))
+    want = [emb._subtokenize_words([t.text for t in s.tokens]) for s in (s1, s2, s3)]
+    assert [emb.subtokenize(s) for s in (s1, s2)] == want[:2] and emb._by_word is True
+    calls = []
+    real = emb.tokenizer.tokenize
+    emb.tokenizer.tokenize = lambda text: (calls.append(text), real(text))[1]
+    assert emb.subtokenize(s3) == want[2] and calls == ["beta2"]          # only the never-seen word reached the tokenizer
+
+    class Contextual(FakeSentencePieceTokenizer):                        # merges a word with its left neighbour's last letter
+        def tokenize(self, text):
+            ws = text.split()
+            return [p for i, w in enumerate(ws) for p in super(Contextual, self).tokenize(w if i == 0 else w + ws[i - 1][-1:])]
+    emb = _embeddings({}, g["tokenizer"])
+    emb.tokenizer = Contextual(**g["tokenizer"])
+    emb.subtokenize(Sentence(tokens=["abc", "def", "ghi"]))
+    assert emb._by_word is False
