@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from .data import BatchedData, Dictionary, Label, LabelSeq, Sentence
-from .training_utils import Metric, Result, span_counts, store_embeddings
+from .training_utils import Metric, Result, frozen_gc, span_counts, store_embeddings
 
 log = logging.getLogger("kbner_b200")
 
@@ -337,6 +337,10 @@ class SequenceTagger(torch.nn.Module):
         """-> (Result, eval_loss) like the reference (:2593-2729): per-class span counts in a Metric, the remove-X filter
         (:2653-2672) when self.remove_x, the prediction file "text gold pred score" streamed to out_path."""
         self.eval()
+        with frozen_gc():
+            return self._evaluate(data_loader, out_path, embeddings_storage_mode, prediction_mode, speed_test, materialize_labels)
+
+    def _evaluate(self, data_loader, out_path, embeddings_storage_mode, prediction_mode, speed_test, materialize_labels):
         eval_loss, batches = 0.0, 0
         n_sent, t0 = 0, time.time()
         if speed_test:

@@ -35,7 +35,7 @@ import torch
 from .data import BatchedData
 from .distributed import GradExchange, allreduce_counts, shard_indices
 from .optim import build_reference_optimizer
-from .training_utils import Metric
+from .training_utils import Metric, frozen_gc
 
 log = logging.getLogger("kbner_b200")
 
@@ -110,6 +110,7 @@ class ModelFinetuner:
             emb.train()
             opt.zero_grad()
             seen, t0, run_loss = 0, time.time(), 0.0
+            gc_guard = frozen_gc().__enter__()          # the corpus is long-lived: keep the per-batch collections off it
             for bi, batch in enumerate(mine):
                 batch.features = {}
                 tail = len(mine) - (len(mine) // gradient_accumulation_steps) * gradient_accumulation_steps
@@ -128,6 +129,7 @@ class ModelFinetuner:
                     log.info("epoch %d - iter %d/%d - loss %.6f - samples/sec: %.2f", epoch + 1, bi + 1, len(mine),
                              run_loss, seen / max(time.time() - t0, 1e-9))
                 batch.features = {}
+            gc_guard.__exit__(None, None, None)
             entry = {"epoch": epoch + 1, "train_samples_per_sec": seen * world / max(time.time() - t0, 1e-9)}
             if not train_with_dev and getattr(self.corpus, "dev", None):
                 result, dev_loss = self.evaluate_split(self.corpus.dev, eval_mini_batch_size or mini_batch_size)
