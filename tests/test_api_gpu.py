@@ -376,3 +376,60 @@ def test_finetune_steps_reduce_loss():
     print("finetune losses:", [round(x, 3) for x in losses])
     assert losses[-1] < losses[0] * 0.9, losses
     assert all(np.isfinite(losses))
+
+
+def test_graph_caches_are_bounded_and_survive_shape_churn():
+    """the per-shape CUDA-graph caches must not grow with the number of distinct (R, S) shapes, a captured graph
+    must own its workspace (an eager call with another shape in between must not corrupt a later replay), and rebuilding
+    the compute copies must drop every graph."""
+    tagger, emb, params, ocfg = _models(SMALL, 13, seed=6)
+    enc = emb.model
+    enc._graph_cap = 3
+    torch.manual_seed(0)
+    shapes = [(2, 32), (3, 48), (1, 64), (4, 40), (2, 72), (5, 24)]
+    want = {}
+    for R, S in shapes:
+        ids = torch.randint(3, 1000, (R, S), dtype=torch.int32, device="cuda")
+        kl = torch.full((R,), S, dtype=torch.int32, device="cuda")
+        enc._use_graphs = False
+        want[(R, S)] = (ids, kl, enc.forward_hidden(ids, kl).clone())
+        enc._use_graphs = True
+    for rnd in range(3):                       # round 0: eager + register, round 1: capture, round 2: replay (or re-register)
+        for R, S in shapes:
+            ids, kl, ref = want[(R, S)]
+            got = enc.forward_hidden(ids, kl)
+            assert torch.equal(got, ref), (rnd, R, S)
+            assert len(enc._graphs) <= 3
+    # a graph captured for one shape, another shape run eagerly in between (its workspace replaces the eager one), replay
+    ids, kl, ref = want[(2, 32)]
+    for _ in range(3):
+        enc.forward_hidden(ids, kl)
+    big = torch.randint(3, 1000, (6, 96), dtype=torch.int32, device="cuda")
+    enc.forward_hidden(big, torch.full((6,), 96, dtype=torch.int32, device="cuda"))
+    junk = torch.full((4096, 4096), 7.0, device="cuda")          # lands wherever the allocator has free blocks
+    assert torch.equal(enc.forward_hidden(ids, kl), ref)
+    assert float(junk.min()) == 7.0 and float(junk.max()) == 7.0
+    gen = enc._gen
+    enc.sync_compute_weights()
+    assert len(enc._graphs) == 0 and enc._gen > gen
+
+
+def test_re_evaluating_the_same_batches_re_encodes():
+    """an EncodedBatch aliases the encoder's buffers, so embed() must not short-circuit on a cached one --
+    evaluating the same loader twice (and a different batch in between) has to give the same labels both times."""
+    from kbner_b200.data import BatchedData
+    tagger, emb, params, ocfg = _models(SMALL, 13, seed=8)
+    a, b = BatchedData(_sentences(4, 5, 30, seed=1)), BatchedData(_sentences(4, 5, 30, seed=2))
+    with torch.no_grad():
+        tagger.evaluate([a, b], speed_test=True, prediction_mode=True)
+        first = [ls.tag_indices() for ls in tagger.last_labels]
+        fa = tagger.forward(a)
+        la, _ = tagger._obtain_labels(fa, a)
+        tagger.forward(b)                                     # another batch overwrites the encoder's buffers
+        fa2 = tagger.forward(a)                               # a.features still holds the old EncodedBatch: must re-encode
+        la2, _ = tagger._obtain_labels(fa2, a)
+        tagger.evaluate([a, b], speed_test=True, prediction_mode=True)
+        second = [ls.tag_indices() for ls in tagger.last_labels]
+    assert torch.equal(fa, fa2)
+    assert [x.tag_indices() for x in la] == [x.tag_indices() for x in la2]
+    assert first == second
