@@ -8,7 +8,7 @@ python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { ta
 timeout 300 python scripts/attn_bench.py > $OUT/attn_bench.json 2>$OUT/attn.err; cat $OUT/attn_bench.json
 timeout 300 python scripts/train_kernels_bench.py > $OUT/train_kernels.json 2>>$OUT/attn.err; tail -c 1500 $OUT/train_kernels.json; echo
 # launch lists (graphs off so that ncu sees every kernel by name)
-KBNER_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kbner -c 400 --csv --log-file $OUT/launches_infer.csv \
+KBNER_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'attention_|crf_|embed_ln|gather_tagproj|gemm_|layernorm' -c 400 --csv --log-file $OUT/launches_infer.csv \
     python bench.py --steps 2 --warmup 3 --workload infer --no-cpu > $OUT/ncu_infer.log 2>&1; echo "ncu infer rc=$?"
 KBNER_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_train.csv \
     python bench.py --steps 4 --warmup 3 --workload train > $OUT/ncu_train.log 2>&1; echo "ncu train rc=$?"
