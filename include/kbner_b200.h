@@ -129,6 +129,27 @@ int kbner_gemm_bias_resid_layernorm(const uint16_t *A, const uint16_t *W, const 
                                     int M, int N, int K, int lda, int ldw, void *stream);
 int kbner_gemm_ln_resident_clusters(int N);
 
+/* The same fusion with a caller-owned workspace: picks between the cluster kernel above (several rounds of tiles) and the
+ * grid kernel (csrc/gemm_ln_grid_tcgen05.cu; one round: M * N <= 256 * 256 * CTA pairs) -- kbner_gemm_ln_grid is the grid
+ * kernel itself, for every shape.  Grid kernel: a work item is one 256 x 256 tile, every CTA pair walks
+ * its items with double-buffered TMEM accumulators (the main loop of the next tile runs under the LayerNorm epilogue of this
+ * one), and the N/256 pairs that hold the column tiles of one 256-row panel exchange their per-row (mean, M2) partials
+ * through `workspace` (one 16-byte slot {mean, tag, M2, tag} per partial, tag = the workspace's launch epoch + 1) instead
+ * of through a cluster's distributed shared memory.  `workspace`: kbner_gemm_ln_workspace_bytes(M, N) bytes of DEVICE memory,
+ * 16-byte aligned, zeroed ONCE by the caller (the last CTA of a launch bumps the epoch, so a captured graph replays with the
+ * same buffer);
+ * two launches that may run concurrently need separate workspaces.  Same operands, results and call site as above. */
+size_t kbner_gemm_ln_workspace_bytes(int M, int N);
+int kbner_gemm_bias_resid_layernorm_ws(const uint16_t *A, const uint16_t *W, const float *bias, const uint16_t *resid,
+                                       const float *gamma, const float *beta, float eps, uint16_t *Y /*[M,N] bf16*/,
+                                       int M, int N, int K, int lda, int ldw, void *workspace, size_t workspace_bytes,
+                                       void *stream);
+int kbner_gemm_ln_grid(const uint16_t *A, const uint16_t *W, const float *bias, const uint16_t *resid, const float *gamma,
+                       const float *beta, float eps, uint16_t *Y /*[M,N] bf16*/, int M, int N, int K, int lda, int ldw,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* Debug: clock64 stamps of the kernel's warps (148 x 10 x 8 x 8 uint64 of device memory; NULL = off). */
+int kbner_debug_gemm_ln_timeline(void *buf);
+
 /* In-place element-wise dropout with the same counter-hash mask (XLMRobertaEmbeddings.dropout: bf16 activations in the
  * forward, fp32 gradient in the backward). */
 int kbner_dropout_apply(void *x /*[M,H] bf16 or fp32*/, int is_f32, int M, int H, const uint32_t *drop_seed,

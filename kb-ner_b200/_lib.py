@@ -40,6 +40,11 @@ SIGNATURES = {
                                     _c_int),
     "kbner_gemm_bias_resid_layernorm": ([_c_void_p] * 6 + [_c_float, _c_void_p] + [_c_int] * 5 + [_c_void_p], _c_int),
     "kbner_gemm_ln_resident_clusters": ([_c_int], _c_int),
+    "kbner_gemm_ln_grid": ([_c_void_p] * 6 + [_c_float, _c_void_p] + [_c_int] * 5 + [_c_void_p, ctypes.c_size_t, _c_void_p], _c_int),
+    "kbner_debug_gemm_ln_timeline": ([_c_void_p], _c_int),
+    "kbner_gemm_ln_workspace_bytes": ([_c_int, _c_int], ctypes.c_size_t),
+    "kbner_gemm_bias_resid_layernorm_ws": ([_c_void_p] * 6 + [_c_float, _c_void_p] + [_c_int] * 5 + [_c_void_p, ctypes.c_size_t, _c_void_p],
+                                           _c_int),
     "kbner_embed_ln_fwd_ex": ([_c_void_p] * 6 + [_c_float, _c_int] + [_c_int] * 5 + [_c_void_p] * 2 + [_c_int, _c_void_p], _c_int),
     "kbner_add_layernorm_fwd_res32": ([_c_void_p] * 5 + [_c_float, _c_int, _c_int] + [_c_void_p] * 2 + [_c_int, _c_void_p], _c_int),
     "kbner_bias_gelu_split": ([_c_void_p] * 2 + [_c_int] * 2 + [_c_void_p] * 2, _c_int),

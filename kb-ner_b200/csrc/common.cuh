@@ -107,6 +107,28 @@ __device__ __forceinline__ void fadd2(float &s0, float &s1, float a0, float a1) 
         "mov.b64 {%0, %1}, rd;}"
         : "+f"(s0), "+f"(s1) : "f"(a0), "f"(a1));
 }
+// the same packed ops on values that STAY pairs (64-bit registers) across several instructions
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -147,6 +169,16 @@ static inline Dropout make_dropout(const uint32_t *seed, uint32_t site, float p)
         d.seed = nullptr;
     }
     return d;
+}
+
+// Chan et al.: merge (n_b, mean_b, M2_b) into (n_a, mean_a, M2_a)
+__device__ __forceinline__ void chan_merge(float &n_a, float &mean_a, float &m2_a, float n_b, float mean_b, float m2_b) {
+    const float n = n_a + n_b;
+    const float delta = mean_b - mean_a;
+    const float f = n_b / n;
+    mean_a = fmaf(delta, f, mean_a);
+    m2_a = m2_a + m2_b + delta * delta * n_a * f;
+    n_a = n;
 }
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------

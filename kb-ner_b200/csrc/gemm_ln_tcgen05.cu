@@ -89,30 +89,6 @@ __device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t *bar, uint32_t pa
         }
     }
 }
-// Chan et al.: merge (n_b, mean_b, M2_b) into (n_a, mean_a, M2_a)
-__device__ __forceinline__ void chan_merge(float &n_a, float &mean_a, float &m2_a, float n_b, float mean_b, float m2_b) {
-    const float n = n_a + n_b;
-    const float delta = mean_b - mean_a;
-    const float f = n_b / n;
-    mean_a = fmaf(delta, f, mean_a);
-    m2_a = m2_a + m2_b + delta * delta * n_a * f;
-    n_a = n;
-}
-
-// registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns (inverse of tmem_ld_32x32b_x32)
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // Cluster = `npairs` CTA pairs; pair p owns T = tiles_per_pair consecutive 256-column tiles (columns p*T*256 ...), one TMEM
 // accumulator buffer per tile.  Per 256-row panel:
 //   MMA      tile 0 -> TMEM buffer 0, tile 1 -> buffer 1                        (T = 1: buffers alternate between panels)
@@ -307,7 +283,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             sm += z;
                         }
                     }
-                    tmem_st_32x32b_x32(taddr0 + c * 32, r);
+                    ptx::tmem_st_32x32b_x32(taddr0 + c * 32, r);
                     const float cm = sm * (1.0f / 32.0f);
                     float sq = 0.0f;
 #pragma unroll
@@ -315,7 +291,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (j == 0 && c == 0) { n_a = 32.0f; mean_a = cm; m2_a = sq; }
                     else chan_merge(n_a, mean_a, m2_a, 32.0f, cm, sq);
                 }
-                tmem_st_wait();
+                ptx::tmem_st_wait();
             }
             // ---- publish the partial to the CTAs that hold the same rows (same parity in every pair), then collect
             const int sbuf = it & 1;

@@ -33,13 +33,19 @@
 
 namespace kbner {
 
-constexpr int BM = 256, BN = 256, BK = 64, kStages = 5;
+// Tile width TN (template): 256.  The 128-wide instantiation exists to measure whether finer tiles pay where 256-wide ones
+// quantise badly onto the 74 CTA pairs (M = 4096 x N = 4096: 3.46 rounds -> 4 against 6.92 half-rounds -> 7): they do not
+// (pick_tile_n below).
+constexpr int BM = 256, BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr uint32_t kABytes = 128 * BK * 2, kBBytes = 128 * BK * 2;   // per CTA per stage
+constexpr uint32_t kABytes = 128 * BK * 2;                           // per CTA per stage
 constexpr uint32_t kTmemCols = 512;
 
-struct GemmSmem {
+template <int TN>
+struct GemmSmemT {
+    static constexpr int kStages = TN == 256 ? 5 : 6;
+    static constexpr uint32_t kBBytes = (TN / 2) * BK * 2;           // per CTA per stage: half of the pair's B tile
     uint8_t a[kStages][kABytes];
     uint8_t b[kStages][kBBytes];
     uint8_t cstage[kEpiWarps][2][4096];     // per epilogue warp: 2 x (32 rows x 128 B) SWIZZLE_128B store staging
@@ -51,23 +57,49 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 output ulp): 2 MUFU + ~12 FMA-pipe ops,
-// about half of erff().  HF "gelu" = x * 0.5 * (1 + erf(x / sqrt(2))).
-__device__ __forceinline__ float erf_as(float x) {
-    const float ax = fabsf(x);
-    const float t = rcp_fast(fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = ex2_fast(-1.4426950408889634f * ax * ax);
-    return copysignf(fmaf(-p, e, 1.0f), x);
+// HF "gelu" = x * Phi(x), Phi the standard normal CDF (transformers' erf GELU, not the tanh form).  Evaluated from the
+// upper-tail probability Q(u) = Phi(-u) = 2^p(u), u = min(|x|, 6), p a degree-6 polynomial fitted to log2 Q on [0, 6]
+// (relative error of Q <= 4.8e-5 with fp32 Horner; fit script: scripts/fit_gelu_tail.py):
+//     gelu(x)  = max(x, 0) - u * Q(u)                       (|error| <= 6.7e-6 absolute, far below the bf16 output ulp)
+//     gelu'(x) = Phi(x) + x * phi(x),  Phi(x) = x >= 0 ? 1 - Q(u) : Q(u),  phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi)
+// on PAIRS of columns: the polynomial runs as packed fp32 FMAs (FFMA2), one MUFU.EX2 per element (two for the gradient).
+// The first version (Abramowitz-Stegun 7.1.26 on rcp.approx + ex2.approx, scalar) cost ~17 issue slots and 2 MUFU per
+// element and made the FFN-up epilogue longer than its main loop: 33.2 us at 4096 x 4096 x 1024 against 26.4 us with the
+// bias-only epilogue (profiles/r02/gemm_tile_width.json).
+__device__ __forceinline__ void gelu_tail2(float x0, float x1, float &u0, float &u1, float &q0, float &q1) {
+    u0 = fminf(fabsf(x0), 6.0f);
+    u1 = fminf(fabsf(x1), 6.0f);
+    const uint64_t u = f2_pack(u0, u1);
+    uint64_t p = f2_fma(u, f2_pack(2.2990062444007588e-05f, 2.2990062444007588e-05f), f2_pack(-0.0006111000751876989f, -0.0006111000751876989f));
+    p = f2_fma(p, u, f2_pack(0.007195565982293077f, 0.007195565982293077f));
+    p = f2_fma(p, u, f2_pack(-0.05118533844324097f, -0.05118533844324097f));
+    p = f2_fma(p, u, f2_pack(-0.46127192160306274f, -0.46127192160306274f));
+    p = f2_fma(p, u, f2_pack(-1.150174258384186f, -1.150174258384186f));
+    p = f2_fma(p, u, f2_pack(-1.0000647888776388f, -1.0000647888776388f));
+    float p0, p1;
+    f2_unpack(p, p0, p1);
+    q0 = ex2_fast(p0);
+    q1 = ex2_fast(p1);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
-// d/dx gelu(x) = 0.5 (1 + erf(x/sqrt2)) + x * exp(-x^2/2) / sqrt(2 pi)
-__device__ __forceinline__ float gelu_grad(float x) {
-    return fmaf(x * 0.3989422804014327f, ex2_fast(-0.7213475204444817f * x * x), 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f)));
+__device__ __forceinline__ void gelu_erf2(float &x0, float &x1) {
+    float u0, u1, q0, q1;
+    gelu_tail2(x0, x1, u0, u1, q0, q1);
+    x0 = fmaf(-u0, q0, fmaxf(x0, 0.0f));
+    x1 = fmaf(-u1, q1, fmaxf(x1, 0.0f));
+}
+// (d0, d1) *= gelu'(x0), gelu'(x1)
+__device__ __forceinline__ void gelu_grad_mul2(float &d0, float &d1, float x0, float x1) {
+    float u0, u1, q0, q1;
+    gelu_tail2(x0, x1, u0, u1, q0, q1);
+    const uint64_t x = f2_pack(x0, x1);
+    float t0, t1;
+    f2_unpack(f2_mul(f2_mul(x, f2_pack(-0.7213475204444817f, -0.7213475204444817f)), x), t0, t1);
+    const float e0 = ex2_fast(t0), e1 = ex2_fast(t1);
+    const float c0 = x0 >= 0.0f ? 1.0f - q0 : q0, c1 = x1 >= 0.0f ? 1.0f - q1 : q1;
+    float g0, g1;
+    f2_unpack(f2_fma(f2_mul(x, f2_pack(0.3989422804014327f, 0.3989422804014327f)), f2_pack(e0, e1), f2_pack(c0, c1)), g0, g1);
+    d0 *= g0;
+    d1 *= g1;
 }
 
 struct GemmArgs {
@@ -80,11 +112,14 @@ struct GemmArgs {
     int kb_per_split;         // k-blocks per work item (split-K, ACCUM epilogue only; otherwise all of K)
 };
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    using GemmSmem = GemmSmemT<BN>;
+    constexpr int kStages = GemmSmem::kStages;
+    constexpr uint32_t kBBytes = GemmSmem::kBBytes;
     GemmSmem &s = *reinterpret_cast<GemmSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -142,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int w = cluster_id; w < num_work; w += num_clusters) {
             const int tile = w % num_tiles, split = w / num_tiles;
             const int m_blk = tile / num_n, n_blk = tile % num_n;
-            const int am0 = m_blk * BM + (int)rank * 128, bn0 = n_blk * BN + (int)rank * 128;
+            const int am0 = m_blk * BM + (int)rank * 128, bn0 = n_blk * BN + (int)rank * (BN / 2);
             const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, num_kb);
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(&s.empty[stage], phase ^ 1);
@@ -160,7 +195,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d_2sm(b_dst, &tmB, bar, kb * BK, bn0);
                     } else {
                         tma_load_2d_2sm(b_dst, &tmB, bar, bn0, kb * BK);
-                        tma_load_2d_2sm(b_dst + 8192, &tmB, bar, bn0 + 64, kb * BK);
+                        if (BN == 256) tma_load_2d_2sm(b_dst + 8192, &tmB, bar, bn0 + 64, kb * BK);
                     }
                 }
                 __syncwarp();
@@ -281,17 +316,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 __syncwarp();
             }
-            uint4 raux[EPI == KBNER_EPI_BIAS_RESID_F32 ? 16 : 1];
+            uint4 raux[EPI == KBNER_EPI_BIAS_RESID_F32 ? BN / 16 : 1];
             if (EPI == KBNER_EPI_BIAS_RESID_F32) {
                 const uint16_t *rrow = g.aux + (size_t)(row_ok ? row : 0) * ldc + colbase;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
+                for (int i = 0; i < BN / 16; ++i)
                     raux[i] = (row_ok && colbase + i * 8 < N) ? ld_nc_v4(rrow + i * 8) : make_uint4(0, 0, 0, 0);
             }
             // this warp's 128 bias values: one coalesced float4 per lane, redistributed with shuffles in the chunk loop
             // (per-chunk __ldg's exposed an L2 round trip four times per tile)
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_bias && colbase + lane * 4 < N) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + colbase) + lane);
+            if (has_bias && lane * 4 < BN / 2 && colbase + lane * 4 < N) bias4 = __ldg(reinterpret_cast<const float4 *>(g.bias + colbase) + lane);
             ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
 #pragma unroll
@@ -337,7 +372,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         stage_and_store(q, &tmAux, col0, row_base, false);
                     }
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
+                    for (int i = 0; i < CW; i += 2) gelu_erf2(v[i], v[i + 1]);
                 }
                 if (EPI == KBNER_EPI_DGELU_BF16) {
                     const uint32_t b = (nb + c) & 1;
@@ -357,9 +392,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         unpack_bf16x2(rv.x, a[0], a[1]); unpack_bf16x2(rv.y, a[2], a[3]);
                         unpack_bf16x2(rv.z, a[4], a[5]); unpack_bf16x2(rv.w, a[6], a[7]);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (EPI == KBNER_EPI_BIAS_RESID_F32) v[i + e] += a[e];
-                            else v[i + e] *= gelu_grad(a[e]);
+                        for (int e = 0; e < 8; e += 2) {
+                            if (EPI == KBNER_EPI_BIAS_RESID_F32) { v[i + e] += a[e]; v[i + e + 1] += a[e + 1]; }
+                            else gelu_grad_mul2(v[i + e], v[i + e + 1], a[e], a[e + 1]);
                         }
                     }
                 }
@@ -390,13 +425,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int EPI>
-static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmAux,
+template <int EPI, int BN>
+static int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmAux,
                        const GemmArgs &g, cudaStream_t st) {
-    const size_t smem = sizeof(GemmSmem);
+    const size_t smem = sizeof(GemmSmemT<BN>);
     static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return KBNER_ECUDA;
@@ -408,7 +443,7 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
     const int pairs = sm_budget() / 2;               // persistent: one CTA pair per two SMs of the budget
     const int clusters = num_work < pairs ? num_work : pairs;
-    cudaError_t le = launch_kernel(gemm_bf16_kernel<EPI>, dim3(clusters * 2), dim3(kGemmThreads), smem, st, 0, true, tmA, tmB, tmC,
+    cudaError_t le = launch_kernel(gemm_bf16_kernel<EPI, BN>, dim3(clusters * 2), dim3(kGemmThreads), smem, st, 0, true, tmA, tmB, tmC,
                                    tmAux, g);
     if (le != cudaSuccess) {
         set_error("gemm_bf16: launch failed: %s", cudaGetErrorString(le));
@@ -416,6 +451,24 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUt
     }
     KBNER_CHECK_LAUNCH("gemm_bf16");
     return KBNER_OK;
+}
+
+template <int EPI>
+static int launch_gemm(int TN, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmAux,
+                       const GemmArgs &g, cudaStream_t st) {
+    return TN == 128 ? launch_gemm_t<EPI, 128>(tmA, tmB, tmC, tmAux, g, st) : launch_gemm_t<EPI, 256>(tmA, tmB, tmC, tmAux, g, st);
+}
+
+// Tile width: 256.  KBNER_GEMM_TN=128 forces the 128-wide instantiation, kept as a measured negative result
+// (profiles/r02/gemm_tile_width.json): its operand traffic from shared memory (128 rows of A + 64 of B per CTA per 64 MMA
+// cycles = 128 B/clk) caps it at ~78 % of the 256-wide rate, which costs more than the rounds it saves on any shape here
+// (16384 x 1024 x 4096: 119.8 vs 103.0 us; 4096 x 4096 x 1024: 32.9 vs 26.4 us).
+static int pick_tile_n(int, int, int) {
+    static const int forced = [] {
+        const char *e = getenv("KBNER_GEMM_TN");
+        return e ? atoi(e) : 0;
+    }();
+    return forced == 128 ? 128 : 256;
 }
 
 }  // namespace kbner
@@ -436,14 +489,15 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     KBNER_CHECK_ARG(((uintptr_t)C & 15u) == 0 && (!bias || ((uintptr_t)bias & 15u) == 0) &&
                         (!aux || ((uintptr_t)aux & 15u) == 0) && (!aux_out || ((uintptr_t)aux_out & 15u) == 0),
                     "gemm: C / bias / aux must be 16-byte aligned");
+    const int TN = pick_tile_n(M, N, epilogue);
     CUtensorMap tmA, tmB;
     int rc;
-    // K-major operand: tensor [rows = M|N][cols = K], box 128 rows x 64 k.  MN-major: [rows = K][cols = M|N], box 64 k x 64 mn.
+    // K-major operand: tensor [rows = M|N][cols = K], box 128 (A) or TN/2 (B) rows x 64 k.  MN-major: [rows = K][cols = M|N], box 64 k x 64 mn.
     rc = a_mn_major ? make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64)
                     : make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, BK);
     if (rc) return rc;
     rc = b_mn_major ? make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
-                    : make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, BK);
+                    : make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(TN / 2), BK);
     if (rc) return rc;
     const bool bf16_out = (epilogue == KBNER_EPI_BIAS || epilogue == KBNER_EPI_BIAS_GELU || epilogue == KBNER_EPI_DGELU_BF16);
     CUtensorMap tmC, tmAux;
@@ -458,7 +512,7 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     int kb_per = num_kb_h;
     if (epilogue == KBNER_EPI_ACCUM_F32) {
         // fill ~2 work items per cluster, but keep >= 4 k-blocks per item so the pipeline prologue stays amortised
-        const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+        const int tiles = ((M + BM - 1) / BM) * ((N + TN - 1) / TN);
         int splits = (2 * (sm_budget() / 2)) / tiles;
         if (splits > num_kb_h / 4) splits = num_kb_h / 4;
         if (splits < 1) splits = 1;
@@ -467,12 +521,12 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
     GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, kb_per};
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
-        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(tmA, tmB, tmC, tmAux, g, st);
-        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(tmA, tmB, tmC, tmAux, g, st);
-        case KBNER_EPI_BIAS_RESID_F32: return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, tmAux, g, st);
-        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(tmA, tmB, tmC, tmAux, g, st);
-        case KBNER_EPI_DGELU_BF16: return launch_gemm<KBNER_EPI_DGELU_BF16>(tmA, tmB, tmC, tmAux, g, st);
-        case KBNER_EPI_ACCUM_F32: return launch_gemm<KBNER_EPI_ACCUM_F32>(tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(TN, tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_BIAS_GELU: return launch_gemm<KBNER_EPI_BIAS_GELU>(TN, tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_BIAS_RESID_F32: return launch_gemm<KBNER_EPI_BIAS_RESID_F32>(TN, tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_NONE_F32: return launch_gemm<KBNER_EPI_NONE_F32>(TN, tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_DGELU_BF16: return launch_gemm<KBNER_EPI_DGELU_BF16>(TN, tmA, tmB, tmC, tmAux, g, st);
+        case KBNER_EPI_ACCUM_F32: return launch_gemm<KBNER_EPI_ACCUM_F32>(TN, tmA, tmB, tmC, tmAux, g, st);
         default: set_error("gemm: unknown epilogue %d", epilogue); return KBNER_EINVAL;
     }
 }

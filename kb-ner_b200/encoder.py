@@ -218,8 +218,11 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         bf, f32 = torch.bfloat16, torch.float32
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         if self.precision == "bf16":
-            return dict(x0=e((M, H), bf), x1=e((M, H), bf), qkv=e((M, 3 * H), bf), ctx=e((M, H), bf), y=e((M, H), f32),
-                        h=e((M, F), bf))
+            ws = dict(x0=e((M, H), bf), x1=e((M, H), bf), qkv=e((M, 3 * H), bf), ctx=e((M, H), bf), y=e((M, H), f32),
+                      h=e((M, F), bf))
+            if self._fuse_ln and H in (256, 512, 768, 1024):
+                ws["ln_ws"] = ops.gemm_ln_workspace(M, H, dev)    # LayerNorm statistics exchange of the fused kernel
+            return ws
         k = 3 if self.precision == "bf16x3" else 1
         ws = dict(x=e((M, k * H), bf), r0=e((M, H), f32), r1=e((M, H), f32), qkv=e((M, 3 * H), bf), ctx=e((M, k * H), bf),
                   y=e((M, H), f32), h=e((M, k * F), bf))
@@ -252,8 +255,8 @@ class XLMRobertaEncoderB200(torch.nn.Module):
         ops.embed_ln_fwd(ids, e.word_embeddings.weight, e.position_embeddings.weight,
                          e.token_type_embeddings.weight[0], e.LayerNorm.weight, e.LayerNorm.bias,
                          c.layer_norm_eps, c.pad_token_id, out=x)
-        # attention-output and FFN-down projections: bias + residual + LayerNorm fused into the GEMM epilogue over a
-        # thread-block cluster that owns full rows (csrc/gemm_ln_tcgen05.cu); hidden sizes it is not built for, or
+        # attention-output and FFN-down projections: bias + residual + LayerNorm fused into the GEMM epilogue, the CTA pairs
+        # of a row panel exchanging their LayerNorm partials (csrc/gemm_ln_grid_tcgen05.cu); hidden sizes it is not built for, or
         # KBNER_FUSE_LN=0, take the GEMM (fp32 out) + LayerNorm-with-bias-and-residual pair instead
         fuse = self._fuse_ln and c.hidden_size in (256, 512, 768, 1024)
         y, h, ctx = ws["y"], ws["h"], ws["ctx"]
@@ -261,13 +264,13 @@ class XLMRobertaEncoderB200(torch.nn.Module):
             ops.gemm_bf16_tn(x, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BIAS, out=ws["qkv"])
             ops.attention_fwd(ws["qkv"], key_len, R, S, c.num_attention_heads, out=ctx)
             if fuse:
-                ops.gemm_ln(ctx, w["wo"], w["bo"], x, w["g1"], w["b1"], c.layer_norm_eps, out=xn)
+                ops.gemm_ln(ctx, w["wo"], w["bo"], x, w["g1"], w["b1"], c.layer_norm_eps, out=xn, ws=ws["ln_ws"])
             else:
                 ops.gemm_bf16_tn(ctx, w["wo"], None, epilogue=ops.EPI_NONE_F32, out=y)
                 ops.layernorm_fwd(y, w["g1"], w["b1"], c.layer_norm_eps, out=xn, bias=w["bo"], resid=x)
             ops.gemm_bf16_tn(xn, w["w1"], w["bi"], epilogue=ops.EPI_BIAS_GELU, out=h)
             if fuse:
-                ops.gemm_ln(h, w["w2"], w["b2"], xn, w["g2"], w["bb2"], c.layer_norm_eps, out=x)
+                ops.gemm_ln(h, w["w2"], w["b2"], xn, w["g2"], w["bb2"], c.layer_norm_eps, out=x, ws=ws["ln_ws"])
             else:
                 ops.gemm_bf16_tn(h, w["w2"], None, epilogue=ops.EPI_NONE_F32, out=y)
                 ops.layernorm_fwd(y, w["g2"], w["bb2"], c.layer_norm_eps, out=x, bias=w["b2"], resid=xn)

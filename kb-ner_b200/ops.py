@@ -3,6 +3,8 @@
 torch is used only for device memory and the current CUDA stream; every function here ends in
 exactly one call into libkbner_b200.so.  No function has a PyTorch / CPU fallback.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -225,8 +227,21 @@ def gemm_bf16_tn(A, B, bias=None, residual=None, epilogue=EPI_BIAS, out=None):
     return out
 
 
-def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None):
-    """out[M,N] (bf16) = LayerNorm(A[M,K] @ W[N,K]^T + bias + resid) * gamma + beta, one kernel (N in 256..1024 step 256)."""
+_GEMM_LN_IMPL = None      # tests: "grid" | "cluster" forces one kernel; None: the library picks (one round of tiles -> grid)
+
+
+def gemm_ln_workspace(M, N, device):
+    """Zeroed workspace of the fused GEMM + LayerNorm kernel for an [M, N] output (statistics slots tagged with the
+    workspace's own launch epoch: one allocation serves every launch of that shape, also inside a replayed CUDA graph)."""
+    n = int(_lib.load().kbner_gemm_ln_workspace_bytes(int(M), int(N)))
+    if n <= 0:
+        raise _lib.KbnerError("gemm_ln_workspace: unsupported shape M=%d N=%d" % (M, N))
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None, ws=None):
+    """out[M,N] (bf16) = LayerNorm(A[M,K] @ W[N,K]^T + bias + resid) * gamma + beta, one kernel (N in 256..1024 step 256).
+    ws: gemm_ln_workspace(M, N) of the caller (a fresh one is allocated when omitted)."""
     _chk(A, torch.bfloat16, "A", 2)
     _chk(W, torch.bfloat16, "W", 2)
     _chk(bias, torch.float32, "bias", 1)
@@ -243,8 +258,15 @@ def gemm_ln(A, W, bias, resid, gamma, beta, eps, out=None):
         _chk(out, torch.bfloat16, "out", 2)
     if resid is not None and resid.data_ptr() == out.data_ptr():
         raise _lib.KbnerError("gemm_ln: out must not alias resid (other CTAs still read the residual rows)")
-    _lib.check(_lib.load().kbner_gemm_bias_resid_layernorm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta),
-                                                           float(eps), _ptr(out), M, N, K, K, K, _stream()), "gemm_ln")
+    if _GEMM_LN_IMPL == "cluster":
+        _lib.check(_lib.load().kbner_gemm_bias_resid_layernorm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta),
+                                                               float(eps), _ptr(out), M, N, K, K, K, _stream()), "gemm_ln")
+        return out
+    if ws is None:
+        ws = gemm_ln_workspace(M, N, A.device)
+    fn = _lib.load().kbner_gemm_ln_grid if _GEMM_LN_IMPL == "grid" else _lib.load().kbner_gemm_bias_resid_layernorm_ws
+    _lib.check(fn(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), M, N, K, K, K,
+                  _ptr(ws), ws.numel(), _stream()), "gemm_ln")
     return out
 
 

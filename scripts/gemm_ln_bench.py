@@ -25,8 +25,16 @@ for M, N, K in ((16384, 1024, 1024), (16384, 1024, 4096), (4096, 1024, 1024), (1
     y = torch.empty(M, N, device="cuda", dtype=torch.float32)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     row = {"M": M, "N": N, "K": K}
-    row["fused_us"] = round(timeit(lambda: ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5, out=out)), 1)
-    row["fused_noresid_us"] = round(timeit(lambda: ops.gemm_ln(a, w, bias, None, gamma, beta, 1e-5, out=out)), 1)
+    lws = ops.gemm_ln_workspace(M, N, "cuda")
+    ops._GEMM_LN_IMPL = "grid"
+    row["fused_us"] = round(timeit(lambda: ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5, out=out, ws=lws)), 1)
+    row["fused_noresid_us"] = round(timeit(lambda: ops.gemm_ln(a, w, bias, None, gamma, beta, 1e-5, out=out, ws=lws)), 1)
+    y_grid = out.clone()
+    ops._GEMM_LN_IMPL = "cluster"
+    row["fused_cluster_us"] = round(timeit(lambda: ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5, out=out)), 1)
+    ops.gemm_ln(a, w, bias, None, gamma, beta, 1e-5, out=out)
+    row["grid_vs_cluster_max_diff"] = float((out.float() - y_grid.float()).abs().max())
+    ops._GEMM_LN_IMPL = "grid"
     row["gemm_f32_us"] = round(timeit(lambda: ops.gemm_bf16_tn(a, w, None, epilogue=3, out=y)), 1)
     row["ln_us"] = round(timeit(lambda: ops.layernorm_fwd(y, gamma, beta, 1e-5, out=out, bias=bias, resid=resid)), 1)
 

@@ -195,10 +195,14 @@ def test_gemm_tcgen05(ops, M, N, K, epi):
 @pytest.mark.parametrize("M,N,K,with_resid", [(300, 256, 192, True), (1000, 512, 256, True), (2125, 768, 320, True),
                                               (4096, 1024, 1024, True), (16384, 1024, 1024, True), (16384, 1024, 4096, True),
                                               (777, 1024, 512, False)])
-def test_gemm_bias_resid_layernorm_fused(ops, M, N, K, with_resid):
-    """One-kernel LayerNorm(A.W^T + bias + resid): cluster of 2*N/256 CTAs, statistics exchanged through DSMEM.  Checked
-    against the fp32 restatement on the same bf16 inputs, and against the unfused pair of kernels (which must agree to one
-    bf16 rounding of nearly identical fp32 values)."""
+@pytest.mark.parametrize("impl", ["grid", "cluster"])
+def test_gemm_bias_resid_layernorm_fused(ops, M, N, K, with_resid, impl, monkeypatch):
+    """One-kernel LayerNorm(A.W^T + bias + resid).  "grid": CTA pairs walk 256 x 256 tiles and exchange the per-row
+    statistics through tagged 16-byte slots of a global workspace (launched three times on the SAME workspace: the tag is
+    the workspace's launch epoch + 1, bumped by the last CTA to leave); "cluster": round 1's cluster of
+    2*N/256 CTAs with the DSMEM exchange.  Checked against the fp32 restatement on the same bf16 inputs, and against the
+    unfused pair of kernels (which must agree to one bf16 rounding of nearly identical fp32 values)."""
+    monkeypatch.setattr(ops, "_GEMM_LN_IMPL", impl)
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
@@ -206,7 +210,8 @@ def test_gemm_bias_resid_layernorm_fused(ops, M, N, K, with_resid):
     resid = (torch.randn(M, N, device="cuda", generator=g) + 0.3).bfloat16() if with_resid else None
     gamma = torch.rand(N, device="cuda", generator=g) + 0.5
     beta = torch.randn(N, device="cuda", generator=g) * 0.1
-    y = ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5)
+    ws = ops.gemm_ln_workspace(M, N, "cuda")
+    y = ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5, ws=ws)
     assert y.dtype == torch.bfloat16 and y.shape == (M, N)
     z = a.float() @ w.float().t() + bias[None, :]
     if with_resid:
@@ -219,6 +224,13 @@ def test_gemm_bias_resid_layernorm_fused(ops, M, N, K, with_resid):
     y1 = ops.layernorm_fwd(y0, gamma, beta, 1e-5, bias=bias, resid=resid)
     mism = (y.float() - y1.float()).abs() > 2.0 ** -7 * y1.float().abs() + 1e-3
     assert int(mism.sum()) == 0, int(mism.sum())
+    if impl == "grid":
+        ctl = ws[:8].view(torch.int32)
+        assert ctl.tolist() == [1, 0]                           # one launch completed on this workspace, no CTA still inside
+        for n in (2, 3):                                        # same workspace, same bits (fixed merge order; the slots of
+            y2 = ops.gemm_ln(a, w, bias, resid, gamma, beta, 1e-5, ws=ws)      # the previous launch carry an older tag)
+            assert torch.equal(y2, y)
+            assert ctl.tolist() == [n, 0]
 
 
 def test_gemm_linearity_full_size(ops):
