@@ -39,8 +39,10 @@ struct AttnBwdSmem {
     uint8_t dO[2][kT128];
     uint8_t pt[2][kT128];                // P^T  [128 keys][128 queries] as two 64-query sub-tiles
     uint8_t dst[2][kT128];               // dS^T, same layout (scaled by 1/8)
-    float lse2[512];                     // LSE * log2(e) of every query row of the window (+inf beyond it)
-    float dsum[512];                     // D of every query row
+    uint8_t stage[8][4096];              // per compute warp: 32 rows x 128 B SWIZZLE_128B tile of a TMA store / reduce-add
+                                         // (dQ_i partials as fp32, then dK_j / dV_j as bf16)
+    alignas(16) float lse2[512];         // -LSE * log2(e) of every query row of the window (-inf beyond it)
+    alignas(16) float dsum[512];         // -D of every query row
     uint64_t bar_kv;
     uint64_t qdo_full[2];
     uint64_t bar_sdp;                    // S^T and dP^T ready in TMEM
@@ -101,6 +103,19 @@ attn_bwd_dq_kernel(const float *__restrict__ dq_acc, int M, int H, uint16_t *__r
     *reinterpret_cast<uint4 *>(dqkv + row * 3 * H + col) = o;
 }
 
+// Debug build (KBNER_EXTRA_NVCC_FLAGS=-DKBNER_ATTN_BWD_DEBUG, scripts/attn_bwd_timeline.py): clock64 stamps of the MMA warp and
+// of compute warps 0 / 7 of CTAs 0 and 300, per query block.
+#ifdef KBNER_ATTN_BWD_DEBUG
+__device__ unsigned long long g_attn_bwd_dbg[2 * 3 * 6 * 6];
+#define BWD_STAMP(role, blk, ev)                                                                          \
+    do {                                                                                                  \
+        if (dbg_cta >= 0 && lane == 0 && (blk) < 6)                                                       \
+            g_attn_bwd_dbg[((dbg_cta * 3 + (role)) * 6 + (blk)) * 6 + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
+#else
+#define BWD_STAMP(role, blk, ev) do { } while (0)
+#endif
+
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -111,6 +126,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 template <bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDKV,
                      const int32_t *__restrict__ key_len, const float *__restrict__ lse, const float *__restrict__ Dsum,
                      int S, int H, int heads, float *__restrict__ dq_acc, uint16_t *__restrict__ dqkv, const Dropout drop) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -121,11 +137,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int row0 = r * S;
     const int nqb = (S + 127) / 128;
     const bool active = jb * 128 < klen;          // key block with at least one valid key
+#ifdef KBNER_ATTN_BWD_DEBUG
+    const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int dbg_cta = lin == 0 ? 0 : (lin == 300 ? 1 : -1);
+#endif
 
     if (threadIdx.x == 0) {
         if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
         ptx::prefetch_tensormap(&tmQKV);
         ptx::prefetch_tensormap(&tmDO);
+        ptx::prefetch_tensormap(&tmDQ);
+        ptx::prefetch_tensormap(&tmDKV);
         ptx::mbar_init(&s.bar_kv, 1);
         ptx::mbar_init(&s.qdo_full[0], 1);
         ptx::mbar_init(&s.qdo_full[1], 1);
@@ -160,7 +182,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : both K-major
         constexpr uint32_t idesc_kmn = ptx::make_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major, B MN-major
         constexpr uint32_t idesc_mnmn = ptx::make_idesc_bf16(128, 64, 1, 1);  // dQ        : both MN-major
-        const uint32_t k_addr = ptx::smem_u32(s.k), v_addr = ptx::smem_u32(s.v);
+        // Shared-memory descriptors: hi word is the same for every operand (SBO 1024 B, version 1, SWIZZLE_128B); the lo
+        // word is (address >> 4) | LBO field, so a k-step is an ADD of a constant.  (Building each descriptor with 64-bit
+        // shifts and ors made the elected lane spend 1300 cycles issuing the 24 MMAs of a query block --
+        // profiles/r02/attn_bwd_timeline_t1.json -- for 768 cycles of tensor work.)
+        const uint32_t dhi = 0x40004040u;
+        const uint32_t k_lo = ((ptx::smem_u32(s.k) >> 4) & 0x3FFFu) | (1u << 16), v_lo = ((ptx::smem_u32(s.v) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t pt_lo = ((ptx::smem_u32(s.pt[0]) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t dst_lo = ((ptx::smem_u32(s.dst[0]) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t dst_mn_lo = ((ptx::smem_u32(s.dst[0]) >> 4) & 0x3FFFu) | ((kT128 >> 4) << 16);   // MN-major A: 2 query slabs, LBO 16 KB
+        auto desc = [&](uint32_t lo, uint32_t byte_off) {
+            uint64_t d;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo + (byte_off >> 4)), "r"(dhi));
+            return d;
+        };
         auto load_qdo = [&](int i) {
             const int st = i & 1;
             ptx::mbar_expect_tx(&s.qdo_full[st], 2 * kT128);
@@ -169,17 +204,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         };
         auto issue_sdp = [&](int i) {     // S^T and dP^T of query block i
             const int st = i & 1;
-            const uint32_t q_addr = ptx::smem_u32(s.q[st]), do_addr = ptx::smem_u32(s.dO[st]);
+            const uint32_t q_lo = ((ptx::smem_u32(s.q[st]) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t do_lo = ((ptx::smem_u32(s.dO[st]) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                ptx::mma_f16_ss(t_st, ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024),
-                                ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024), idesc_kk, kk != 0);
-            }
+            for (int kk = 0; kk < 4; ++kk) ptx::mma_f16_ss(t_st, desc(k_lo, kk * 32), desc(q_lo, kk * 32), idesc_kk, kk != 0);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                ptx::mma_f16_ss(t_dpt, ptx::make_sw128_desc(v_addr + kk * 32, 16, 1024),
-                                ptx::make_sw128_desc(do_addr + kk * 32, 16, 1024), idesc_kk, kk != 0);
-            }
+            for (int kk = 0; kk < 4; ++kk) ptx::mma_f16_ss(t_dpt, desc(v_lo, kk * 32), desc(do_lo, kk * 32), idesc_kk, kk != 0);
             ptx::mma_commit(&s.bar_sdp);
         };
         if (ptx::elect_one()) {
@@ -199,32 +229,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const int st = i & 1;
             ptx::mbar_wait(&s.bar_pd, i & 1);              // P^T / dS^T of block i are in smem; S^T / dP^T were drained
             ptx::tc_fence_after();
+            BWD_STAMP(0, i, 0);
             if (ptx::elect_one()) {
-                const uint32_t pt_addr = ptx::smem_u32(s.pt[0]), dst_addr = ptx::smem_u32(s.dst[0]);
-                const uint32_t q_addr = ptx::smem_u32(s.q[st]), do_addr = ptx::smem_u32(s.dO[st]);
+                const uint32_t q_lo = ((ptx::smem_u32(s.q[st]) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t do_lo = ((ptx::smem_u32(s.dO[st]) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {           // K = 128 queries: 8 steps of 16 over the two sub-tiles
                     const uint32_t a_off = (kk >> 2) * kT128 + (kk & 3) * 32;
                     const uint32_t b_off = kk * 16 * 128;  // 16 query rows of the [query][d] tile (MN-major B)
-                    ptx::mma_f16_ss(t_dv, ptx::make_sw128_desc(pt_addr + a_off, 16, 1024),
-                                    ptx::make_sw128_desc(do_addr + b_off, 16, 1024), idesc_kmn, (i | kk) != 0);
-                    ptx::mma_f16_ss(t_dk, ptx::make_sw128_desc(dst_addr + a_off, 16, 1024),
-                                    ptx::make_sw128_desc(q_addr + b_off, 16, 1024), idesc_kmn, (i | kk) != 0);
+                    ptx::mma_f16_ss(t_dv, desc(pt_lo, a_off), desc(do_lo, b_off), idesc_kmn, (i | kk) != 0);
+                    ptx::mma_f16_ss(t_dk, desc(dst_lo, a_off), desc(q_lo, b_off), idesc_kmn, (i | kk) != 0);
                 }
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {           // dQ_i = dS . K_j : K = 128 keys
                     const uint32_t off = kk * 16 * 128;    // 16 key rows of dS^T (MN-major A: 2 query slabs, LBO 16 KB) / K_j
-                    ptx::mma_f16_ss(t_dq, ptx::make_sw128_desc(dst_addr + off, kT128, 1024),
-                                    ptx::make_sw128_desc(k_addr + off, 16, 1024), idesc_mnmn, kk != 0);
+                    ptx::mma_f16_ss(t_dq, desc(dst_mn_lo, off), desc(k_lo, off), idesc_mnmn, kk != 0);
                 }
                 ptx::mma_commit(&s.bar_out);
             }
             __syncwarp();
+            BWD_STAMP(0, i, 1);
             if (i + 1 < nqb) {
                 ptx::mbar_wait(&s.qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) issue_sdp(i + 1);     // S^T / dP^T TMEM was drained before bar_pd(i)
                 __syncwarp();
+                BWD_STAMP(0, i, 2);
             }
             if (i + 2 < nqb) {                              // refill this ring stage once block i's MMAs retired
                 ptx::mbar_wait(&s.bar_out, i & 1);
@@ -243,20 +273,41 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const float scale_log2 = 0.125f * 1.4426950408889634f;
         const uint32_t dkey = DROP ? drop_key(drop) : 0u;
         const uint32_t kpair = (uint32_t)(jb * 128 + t) >> 1;          // this thread's key: pair index and half
-        const bool khi = ((jb * 128 + t) & 1) != 0;
+        const uint32_t dshift = ((jb * 128 + t) & 1) ? 0u : 16u;       // the key's 16-bit half of the mask word, moved to the top
+        const uint32_t dthr = drop.thresh << 16;
         const uint32_t dwin = (uint32_t)(r * heads + h) * 512u;        // same counter layout as attention_fwd_kernel
         // LSE / D of the whole window are staged once, while the first TMA loads are in flight.  (Staging them per query block
         // put a DRAM round trip at the top of every block: 23 % of the stall samples of profiles/r01/attn_bwd_ncu_r38.txt.)
         for (int qi = threadIdx.x; qi < nqb * 128; qi += 256) {
             const size_t off = ((size_t)r * heads + h) * S + qi;
-            s.lse2[qi] = (qi < S) ? __ldg(lse + off) * 1.4426950408889634f : CUDART_INF_F;
-            s.dsum[qi] = (qi < S) ? __ldg(Dsum + off) : 0.0f;
+            s.lse2[qi] = (qi < S) ? -__ldg(lse + off) * 1.4426950408889634f : -CUDART_INF_F;     // both negated: FMA addends
+            s.dsum[qi] = (qi < S) ? -__ldg(Dsum + off) : 0.0f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
+#ifdef KBNER_ATTN_BWD_DEBUG
+        const int drole = warp == 0 ? 1 : (warp == 7 ? 2 : 0);
+        const int dbg_cta_w = drole ? dbg_cta : -1;
+#define BWD_STAMP_C(blk, ev) do { if (dbg_cta_w >= 0 && lane == 0 && (blk) < 6) g_attn_bwd_dbg[((dbg_cta_w * 3 + drole) * 6 + (blk)) * 6 + (ev)] = (unsigned long long)clock64(); } while (0)
+#else
+#define BWD_STAMP_C(blk, ev) do { } while (0)
+#endif
         for (int i = 0; i < nqb; ++i) {
+            BWD_STAMP_C(i, 0);
             ptx::mbar_wait(&s.bar_sdp, i & 1);
             ptx::tc_fence_after();
-            const float *lse2 = s.lse2 + i * 128, *dsum = s.dsum + i * 128;
+            BWD_STAMP_C(i, 1);
+            // The 64 elements per thread of this block cost 24 issue slots each in the first version and the eight warps
+            // were issue-bound on them (3700 of a block's 6170 cycles, profiles/r02/attn_bwd_timeline_t2.json).  Now:
+            //  * packed fp32 pairs for the arithmetic: arg = S scale - LSE (FFMA2), P = p m (FMUL2), t = dP m - D (FFMA2),
+            //    dS = (p / 8) t (2 FMUL2) -- -LSE and -D are staged negated, m = keep ? 1/(1-p) : 0;
+            //  * the mask bits of a (query, key pair) serve BOTH keys of the pair, i.e. this lane and lane ^ 1: each lane
+            //    hashes the query columns of its own parity and fetches the other half with one shuffle;
+            //  * key padding zeroes the packed words, not every element.
+            const float *nlse2 = s.lse2 + i * 128, *ndsum = s.dsum + i * 128;
+            const uint64_t scale2 = f2_pack(scale_log2, scale_log2), eighth2 = f2_pack(0.125f, 0.125f);
+            const uint32_t odd = lane & 1u;
+            // hash input of query column q: ((dwin + i*128 + q) * 256 + kpair) * 0x9E3779B1 + dkey
+            const uint32_t hbase = DROP ? ((dwin + (uint32_t)(i * 128) + odd) * 256u + kpair) * 0x9E3779B1u + dkey : 0u;
 #pragma unroll
             for (int cl = 0; cl < 2; ++cl) {              // this thread's 2 chunks of 32 query columns
                 const int c = half * 2 + cl;
@@ -267,26 +318,44 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 uint8_t *prow = s.pt[half] + t * 128, *drow = s.dst[half] + t * 128;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks of 8 queries
-                    float p[8], d[8];
+                    uint32_t pw[4], dw[4];
+                    const float4 nl0 = *reinterpret_cast<const float4 *>(nlse2 + c * 32 + cc * 8),
+                                 nl1 = *reinterpret_cast<const float4 *>(nlse2 + c * 32 + cc * 8 + 4);
+                    const float4 nd0 = *reinterpret_cast<const float4 *>(ndsum + c * 32 + cc * 8),
+                                 nd1 = *reinterpret_cast<const float4 *>(ndsum + c * 32 + cc * 8 + 4);
+                    const float nl[8] = {nl0.x, nl0.y, nl0.z, nl0.w, nl1.x, nl1.y, nl1.z, nl1.w};
+                    const float nd[8] = {nd0.x, nd0.y, nd0.z, nd0.w, nd1.x, nd1.y, nd1.z, nd1.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = c * 32 + cc * 8 + e;
-                        const float pe = key_ok ? ex2_fast(fmaf(__uint_as_float(rs[cc * 8 + e]), scale_log2, -lse2[col])) : 0.0f;
-                        float dp = __uint_as_float(rd[cc * 8 + e]);
-                        p[e] = pe;
+                    for (int e = 0; e < 8; e += 2) {
+                        const int col = c * 32 + cc * 8 + e;                 // even query column of the pair (col, col + 1)
+                        float a0, a1;
+                        f2_unpack(f2_fma(f2_pack(__uint_as_float(rs[cc * 8 + e]), __uint_as_float(rs[cc * 8 + e + 1])), scale2,
+                                         f2_pack(nl[e], nl[e + 1])), a0, a1);
+                        const uint64_t pe2 = f2_pack(ex2_fast(a0), ex2_fast(a1));
+                        uint64_t dp2 = f2_pack(__uint_as_float(rd[cc * 8 + e]), __uint_as_float(rd[cc * 8 + e + 1]));
+                        uint64_t p2 = pe2, t2;
                         if (DROP) {
-                            const uint32_t bits = drop_bits(dkey, (dwin + (uint32_t)(i * 128 + col)) * 256u + kpair);
-                            const bool keep = khi ? drop_keep_hi(bits, drop.thresh) : drop_keep_lo(bits, drop.thresh);
-                            p[e] = keep ? pe * drop.scale : 0.0f;      // P after dropout: the A operand of dV
-                            dp = keep ? dp * drop.scale : 0.0f;
+                            // this lane hashes column col + odd, its partner column col + 1 - odd
+                            const uint32_t mine = fmix32(hbase + (uint32_t)col * (256u * 0x9E3779B1u));
+                            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                            const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;       // bits of column col, col + 1
+                            // 16-bit half of THIS key: (bits >> 16) >= thresh  <=>  bits >= thresh << 16; the low half is shifted up first
+                            const float m0 = ((b0 << dshift) >= dthr) ? drop.scale : 0.0f;
+                            const float m1 = ((b1 << dshift) >= dthr) ? drop.scale : 0.0f;
+                            const uint64_t m2 = f2_pack(m0, m1);
+                            p2 = f2_mul(pe2, m2);                                  // P after dropout: the A operand of dV
+                            t2 = f2_fma(dp2, m2, f2_pack(nd[e], nd[e + 1]));
+                        } else {
+                            t2 = f2_add(dp2, f2_pack(nd[e], nd[e + 1]));
                         }
-                        d[e] = pe * (dp - dsum[col]) * 0.125f;
+                        float p0, p1, d0, d1;
+                        f2_unpack(p2, p0, p1);
+                        f2_unpack(f2_mul(f2_mul(pe2, eighth2), t2), d0, d1);
+                        pw[e >> 1] = pack_bf16x2(p0, p1);
+                        dw[e >> 1] = pack_bf16x2(d0, d1);
                     }
-                    uint4 pk, dk;
-                    pk.x = pack_bf16x2(p[0], p[1]); pk.y = pack_bf16x2(p[2], p[3]);
-                    pk.z = pack_bf16x2(p[4], p[5]); pk.w = pack_bf16x2(p[6], p[7]);
-                    dk.x = pack_bf16x2(d[0], d[1]); dk.y = pack_bf16x2(d[2], d[3]);
-                    dk.z = pack_bf16x2(d[4], d[5]); dk.w = pack_bf16x2(d[6], d[7]);
+                    const uint4 pk = key_ok ? make_uint4(pw[0], pw[1], pw[2], pw[3]) : make_uint4(0, 0, 0, 0);
+                    const uint4 dk = key_ok ? make_uint4(dw[0], dw[1], dw[2], dw[3]) : make_uint4(0, 0, 0, 0);
                     const int chunk = cl * 4 + cc;        // 16-byte chunk inside the 128-byte row of sub-tile `half`
                     const int phys = (chunk ^ (t & 7)) << 4;
                     *reinterpret_cast<uint4 *>(prow + phys) = pk;
@@ -295,48 +364,89 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
+            BWD_STAMP_C(i, 2);
             ptx::mbar_arrive(&s.bar_pd);
             // dQ_i read-out: thread = (query row, 32-column half)
             ptx::mbar_wait(&s.bar_out, i & 1);
             ptx::tc_fence_after();
+            BWD_STAMP_C(i, 3);
+            // dQ_i partial of this key block -> fp32 accumulator: the warp's 32 rows x 32 columns go through its staging tile
+            // (row = 128 B, 16-byte chunks XOR-swizzled as SWIZZLE_128B wants them) and leave as ONE TMA reduce-add.  The
+            // red.global.add.v4 per thread this replaces was 32 separate 16-byte row segments per request and took 2000
+            // cycles per query block (profiles/r02/attn_bwd_timeline_t1.json).  Rows past the window end add zeros.
             const int qi = i * 128 + t;
-            float *qrow = dq_acc + (size_t)(row0 + qi) * H + h * 64 + half * 32;
             {
                 uint32_t rq[32];
                 ptx::tmem_ld_32x32b_x32(t_dq + lane_addr + half * 32, rq);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous block's reduce has read the tile
+                __syncwarp();
                 ptx::tmem_ld_wait();
-                if (qi < S) {
+                uint8_t *dstq = s.stage[warp] + lane * 128;
+                const bool row_in = qi < S;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        red_add_v4(qrow + e, __uint_as_float(rq[e]), __uint_as_float(rq[e + 1]),
-                                   __uint_as_float(rq[e + 2]), __uint_as_float(rq[e + 3]));
+                for (int e = 0; e < 8; ++e) {
+                    const uint4 val = row_in ? make_uint4(rq[e * 4], rq[e * 4 + 1], rq[e * 4 + 2], rq[e * 4 + 3]) : make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(dstq + ((e ^ (lane & 7)) << 4)) = val;
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmDQ)), "r"(ptx::smem_u32(s.stage[warp])), "r"(h * 64 + half * 32),
+                                   "r"(row0 + i * 128 + quarter * 32)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             ptx::tc_fence_before();
+            BWD_STAMP_C(i, 4);
         }
-        // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them).
-        // tcgen05.ld is warp-collective: every lane executes it, only the stores are guarded (a per-lane guard around
-        // the load deadlocked windows whose length is not a multiple of 128).
-        const int krow = jb * 128 + t;
+        // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them): warps 0..3 take dK, warps 4..7 dV,
+        // each thread its key row's 64 columns -> bf16 -> the warp's staging tile -> one TMA store of 32 rows x 64 columns
+        // into the K | V column block of dqkv.  (Row-per-thread 16-byte global stores, 32 sectors per request, made this
+        // write-out 3300 cycles per CTA.)  A warp whose 32 rows reach past the window end stores row by row instead: the TMA
+        // box would overwrite rows of the next window.
+        // tcgen05.ld is warp-collective: every lane executes it, only the stores are guarded.
         {
-            uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + h * 64 + half * 32;
+            const int krow = jb * 128 + t;
+            const int which = half;                       // 0: dK, 1: dV
+            uint32_t rr[64];
+            ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr, *reinterpret_cast<uint32_t (*)[32]>(&rr[0]));
+            ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + 32, *reinterpret_cast<uint32_t (*)[32]>(&rr[32]));
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the last dQ reduce has read the tile
+            __syncwarp();
+            ptx::tmem_ld_wait();
+            uint4 ov[8];
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                uint32_t rr[32];
-                ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + half * 32, rr);
-                ptx::tmem_ld_wait();
-                if (krow >= S) continue;
-#pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                    uint4 ov;
-                    ov.x = pack_bf16x2(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]));
-                    ov.y = pack_bf16x2(__uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
-                    ov.z = pack_bf16x2(__uint_as_float(rr[e + 4]), __uint_as_float(rr[e + 5]));
-                    ov.w = pack_bf16x2(__uint_as_float(rr[e + 6]), __uint_as_float(rr[e + 7]));
-                    *reinterpret_cast<uint4 *>(o + (which ? 2 * H : H) + e) = ov;
-                }
+            for (int e = 0; e < 8; ++e) {
+                ov[e].x = pack_bf16x2(__uint_as_float(rr[e * 8]), __uint_as_float(rr[e * 8 + 1]));
+                ov[e].y = pack_bf16x2(__uint_as_float(rr[e * 8 + 2]), __uint_as_float(rr[e * 8 + 3]));
+                ov[e].z = pack_bf16x2(__uint_as_float(rr[e * 8 + 4]), __uint_as_float(rr[e * 8 + 5]));
+                ov[e].w = pack_bf16x2(__uint_as_float(rr[e * 8 + 6]), __uint_as_float(rr[e * 8 + 7]));
             }
+            const int wrow0 = jb * 128 + quarter * 32;    // first key row of this warp
+            if (wrow0 + 32 <= S) {
+                uint8_t *dsto = s.stage[warp] + lane * 128;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4 *>(dsto + ((e ^ (lane & 7)) << 4)) = ov[e];
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmDKV)), "r"(ptx::smem_u32(s.stage[warp])),
+                                   "r"((which ? 2 * H : H) + h * 64), "r"(row0 + wrow0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (krow < S) {
+                uint16_t *o = dqkv + (size_t)(row0 + krow) * 3 * H + (which ? 2 * H : H) + h * 64;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4 *>(o + e * 8) = ov[e];
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // stores done before smem goes away
+            __syncwarp();
         }
+        BWD_STAMP_C(nqb, 0);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -377,6 +487,11 @@ extern "C" int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, 
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmDO, d_out, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
     if (rc) return rc;
+    CUtensorMap tmDQ, tmDKV;
+    rc = make_tmap_2d(&tmDQ, dq_acc, (uint64_t)M, (uint64_t)H, (uint64_t)H, 32, 32, 4);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmDKV, dqkv, (uint64_t)M, (uint64_t)3 * H, (uint64_t)3 * H, 32, 64, 2);
+    if (rc) return rc;
     const size_t smem = sizeof(AttnBwdSmem);
     static std::atomic<bool> configured{false};   // idempotent set-up: a race only repeats it
     if (!configured) {
@@ -391,15 +506,21 @@ extern "C" int kbner_attention_bwd_ex(const uint16_t *qkv, const uint16_t *out, 
     }
     dim3 grid((S + 127) / 128, heads, R);
     if (drop.thresh)
-        attention_bwd_kernel<true><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
+        attention_bwd_kernel<true><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, tmDQ, tmDKV, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
     else
-        attention_bwd_kernel<false><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
+        attention_bwd_kernel<false><<<grid, kBwdThreads, smem, st>>>(tmQKV, tmDO, tmDQ, tmDKV, key_len, lse, d_scratch, S, H, heads, dq_acc, dqkv, drop);
     KBNER_CHECK_LAUNCH("attention_bwd");
     const size_t n8 = (size_t)M * H / 8;
     attn_bwd_dq_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq_acc, M, H, dqkv);
     KBNER_CHECK_LAUNCH("attn_bwd_dq");
     return KBNER_OK;
 }
+
+#ifdef KBNER_ATTN_BWD_DEBUG
+extern "C" int kbner_attention_bwd_debug_read(unsigned long long *host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_attn_bwd_dbg, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 extern "C" int kbner_attention_bwd_dropout(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out,
                                            const float *lse, const int32_t *key_len, int R, int S, int heads,

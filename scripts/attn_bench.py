@@ -18,7 +18,7 @@ def timeit(fn, reps=50):
     return s.elapsed_time(e) / reps * 1e3
 
 
-R, S, heads = 32, 512, 16
+R, S, heads = int(os.environ.get("R", "32")), 512, 16
 H = heads * 64
 qkv = torch.randn(R * S, 3 * H, device="cuda").bfloat16()
 key_len = torch.full((R,), S, dtype=torch.int32, device="cuda")
