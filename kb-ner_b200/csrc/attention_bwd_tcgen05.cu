@@ -37,17 +37,18 @@ struct AttnBwdSmem {
     uint8_t v[kT128];
     uint8_t q[2][kT128];                 // query-block ring
     uint8_t dO[2][kT128];
-    uint8_t pt[2][kT128];                // P^T  [128 keys][128 queries] as two 64-query sub-tiles
-    uint8_t dst[2][kT128];               // dS^T, same layout (scaled by 1/8)
-    uint8_t stage[8][4096];              // per compute warp: 32 rows x 128 B SWIZZLE_128B tile of a TMA store / reduce-add
-                                         // (dQ_i partials as fp32, then dK_j / dV_j as bf16)
-    alignas(16) float lse2[512];         // -LSE * log2(e) of every query row of the window (-inf beyond it)
-    alignas(16) float dsum[512];         // -D of every query row
+    uint8_t pt[2][2][kT128];             // [query-block parity] P^T  [128 keys][128 queries] as two 64-query sub-tiles
+    uint8_t dst[2][2][kT128];            // [query-block parity] dS^T, same layout (scaled by 1/8)
+                                         // Once the MMAs of block i have retired, pt[i & 1] doubles as the eight per-warp staging tiles
+                                         // (32 rows x 128 B, SWIZZLE_128B) of the dQ_i reduce-add, and at the end of dK_j / dV_j.
+    alignas(16) float lse2[2][128];      // [query-block parity] -LSE * log2(e) of the block's query rows (-inf beyond the window)
+    alignas(16) float dsum[2][128];      // -D of the block's query rows
     uint64_t bar_kv;
     uint64_t qdo_full[2];
     uint64_t bar_sdp;                    // S^T and dP^T ready in TMEM
-    uint64_t bar_pd;                     // P^T and dS^T written to smem (128 arrivals)
-    uint64_t bar_out;                    // dV/dK/dQ MMAs of this query block retired (also: ring stage free)
+    uint64_t bar_drain;                  // every thread has loaded its S^T / dP^T columns (256 arrivals): the next block's may be issued
+    uint64_t bar_pd;                     // P^T and dS^T written to smem (256 arrivals)
+    uint64_t bar_out[2];                 // [query-block parity] dV/dK/dQ MMAs of the block retired (also: ring stage free)
     uint32_t tmem_base;
 };
 
@@ -153,7 +154,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         ptx::mbar_init(&s.qdo_full[1], 1);
         ptx::mbar_init(&s.bar_sdp, 1);
         ptx::mbar_init(&s.bar_pd, 256);
-        ptx::mbar_init(&s.bar_out, 1);
+        ptx::mbar_init(&s.bar_drain, 256);
+        ptx::mbar_init(&s.bar_out[0], 1);
+        ptx::mbar_init(&s.bar_out[1], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 8) ptx::tmem_alloc<512>(&s.tmem_base);
@@ -162,7 +165,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
     const uint32_t t_st = tmem_base, t_dpt = tmem_base + 128, t_dk = tmem_base + 256, t_dv = tmem_base + 320,
-                   t_dq = tmem_base + 384;
+                   t_dq0 = tmem_base + 384;        // dQ: two buffers (+64), block i accumulates into t_dq0 + (i & 1) * 64
 
     if (!active) {
         // every key of this block is padding: dK = dV = 0 for its rows (rows inside the window), no dQ contribution
@@ -188,9 +191,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         // profiles/r02/attn_bwd_timeline_t1.json -- for 768 cycles of tensor work.)
         const uint32_t dhi = 0x40004040u;
         const uint32_t k_lo = ((ptx::smem_u32(s.k) >> 4) & 0x3FFFu) | (1u << 16), v_lo = ((ptx::smem_u32(s.v) >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t pt_lo = ((ptx::smem_u32(s.pt[0]) >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t dst_lo = ((ptx::smem_u32(s.dst[0]) >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t dst_mn_lo = ((ptx::smem_u32(s.dst[0]) >> 4) & 0x3FFFu) | ((kT128 >> 4) << 16);   // MN-major A: 2 query slabs, LBO 16 KB
+        const uint32_t pt_lo0 = ((ptx::smem_u32(s.pt[0][0]) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t dst_lo0 = ((ptx::smem_u32(s.dst[0][0]) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t dst_mn_lo0 = ((ptx::smem_u32(s.dst[0][0]) >> 4) & 0x3FFFu) | ((kT128 >> 4) << 16);   // MN-major A: 2 query slabs, LBO 16 KB
         auto desc = [&](uint32_t lo, uint32_t byte_off) {
             uint64_t d;
             asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo + (byte_off >> 4)), "r"(dhi));
@@ -225,14 +228,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         ptx::tc_fence_after();
         if (ptx::elect_one()) issue_sdp(0);
         __syncwarp();
+        // Order inside the tensor pipe per query block i: S^T / dP^T of block i+1 FIRST (their TMEM was drained before
+        // bar_pd(i)), then dV / dK / dQ of block i -- so the threads can start on block i+1 while block i's products are
+        // still running; P^T / dS^T and dQ are double-buffered by block parity for that.  (With one buffer the threads sat
+        // out the 1600 cycles of a block's dV / dK / dQ plus the next S^T / dP^T: profiles/r02/attn_bwd_timeline_t3.json.)
         for (int i = 0; i < nqb; ++i) {
             const int st = i & 1;
-            ptx::mbar_wait(&s.bar_pd, i & 1);              // P^T / dS^T of block i are in smem; S^T / dP^T were drained
+            if (i + 1 < nqb) {
+                // S^T / dP^T of block i are in the threads' registers (half-way through their element-wise phase): the next
+                // block's go into the tensor pipe now, 8 MMAs that shared-memory bandwidth holds at ~660 cycles, instead of
+                // after bar_pd(i), where the threads waited for them (850 cycles per block, attn_bwd_timeline_t5.json)
+                ptx::mbar_wait(&s.bar_drain, i & 1);
+                ptx::mbar_wait(&s.qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) issue_sdp(i + 1);
+                __syncwarp();
+                BWD_STAMP(0, i, 1);
+            }
+            ptx::mbar_wait(&s.bar_pd, i & 1);              // P^T / dS^T of block i are in smem
             ptx::tc_fence_after();
             BWD_STAMP(0, i, 0);
             if (ptx::elect_one()) {
                 const uint32_t q_lo = ((ptx::smem_u32(s.q[st]) >> 4) & 0x3FFFu) | (1u << 16);
                 const uint32_t do_lo = ((ptx::smem_u32(s.dO[st]) >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t boff = (uint32_t)st * ((2 * kT128) >> 4);              // this block's P^T / dS^T buffer
+                const uint32_t pt_lo = pt_lo0 + boff, dst_lo = dst_lo0 + boff, dst_mn_lo = dst_mn_lo0 + boff;
+                const uint32_t t_dq = t_dq0 + (uint32_t)st * 64;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {           // K = 128 queries: 8 steps of 16 over the two sub-tiles
                     const uint32_t a_off = (kk >> 2) * kT128 + (kk & 3) * 32;
@@ -245,19 +266,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     const uint32_t off = kk * 16 * 128;    // 16 key rows of dS^T (MN-major A: 2 query slabs, LBO 16 KB) / K_j
                     ptx::mma_f16_ss(t_dq, desc(dst_mn_lo, off), desc(k_lo, off), idesc_mnmn, kk != 0);
                 }
-                ptx::mma_commit(&s.bar_out);
+                ptx::mma_commit(&s.bar_out[st]);
             }
             __syncwarp();
-            BWD_STAMP(0, i, 1);
-            if (i + 1 < nqb) {
-                ptx::mbar_wait(&s.qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) issue_sdp(i + 1);     // S^T / dP^T TMEM was drained before bar_pd(i)
-                __syncwarp();
-                BWD_STAMP(0, i, 2);
-            }
+            BWD_STAMP(0, i, 2);
             if (i + 2 < nqb) {                              // refill this ring stage once block i's MMAs retired
-                ptx::mbar_wait(&s.bar_out, i & 1);
+                ptx::mbar_wait(&s.bar_out[st], (i >> 1) & 1);
                 if (ptx::elect_one()) load_qdo(i + 2);
                 __syncwarp();
             }
@@ -276,14 +290,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t dshift = ((jb * 128 + t) & 1) ? 0u : 16u;       // the key's 16-bit half of the mask word, moved to the top
         const uint32_t dthr = drop.thresh << 16;
         const uint32_t dwin = (uint32_t)(r * heads + h) * 512u;        // same counter layout as attention_fwd_kernel
-        // LSE / D of the whole window are staged once, while the first TMA loads are in flight.  (Staging them per query block
-        // put a DRAM round trip at the top of every block: 23 % of the stall samples of profiles/r01/attn_bwd_ncu_r38.txt.)
-        for (int qi = threadIdx.x; qi < nqb * 128; qi += 256) {
-            const size_t off = ((size_t)r * heads + h) * S + qi;
-            s.lse2[qi] = (qi < S) ? -__ldg(lse + off) * 1.4426950408889634f : -CUDART_INF_F;     // both negated: FMA addends
-            s.dsum[qi] = (qi < S) ? -__ldg(Dsum + off) : 0.0f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
 #ifdef KBNER_ATTN_BWD_DEBUG
         const int drole = warp == 0 ? 1 : (warp == 7 ? 2 : 0);
         const int dbg_cta_w = drole ? dbg_cta : -1;
@@ -291,8 +297,60 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #else
 #define BWD_STAMP_C(blk, ev) do { } while (0)
 #endif
+        // -LSE / -D (negated: FMA addends) of a query block: 256 threads = 128 + 128 values.  Block i+1's are requested at the
+        // top of block i and parked in shared memory after its element-wise phase, so no block waits for DRAM (staging them
+        // at the top of their own block was 23 % of the stall samples of profiles/r01/attn_bwd_ncu_r38.txt).
+        const int sidx = threadIdx.x & 127;
+        const bool s_is_lse = threadIdx.x < 128;
+        const float *stat_src = (s_is_lse ? lse : Dsum) + ((size_t)r * heads + h) * S;
+        auto load_stat = [&](int blk) -> float {          // the raw value: nothing may depend on it before store_stat
+            const int qi = blk * 128 + sidx;
+            return (qi < S) ? __ldg(stat_src + qi) : 0.0f;
+        };
+        auto store_stat = [&](int blk, float raw) {
+            const int qi = blk * 128 + sidx;
+            if (s_is_lse) s.lse2[blk & 1][sidx] = (qi < S) ? -raw * 1.4426950408889634f : -CUDART_INF_F;
+            else s.dsum[blk & 1][sidx] = -raw;
+        };
+        store_stat(0, load_stat(0));
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // compute warps only
+        // dQ_i partial of this key block -> fp32 accumulator: the warp's 32 rows x 32 columns go through a staging tile (row =
+        // 128 B, 16-byte chunks XOR-swizzled as SWIZZLE_128B wants them) and leave as ONE TMA reduce-add.  The red.global.add.v4
+        // per thread this replaces was 32 separate 16-byte row segments per request and took 2000 cycles per query block
+        // (profiles/r02/attn_bwd_timeline_t1.json).  Rows past the window end add zeros.  The tile lives in pt[i & 1]: free
+        // since bar_out(i), written again by block i+2 after the wait_group.read + bar.sync at its top.
+        auto read_out_dq = [&](int i) {
+            const int b = i & 1;
+            ptx::mbar_wait(&s.bar_out[b], (i >> 1) & 1);
+            ptx::tc_fence_after();
+            BWD_STAMP_C(i, 3);
+            uint32_t rq[32];
+            ptx::tmem_ld_32x32b_x32(t_dq0 + (uint32_t)b * 64 + lane_addr + half * 32, rq);
+            ptx::tmem_ld_wait();
+            uint8_t *tile = &s.pt[b][0][0] + warp * 4096;
+            uint8_t *dstq = tile + lane * 128;
+            const bool row_in = i * 128 + t < S;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint4 val = row_in ? make_uint4(rq[e * 4], rq[e * 4 + 1], rq[e * 4 + 2], rq[e * 4 + 3]) : make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(dstq + ((e ^ (lane & 7)) << 4)) = val;
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmDQ)), "r"(ptx::smem_u32(tile)), "r"(h * 64 + half * 32),
+                               "r"(row0 + i * 128 + quarter * 32)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ptx::tc_fence_before();
+            BWD_STAMP_C(i, 4);
+        };
         for (int i = 0; i < nqb; ++i) {
+            const int b = i & 1;
             BWD_STAMP_C(i, 0);
+            const float stat_next = (i + 1 < nqb) ? load_stat(i + 1) : 0.0f;
             ptx::mbar_wait(&s.bar_sdp, i & 1);
             ptx::tc_fence_after();
             BWD_STAMP_C(i, 1);
@@ -303,7 +361,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             //  * the mask bits of a (query, key pair) serve BOTH keys of the pair, i.e. this lane and lane ^ 1: each lane
             //    hashes the query columns of its own parity and fetches the other half with one shuffle;
             //  * key padding zeroes the packed words, not every element.
-            const float *nlse2 = s.lse2 + i * 128, *ndsum = s.dsum + i * 128;
+            const float *nlse2 = s.lse2[b], *ndsum = s.dsum[b];
             const uint64_t scale2 = f2_pack(scale_log2, scale_log2), eighth2 = f2_pack(0.125f, 0.125f);
             const uint32_t odd = lane & 1u;
             // hash input of query column q: ((dwin + i*128 + q) * 256 + kpair) * 0x9E3779B1 + dkey
@@ -314,8 +372,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 uint32_t rs[32], rd[32];
                 ptx::tmem_ld_32x32b_x32(t_st + lane_addr + c * 32, rs);
                 ptx::tmem_ld_32x32b_x32(t_dpt + lane_addr + c * 32, rd);
+                if (cl == 0 && i > 0) {
+                    // pt[b] is about to be rewritten: the dQ reduce of block i-2 (issued in the middle of block i-1) staged this
+                    // warp's tile exactly where the warp now writes its 32 rows of the sub-tile; lse2[b] / dsum[b] were stored
+                    // by all threads in block i-1 (hence the barrier).
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
                 ptx::tmem_ld_wait();
-                uint8_t *prow = s.pt[half] + t * 128, *drow = s.dst[half] + t * 128;
+                if (cl == 1) {                            // this thread's last S^T / dP^T columns are in registers
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&s.bar_drain);
+                }
+                uint8_t *prow = s.pt[b][half] + t * 128, *drow = s.dst[b][half] + t * 128;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks of 8 queries
                     uint32_t pw[4], dw[4];
@@ -361,46 +430,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     *reinterpret_cast<uint4 *>(prow + phys) = pk;
                     *reinterpret_cast<uint4 *>(drow + phys) = dk;
                 }
+                // dQ read-out of the PREVIOUS block (thread = query row, 32-column half), between this block's two column
+                // chunks: by now its MMAs have retired (they were issued behind this block's S^T / dP^T), and the reduce-add
+                // has the second chunk, the wait for the next S^T / dP^T and the next block's TMEM loads to read its staging
+                // tile before pt[b ^ 1] is written again.  (At the end of the block it had ~1000 cycles, and the wait for it
+                // grew the element-wise phase from 2800 to 4400 cycles: profiles/r02/attn_bwd_timeline_t4.json.)
+                if (cl == 0 && i > 0) read_out_dq(i - 1);
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
             BWD_STAMP_C(i, 2);
             ptx::mbar_arrive(&s.bar_pd);
-            // dQ_i read-out: thread = (query row, 32-column half)
-            ptx::mbar_wait(&s.bar_out, i & 1);
-            ptx::tc_fence_after();
-            BWD_STAMP_C(i, 3);
-            // dQ_i partial of this key block -> fp32 accumulator: the warp's 32 rows x 32 columns go through its staging tile
-            // (row = 128 B, 16-byte chunks XOR-swizzled as SWIZZLE_128B wants them) and leave as ONE TMA reduce-add.  The
-            // red.global.add.v4 per thread this replaces was 32 separate 16-byte row segments per request and took 2000
-            // cycles per query block (profiles/r02/attn_bwd_timeline_t1.json).  Rows past the window end add zeros.
-            const int qi = i * 128 + t;
-            {
-                uint32_t rq[32];
-                ptx::tmem_ld_32x32b_x32(t_dq + lane_addr + half * 32, rq);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous block's reduce has read the tile
-                __syncwarp();
-                ptx::tmem_ld_wait();
-                uint8_t *dstq = s.stage[warp] + lane * 128;
-                const bool row_in = qi < S;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint4 val = row_in ? make_uint4(rq[e * 4], rq[e * 4 + 1], rq[e * 4 + 2], rq[e * 4 + 3]) : make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(dstq + ((e ^ (lane & 7)) << 4)) = val;
-                }
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&tmDQ)), "r"(ptx::smem_u32(s.stage[warp])), "r"(h * 64 + half * 32),
-                                   "r"(row0 + i * 128 + quarter * 32)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-            ptx::tc_fence_before();
-            BWD_STAMP_C(i, 4);
+            if (i + 1 < nqb) store_stat(i + 1, stat_next);     // read after the next bar.sync
         }
+        read_out_dq(nqb - 1);
         // dK_j, dV_j (accumulated over all query blocks; the last bar_out covered them): warps 0..3 take dK, warps 4..7 dV,
         // each thread its key row's 64 columns -> bf16 -> the warp's staging tile -> one TMA store of 32 rows x 64 columns
         // into the K | V column block of dqkv.  (Row-per-thread 16-byte global stores, 32 sectors per request, made this
@@ -413,9 +456,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             uint32_t rr[64];
             ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr, *reinterpret_cast<uint32_t (*)[32]>(&rr[0]));
             ptx::tmem_ld_32x32b_x32((which ? t_dv : t_dk) + lane_addr + 32, *reinterpret_cast<uint32_t (*)[32]>(&rr[32]));
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the last dQ reduce has read the tile
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // this warp's dQ reduces have read their tiles
             __syncwarp();
             ptx::tmem_ld_wait();
+            uint8_t *tile = &s.pt[nqb & 1][0][0] + warp * 4096;     // (every MMA has retired: both P^T buffers are free)
             uint4 ov[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -426,14 +470,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
             const int wrow0 = jb * 128 + quarter * 32;    // first key row of this warp
             if (wrow0 + 32 <= S) {
-                uint8_t *dsto = s.stage[warp] + lane * 128;
+                uint8_t *dsto = tile + lane * 128;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4 *>(dsto + ((e ^ (lane & 7)) << 4)) = ov[e];
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&tmDKV)), "r"(ptx::smem_u32(s.stage[warp])),
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmDKV)), "r"(ptx::smem_u32(tile)),
                                    "r"((which ? 2 * H : H) + h * 64), "r"(row0 + wrow0)
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -443,7 +487,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
                 for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4 *>(o + e * 8) = ov[e];
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // stores done before smem goes away
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");            // the stores have read their tiles
             __syncwarp();
         }
         BWD_STAMP_C(nqb, 0);

@@ -416,7 +416,7 @@ gemm_ln_grid_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             GLN_STAMP(it, 7);
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
     }
     ptx::tc_fence_before();

@@ -363,7 +363,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             nstores = 0;                               // the next panel starts with wait_group.read 0
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
     }
     ptx::tc_fence_before();

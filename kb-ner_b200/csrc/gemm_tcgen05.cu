@@ -414,7 +414,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 stage_and_store(q, &tmC, col0, row_base, EPI == KBNER_EPI_ACCUM_F32);
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before smem goes away
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores have READ the staging tiles (their global writes complete with the grid)
         __syncwarp();
     }
     ptx::tc_fence_before();

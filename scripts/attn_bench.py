@@ -31,6 +31,9 @@ do = torch.randn(R * S, H, device="cuda").bfloat16()
 dqkv = torch.empty(R * S, 3 * H, device="cuda", dtype=torch.bfloat16)
 ws = (torch.empty((R, heads, S), dtype=torch.float32, device="cuda"), torch.empty((R * S, H), dtype=torch.float32, device="cuda"))
 row["attn_bwd_us"] = round(timeit(lambda: ops.attention_bwd(qkv, o, do, lse, key_len, R, S, heads, dqkv=dqkv, workspace=ws), 20), 1)
+od, lsed = ops.attention_fwd(qkv, key_len, R, S, heads, want_lse=True, drop=(seed, 3, 0.1))
+row["attn_bwd_dropout_us"] = round(timeit(lambda: ops.attention_bwd(qkv, od, do, lsed, key_len, R, S, heads, dqkv=dqkv, workspace=ws,
+                                                                 drop=(seed, 3, 0.1)), 20), 1)
 a = torch.randn(16384, 1024, device="cuda").bfloat16()
 b = torch.randn(3072, 1024, device="cuda").bfloat16()
 row["cublas_qkv_us"] = round(timeit(lambda: torch.matmul(a, b.t())), 1)
