@@ -230,6 +230,16 @@ int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float *bias, con
                     uint16_t *aux_out, void *C, int M, int N, int K, int lda, int ldb, int ldc,
                     int a_mn_major, int b_mn_major, int epilogue, void *stream);
 
+/* GROUPED weight gradients of one encoder layer in ONE launch (csrc/gemm_group_tcgen05.cu):
+ *     dW[p] [n_out[p], n_in[p]] (fp32, row-major, ld = n_in[p])  +=  dY[p]^T . X[p],    p = 0 .. count-1,  count <= 4
+ * with dY[p] [tokens, n_out[p]] (ld_dy[p]) and X[p] [tokens, n_in[p]] (ld_x[p]) bf16, read in place (MN-major tensor-core
+ * operands).  The k-blocks of all tiles of all problems are cut into equal shares for the CTA pairs (stream-K across
+ * problems); every work item adds its partial product with a TMA reduce-add.  Same result as `count` calls of kbner_gemm_bf16
+ * with KBNER_EPI_ACCUM_F32 and both operands MN-major (up to the order of the fp32 additions).
+ * Replaces: the torch.nn.Linear weight gradients of a BertLayer in loss.backward() (finetune_trainer.py:956-957). */
+int kbner_gemm_wgrad_group(int count, const uint16_t *const *dY, const uint16_t *const *X, float *const *dW, const int *n_out,
+                           const int *n_in, const int *ld_dy, const int *ld_x, int tokens, void *stream);
+
 /* C[M,N] = epilogue(A[M,K] . B[N,K]^T): both operands K-major bf16 ("TN" GEMM, the layout of
  * torch.nn.Linear).  M, N, K arbitrary multiples of 8 (TMA handles ragged tile edges);
  * lda/ldb/ldc in elements.  SURVEY E2/E4/E5/E6. */

@@ -28,6 +28,7 @@ SIGNATURES = {
     "kbner_gather_tagproj_fwd": ([_c_void_p] * 6 + [_c_int] * 5 + [_c_void_p] * 2, _c_int),
     "kbner_gemm_bf16_tn": ([_c_void_p] * 5 + [_c_int] * 7 + [_c_void_p], _c_int),
     "kbner_gemm_bf16": ([_c_void_p] * 6 + [_c_int] * 9 + [_c_void_p], _c_int),
+    "kbner_gemm_wgrad_group": ([_c_int] + [_c_void_p] * 7 + [_c_int, _c_void_p], _c_int),
     "kbner_attention_fwd": ([_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p] * 3, _c_int),
     "kbner_attention_bwd": ([_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p] * 4, _c_int),
     "kbner_layernorm_bwd": ([_c_void_p] * 5 + [_c_int] * 2 + [_c_void_p] * 5, _c_int),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libkbner_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["runtime.cu", "crf.cu", "crf_viterbi.cu", "elementwise.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "gemm_ln_grid_tcgen05.cu", "attention_tcgen05.cu", "attention_bwd_tcgen05.cu",
+SOURCES = ["runtime.cu", "crf.cu", "crf_viterbi.cu", "elementwise.cu", "gemm_tcgen05.cu", "gemm_ln_tcgen05.cu", "gemm_ln_grid_tcgen05.cu", "gemm_group_tcgen05.cu", "attention_tcgen05.cu", "attention_bwd_tcgen05.cu",
            "train_kernels.cu"]
 HEADERS = ["common.cuh", "crf_common.cuh", "tc_ptx.cuh", "cluster_ptx.cuh", "tma_host.cuh", os.path.join("..", "..", "include", "kbner_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -110,7 +110,40 @@ struct GemmArgs {
     int M, N, K, ldc;
     int a_mn, b_mn;           // operand layouts (0 = K-major, 1 = MN-major)
     int kb_per_split;         // k-blocks per work item (split-K, ACCUM epilogue only; otherwise all of K)
+    int stream_units;         // > 0 (ACCUM epilogue only): stream-K -- cluster c owns k-block units [c * U, (c + 1) * U) of the
+                              // linearised (tile, k-block) space, every intersection with a tile is one work item
 };
+
+// The work items of one cluster, in the order all three warp roles walk them.  Tile-per-item / split-K: item w =
+// cluster_id + n * num_clusters -> (tile = w % num_tiles, split = w / num_tiles).  Stream-K: the cluster's unit range cut at
+// tile boundaries.  `cursor` is the role's private position (items done, or units done).
+struct GemmItem {
+    int tile, kb0, kb1;
+};
+__device__ __forceinline__ bool gemm_next_item(const GemmArgs &g, int num_tiles, int num_kb, int cluster_id, int num_clusters,
+                                               int &cursor, GemmItem &it) {
+    if (g.stream_units > 0) {
+        const int total = num_tiles * num_kb;
+        const int begin = cluster_id * g.stream_units;
+        const int end = min(begin + g.stream_units, total);
+        const int pos = begin + cursor;
+        if (pos >= end) return false;
+        it.tile = pos / num_kb;
+        it.kb0 = pos - it.tile * num_kb;
+        it.kb1 = min(num_kb, it.kb0 + (end - pos));
+        cursor += it.kb1 - it.kb0;
+        return true;
+    }
+    const int kb_per = g.kb_per_split;
+    const int num_work = num_tiles * ((num_kb + kb_per - 1) / kb_per);
+    const int w = cluster_id + cursor * num_clusters;
+    if (w >= num_work) return false;
+    it.tile = w % num_tiles;
+    it.kb0 = (w / num_tiles) * kb_per;
+    it.kb1 = min(it.kb0 + kb_per, num_kb);
+    ++cursor;
+    return true;
+}
 
 template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -129,11 +162,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (g.K + BK - 1) / BK;
-    // split-K (wgrad: few output tiles, long K): work item w = (tile = w % num_tiles, split = w / num_tiles); every split
-    // adds its partial product into C with the TMA reduce-add epilogue
-    const int kb_per = g.kb_per_split;
-    const int num_splits = (num_kb + kb_per - 1) / kb_per;
-    const int num_work = num_tiles * num_splits;
+    // wgrad (few output tiles, long K) cuts K: every work item adds its partial product into C with the TMA reduce-add
+    // epilogue (gemm_next_item)
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -174,12 +204,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t phase = 0;
         const uint32_t a_smem0 = ptx::smem_u32(s.a[0]), b_smem0 = ptx::smem_u32(s.b[0]);
         const uint32_t full0_leader = mapa(ptx::smem_u32(&s.full[0]), 0);
-        for (int w = cluster_id; w < num_work; w += num_clusters) {
-            const int tile = w % num_tiles, split = w / num_tiles;
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+        int cursor = 0;
+        GemmItem wi;
+        while (gemm_next_item(g, num_tiles, num_kb, cluster_id, num_clusters, cursor, wi)) {
+            const int m_blk = wi.tile / num_n, n_blk = wi.tile % num_n;
             const int am0 = m_blk * BM + (int)rank * 128, bn0 = n_blk * BN + (int)rank * (BN / 2);
-            const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, num_kb);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                 ptx::mbar_wait(&s.empty[stage], phase ^ 1);
                 if (ptx::elect_one()) {
                     if (leader) ptx::mbar_expect_tx(&s.full[stage], 2 * (kABytes + kBBytes));
@@ -217,9 +247,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
-                const int split = w / num_tiles;
-                const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, num_kb);
+            int cursor = 0;
+            GemmItem wi;
+            for (; gemm_next_item(g, num_tiles, num_kb, cluster_id, num_clusters, cursor, wi); ++it) {
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
@@ -285,9 +316,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ++nstores;
         };
         int it = 0;
-        for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
-            const int tile = w % num_tiles;
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+        int cursor = 0;
+        GemmItem wi;
+        for (; gemm_next_item(g, num_tiles, num_kb, cluster_id, num_clusters, cursor, wi); ++it) {
+            const int m_blk = wi.tile / num_n, n_blk = wi.tile % num_n;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row_base = m_blk * BM + (int)rank * 128 + quarter * 32;
@@ -440,9 +472,14 @@ static int launch_gemm_t(const CUtensorMap &tmA, const CUtensorMap &tmB, const C
     }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int num_kb = (g.K + BK - 1) / BK;
-    const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
     const int pairs = sm_budget() / 2;               // persistent: one CTA pair per two SMs of the budget
-    const int clusters = num_work < pairs ? num_work : pairs;
+    int clusters;
+    if (g.stream_units > 0) {
+        clusters = (num_tiles * num_kb + g.stream_units - 1) / g.stream_units;
+    } else {
+        const int num_work = num_tiles * ((num_kb + g.kb_per_split - 1) / g.kb_per_split);
+        clusters = num_work < pairs ? num_work : pairs;
+    }
     cudaError_t le = launch_kernel(gemm_bf16_kernel<EPI, BN>, dim3(clusters * 2), dim3(kGemmThreads), smem, st, 0, true, tmA, tmB, tmC,
                                    tmAux, g);
     if (le != cudaSuccess) {
@@ -509,16 +546,34 @@ extern "C" int kbner_gemm_bf16(const uint16_t *A, const uint16_t *B, const float
         if (rc) return rc;
     }
     const int num_kb_h = (K + BK - 1) / BK;
-    int kb_per = num_kb_h;
+    int kb_per = num_kb_h, stream_units = 0;
     if (epilogue == KBNER_EPI_ACCUM_F32) {
-        // fill ~2 work items per cluster, but keep >= 4 k-blocks per item so the pipeline prologue stays amortised
+        // wgrad: few output tiles (64 at 1024 x 4096), long K (the 4096 tokens).  Stream-K: the tiles' k-blocks form one
+        // line of tiles * num_kb units, cut into equal shares for the CTA pairs; a share that crosses a tile boundary is two
+        // work items, and every item leaves through the reduce-add epilogue.  Shares are even, so no item is shorter than 2
+        // k-blocks when num_kb is even.  Round 1's split-K (kb_per_split, KBNER_GEMM_STREAMK=0) gave every pair whole
+        // splits: 64 tiles x 2 splits = 1.73 rounds of 32 k-blocks on 74 pairs = 64 k-blocks of time for 55.4 of work.
+        static const bool streamk = [] {
+            const char *e = getenv("KBNER_GEMM_STREAMK");
+            return !(e && e[0] == '0');
+        }();
         const int tiles = ((M + BM - 1) / BM) * ((N + TN - 1) / TN);
-        int splits = (2 * (sm_budget() / 2)) / tiles;
-        if (splits > num_kb_h / 4) splits = num_kb_h / 4;
-        if (splits < 1) splits = 1;
-        kb_per = (num_kb_h + splits - 1) / splits;
+        const int pairs = sm_budget() / 2;
+        if (streamk) {
+            const int total = tiles * num_kb_h;
+            int U = (total + pairs - 1) / pairs;
+            U += U & 1;
+            if (U < 4) U = 4;
+            stream_units = U;
+        } else {
+            // fill ~2 work items per cluster, but keep >= 4 k-blocks per item so the pipeline prologue stays amortised
+            int splits = (2 * pairs) / tiles;
+            if (splits > num_kb_h / 4) splits = num_kb_h / 4;
+            if (splits < 1) splits = 1;
+            kb_per = (num_kb_h + splits - 1) / splits;
+        }
     }
-    GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, kb_per};
+    GemmArgs g{bias, aux, aux_out, C, M, N, K, ldc, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, kb_per, stream_units};
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
         case KBNER_EPI_BIAS: return launch_gemm<KBNER_EPI_BIAS>(TN, tmA, tmB, tmC, tmAux, g, st);

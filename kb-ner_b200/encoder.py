@@ -636,6 +636,9 @@ def _forward_train(self, ids, key_len):
     return st["out"], st["saved"]
 
 
+_WGRAD_GROUP = os.environ.get("KBNER_WGRAD_GROUP", "1") != "0"
+
+
 @torch.no_grad()
 def _backward_workspace(self, saved, dev):
     c = self.config
@@ -663,21 +666,27 @@ def _backward_layers(self, saved, dout, dres, li_hi, li_lo, ws):
         dz2 = ops.layernorm_bwd(y2, dout, w["g2"], mean2, rstd2, lyr.output.LayerNorm.weight.grad, lyr.output.LayerNorm.bias.grad,
                                 dxsum=lyr.output.dense.bias.grad, bias=w["b2"], resid=x1, dres=dres, drop=d_h2)
         dz2, dy2 = dz2 if isinstance(dz2, tuple) else (dz2, dz2)      # (residual path, through the dropout mask)
-        ops.gemm_bf16(dy2, h, H, F, M, ops.EPI_ACCUM_F32, out=lyr.output.dense.weight.grad, a_mn=True, b_mn=True)
+        wg = [(dy2, h, lyr.output.dense.weight.grad)]          # the layer's weight gradients: one grouped launch at its end
         dhpre = ops.gemm_bf16(dy2, w["w2"], M, F, H, ops.EPI_DGELU_BF16, aux=hpre, b_mn=True)
         ops.colsum_bf16(dhpre, lyr.intermediate.dense.bias.grad)
-        ops.gemm_bf16(dhpre, x1, F, H, M, ops.EPI_ACCUM_F32, out=lyr.intermediate.dense.weight.grad, a_mn=True, b_mn=True)
+        wg.append((dhpre, x1, lyr.intermediate.dense.weight.grad))
         dx1 = ops.gemm_bf16(dhpre, w["w1"], M, H, F, ops.EPI_NONE_F32, b_mn=True)
         # ---- attention block ------------------------------------------------------------------------
         dz1 = ops.layernorm_bwd(y1, dx1, w["g1"], mean1, rstd1, a.output.LayerNorm.weight.grad, a.output.LayerNorm.bias.grad,
                                 dxsum=a.output.dense.bias.grad, bias=w["bo"], resid=x, dres=dz2, drop=d_h1)
         dz1, dy1 = dz1 if isinstance(dz1, tuple) else (dz1, dz1)
-        ops.gemm_bf16(dy1, ctx, H, H, M, ops.EPI_ACCUM_F32, out=a.output.dense.weight.grad, a_mn=True, b_mn=True)
+        wg.append((dy1, ctx, a.output.dense.weight.grad))
         dctx = ops.gemm_bf16(dy1, w["wo"], M, H, H, ops.EPI_BIAS, b_mn=True)
         dqkv = ops.attention_bwd(qkv, ctx, dctx, lse, key_len, R, S, heads, workspace=ws, drop=d_attn, out_lo=ctx_lo)
         ops.colsum_bf16(dqkv, ar.view(a.self.query.bias, (3 * H,), grad=True))
-        ops.gemm_bf16(dqkv, x, 3 * H, H, M, ops.EPI_ACCUM_F32, out=ar.view(a.self.query.weight, (3 * H, H), grad=True),
-                      a_mn=True, b_mn=True)
+        wg.append((dqkv, x, ar.view(a.self.query.weight, (3 * H, H), grad=True)))
+        if _WGRAD_GROUP:
+            # dW += dY^T . X for the four projections in ONE stream-K launch over all their tiles (csrc/gemm_group_tcgen05.cu):
+            # separately they paid four ramps and four tails for 94 us of work (profiles/r02/wgrad_streamk.json)
+            ops.gemm_wgrad_group(wg)
+        else:
+            for dy_, x_, dw_ in wg:
+                ops.gemm_bf16(dy_, x_, dy_.shape[1], x_.shape[1], M, ops.EPI_ACCUM_F32, out=dw_, a_mn=True, b_mn=True)
         if li > 0:
             dout = ops.gemm_bf16(dqkv, w["wqkv"], M, H, 3 * H, ops.EPI_NONE_F32, b_mn=True)
             dres = dz1

@@ -509,6 +509,28 @@ def gemm_bf16(A, B, M, N, K, epilogue, bias=None, aux=None, aux_out=None, out=No
     return out
 
 
+def gemm_wgrad_group(problems):
+    """One launch for up to four weight gradients over the same token rows: problems = [(dY [tokens, out] bf16,
+    X [tokens, in] bf16, dW [out, in] fp32 -- accumulated into), ...]."""
+    import ctypes
+    n = len(problems)
+    if not 1 <= n <= 4:
+        raise _lib.KbnerError("gemm_wgrad_group: 1..4 problems, got %d" % n)
+    tokens = problems[0][0].shape[0]
+    for dy, x, dw in problems:
+        _chk(dy, torch.bfloat16, "dY", 2)
+        _chk(x, torch.bfloat16, "X", 2)
+        _chk(dw, torch.float32, "dW", 2)
+        if dy.shape[0] != tokens or x.shape[0] != tokens or tuple(dw.shape) != (dy.shape[1], x.shape[1]):
+            raise _lib.KbnerError("gemm_wgrad_group: shapes dY %s X %s dW %s" % (tuple(dy.shape), tuple(x.shape), tuple(dw.shape)))
+    vp, ci = ctypes.c_void_p * n, ctypes.c_int * n
+    _lib.check(_lib.load().kbner_gemm_wgrad_group(
+        n, vp(*[p[0].data_ptr() for p in problems]), vp(*[p[1].data_ptr() for p in problems]),
+        vp(*[p[2].data_ptr() for p in problems]), ci(*[p[0].shape[1] for p in problems]), ci(*[p[1].shape[1] for p in problems]),
+        ci(*[p[0].stride(0) for p in problems]), ci(*[p[1].stride(0) for p in problems]), int(tokens), _stream()),
+        "gemm_wgrad_group")
+
+
 def attention_bwd(qkv, out, d_out, lse, key_len, R, S, heads, dqkv=None, workspace=None, drop=None, out_lo=None):
     """dQ | dK | dV ([R*S, 3H] bf16) of attention_fwd.  workspace = (d_scratch [R,heads,S] f32, dq_acc [R*S,H] f32).
     out_lo: the forward's rounding residual (attention_fwd(out_lo=...)); D = rowsum(dO * (out + out_lo)) when given."""

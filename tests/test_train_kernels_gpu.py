@@ -310,3 +310,36 @@ def test_attention_fwd_bwd_with_dropout(ops, R, S, heads, lens):
     scale = ref[rows].abs().max().item()
     assert diff.max().item() < 3e-2 * max(scale, 1.0), (diff.max().item(), scale)
     assert (diff.mean() / ref[rows].abs().mean()).item() < 1e-2
+
+
+@pytest.mark.parametrize("tokens", [4096, 1000])
+def test_gemm_wgrad_group_matches_the_separate_launches(ops, tokens):
+    """The four weight gradients of a layer in one stream-K launch (csrc/gemm_group_tcgen05.cu) against fp32 matmuls and
+    against four kbner_gemm_bf16 launches with the reduce-add epilogue; dW is accumulated INTO (gradient accumulation over
+    micro-batches), so it starts non-zero.  1000 tokens: a K extent that is not a multiple of the 64-token k-block."""
+    g = torch.Generator(device="cuda").manual_seed(tokens)
+    shapes = [(1024, 4096), (4096, 1024), (1024, 1024), (3072, 1024)]       # (out, in): FFN-down, FFN-up, attention-out, QKV
+    probs, refs, seps = [], [], []
+    for n_out, n_in in shapes:
+        dy = (torch.randn(tokens, n_out, device="cuda", generator=g) * 0.1).bfloat16()
+        x = (torch.randn(tokens, n_in, device="cuda", generator=g) * 0.5).bfloat16()
+        dw0 = torch.randn(n_out, n_in, device="cuda", generator=g)
+        probs.append((dy, x, dw0.clone()))
+        refs.append(dw0 + dy.float().t() @ x.float())
+        sep = dw0.clone()
+        ops.gemm_bf16(dy, x, n_out, n_in, tokens, ops.EPI_ACCUM_F32, out=sep, a_mn=True, b_mn=True)
+        seps.append(sep)
+    ops.gemm_wgrad_group(probs)
+    for (dy, x, dw), ref, sep in zip(probs, refs, seps):
+        tol = 1e-5 * ref.abs() + 2e-3 * math.sqrt(tokens / 1024.0)
+        assert bool(((dw - ref).abs() <= tol).all()), float((dw - ref).abs().max())
+        assert bool(((dw - sep).abs() <= 1e-5 * sep.abs() + 1e-4).all()), float((dw - sep).abs().max())
+    # a group of one, and of two problems with ragged extents
+    dy = (torch.randn(300, 200, device="cuda", generator=g) * 0.1).bfloat16()
+    x = (torch.randn(300, 72, device="cuda", generator=g) * 0.5).bfloat16()
+    dw = torch.zeros(200, 72, device="cuda")
+    dw2 = torch.zeros(200, 72, device="cuda")
+    ops.gemm_wgrad_group([(dy, x, dw)])
+    ops.gemm_wgrad_group([(dy, x, dw2), (x, dy, torch.zeros(72, 200, device="cuda"))])
+    ref = dy.float().t() @ x.float()
+    assert bool(((dw - ref).abs() <= 1e-5 * ref.abs() + 1e-3).all()) and bool(((dw2 - ref).abs() <= 1e-5 * ref.abs() + 1e-3).all())
