@@ -539,6 +539,13 @@ def run_b200(args):
             line["train"] = tr
             line["gpu_launches"] += tr.get("gpu_launches", 0)
         line["clocks"] = sampler.stop(tw0, tw1, t_end) if ctx.rank == 0 else {}
+        ck, rf = line["clocks"], line.get("roofline")
+        if ctx.rank == 0 and rf and ck.get("sm_mhz") and ck.get("sm_max_mhz"):
+            # context, not the headline fraction: the pod's power cap holds the SM clock below its maximum for the whole step
+            # (the GEMMs draw the most), while the burst peak is a kernel timed alone
+            rf["frac_at_step_clock"] = round(rf["achieved"] / (rf["peak"] * ck["sm_mhz"] / ck["sm_max_mhz"]), 4)
+            rf["frac_at_step_clock_note"] = ("achieved / (peak x median SM clock of the timed region / max SM clock); assumes the "
+                                             "burst peak was taken at the maximum clock")
     if ctx.rank == 0:
         if ctx.world == 1 and not args.no_cpu and args.workload != "train":
             line["cpu_baseline"] = cpu_port_baseline(emb, tagger, n_sentences=2, warm=1)
