@@ -1,0 +1,36 @@
+"""Host-only entry points of the C ABI that can be exercised without a GPU: argument validation happens before any CUDA
+call, and the workspace size of the fused GEMM + LayerNorm kernel is plain arithmetic."""
+import ctypes
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import kbner_b200
+    from kbner_b200 import _lib
+    return _lib.load()
+
+
+def test_gemm_ln_workspace_bytes(lib):
+    # 16 control bytes + one 16-byte {mean, tag, M2, tag} slot per (256-row panel, 256-column tile, column half, row)
+    assert lib.kbner_gemm_ln_workspace_bytes(16384, 1024) == 16 + 64 * 4 * 2 * 256 * 16
+    assert lib.kbner_gemm_ln_workspace_bytes(300, 256) == 16 + 2 * 1 * 2 * 256 * 16
+    assert lib.kbner_gemm_ln_workspace_bytes(4096, 1000) == 0          # N must be a multiple of 256
+    assert lib.kbner_gemm_ln_workspace_bytes(0, 1024) == 0
+
+
+def test_wgrad_group_rejects_bad_arguments_before_touching_the_device(lib):
+    vp, ci = ctypes.c_void_p * 1, ctypes.c_int * 1
+    one = vp(16)
+    assert lib.kbner_gemm_wgrad_group(0, one, one, one, ci(8), ci(8), ci(8), ci(8), 64, None) != 0
+    assert b"1..4 problems" in lib.kbner_last_error()
+    assert lib.kbner_gemm_wgrad_group(5, one, one, one, ci(8), ci(8), ci(8), ci(8), 64, None) != 0
+    assert lib.kbner_gemm_wgrad_group(1, one, one, one, ci(8), ci(8), ci(8), ci(8), 0, None) != 0
+    assert lib.kbner_gemm_wgrad_group(1, one, one, one, ci(12), ci(8), ci(12), ci(8), 64, None) != 0   # extents: multiples of 8
+    assert b"multiples of 8" in lib.kbner_last_error()
+
+
+def test_fused_layernorm_rejects_unsupported_hidden_sizes(lib):
+    rc = lib.kbner_gemm_bias_resid_layernorm_ws(16, 16, None, None, 16, 16, 1e-5, 16, 128, 1000, 64, 64, 64, 16, 1 << 20, None)
+    assert rc != 0 and b"256, 512, 768, 1024" in lib.kbner_last_error()
