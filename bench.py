@@ -454,7 +454,21 @@ def parity_leg(ctx, tagger, emb, batch):
             tags, _ = tagger._decode_batch(feats)
         tags_np = tags.cpu().numpy()
         agree = float((tags_np[keep] == ref_tags[keep]).mean())
-        out["modes"][mode] = {"hidden_rel_l2": round(h_rel, 6), "logits_rel_l2": round(l_rel, 6), "logits_max_over_max": round(l_max, 6),
+        # what the mode costs: the same forward + Viterbi call, 5 steps after 2 warm ones (the second captures the mode's graph)
+        with torch.no_grad():
+            for _ in range(2):
+                batch.features = {}
+                tagger._decode_batch(tagger.forward(batch))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                batch.features = {}
+                tagger._decode_batch(tagger.forward(batch))
+            e1.record()
+            torch.cuda.synchronize()
+        sps = 5 * ids.shape[0] / (e0.elapsed_time(e1) / 1e3)
+        out["modes"][mode] = {"sentences_per_s": round(sps, 1),"hidden_rel_l2": round(h_rel, 6), "logits_rel_l2": round(l_rel, 6), "logits_max_over_max": round(l_max, 6),
                               "crf_loss_rel_err": round(abs(loss - ref_loss) / abs(ref_loss), 8), "crf_loss": round(loss, 4),
                               "viterbi_tag_agreement": round(agree, 6), "span_f1_vs_fp32_path": round(float(span_f1(tags_np)), 4)}
     emb.model.set_precision(before)
