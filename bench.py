@@ -222,7 +222,10 @@ def fresh_sentences(n, seed):
     import random
     from kbner_b200.data import Sentence
     if not _ZIPF:
-        _ZIPF["vocab"] = ["v%04x" % i for i in range(1 << 14)]
+        # FOUR characters: one piece of the stand-in tokenizer (piece_len 4), so that 510 words are 510 sub-tokens + <s> </s> =
+        # ONE 512-sub-token window per sentence, the headline's shape.  (Five-character words were two pieces each: every
+        # sentence became four overflow windows and the leg measured 128 x 512 rows per batch, 4x the headline's work.)
+        _ZIPF["vocab"] = ["%04x" % i for i in range(1 << 14)]
         _ZIPF["cum"] = list(itertools.accumulate(1.0 / (r + 1) for r in range(1 << 14)))
     rnd = random.Random(seed)
     return [Sentence(tokens=rnd.choices(_ZIPF["vocab"], cum_weights=_ZIPF["cum"], k=S_LEN - 2)) for _ in range(n)]
