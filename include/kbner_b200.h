@@ -258,6 +258,8 @@ int kbner_attention_fwd(const uint16_t *qkv /*[R*S,3H]*/, const int32_t *key_len
 /* Backward of kbner_attention_fwd (flash-style: P is recomputed per tile from Q, K and the saved LSE).
  * out / d_out: attention output and its gradient, [R*S, H] bf16; lse from the forward call ([R,heads,S]);
  * d_scratch [R,heads,S] fp32 and dq_acc [R*S, H] fp32 are workspaces; dqkv [R*S, 3H] bf16 receives dQ | dK | dV.
+ * dq_acc and dqkv are written through TMA (reduce-add of the per-key-block dQ partials, tile stores of dK / dV): both must
+ * be 16-byte aligned and contiguous.
  * What autograd derives from transformers' eager attention (flair/trainers/finetune_trainer.py:956-957). */
 int kbner_attention_bwd(const uint16_t *qkv, const uint16_t *out, const uint16_t *d_out, const float *lse,
                         const int32_t *key_len, int R, int S, int heads,
