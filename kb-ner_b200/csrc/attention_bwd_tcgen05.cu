@@ -117,10 +117,6 @@ __device__ unsigned long long g_attn_bwd_dbg[2 * 3 * 6 * 6];
 #define BWD_STAMP(role, blk, ev) do { } while (0)
 #endif
 
-__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // DROP: attention-probability dropout.  The forward multiplied P by mask / (1 - p) before P.V, so
 //   dV = (P * mask / (1-p))^T . dO,   dP = (dO . V^T) * mask / (1-p),   dS = P * (dP - D)   with D = rowsum(dO * O)
 // (D needs no change: O already is the dropped product).  The mask bits are regenerated from (window, head, query, key).
